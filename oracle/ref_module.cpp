@@ -1,0 +1,12 @@
+// TEST INFRASTRUCTURE ONLY -- not part of the product path.
+// Five-line pybind11 module stub that exposes the UNMODIFIED reference tokenizer
+// (compiled from /root/reference/src/{tokenize.cpp,omp.cpp} where they lie; see
+// oracle/Makefile) under the module name `ref_cbioseq`, so it can be imported next
+// to the product's own `cbioseq` extension.  Mirrors what src/bioseq.cpp:6-11 does
+// minus fxstats/poa (which need zlib/spoa and are not on the hot path).
+#include "bioseq.h"
+void init_omp_helpers(py::module &m);
+PYBIND11_MODULE(ref_cbioseq, m) {
+    init_tokenize(m);
+    init_omp_helpers(m);
+}
