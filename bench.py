@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""bench.py -- Gbases/s of the batch-tokenisation hot path on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A *step* is one pass of the hot path over one batch: BASELINE.json configs[1], PROTEIN
+`pbeos` batch_tokenize (BOS+EOS+PAD), 65536 ragged sequences of 50..1022 residues, padlen 1024,
+batch_first, 1-byte tokens -- per GPU (weak scaling: every rank owns its own shard of
+sequences; the path has no collective).  Units are input residues ("bases").
+
+  value     device-resident: packed residues + offsets already in HBM, one kernel launch per
+            step through the C ABI (bsq_tokenize), CUDA events on the launching stream.  The
+            batches rotate through ROT distinct input/output sets so every step reads and
+            writes memory that is not in L2 (ROT x 103 MB > 126 MB).
+  e2e       the same batch through the public Python API with HOST buffers
+            (Tokenizer.batch_tokenize_packed on pinned numpy-visible memory): pipelined
+            host->device copies + kernels + a device->host read of the last output row, per step.
+  roofline  HBM-bound: algorithmic bytes per launch (residues + offsets + output, DESIGN.md
+            section 4) / average launch duration, against MEASURED_PEAKS.json's copy bandwidth.
+  cpu_baseline  (rank 0, N=1) the reference's own OpenMP tokenizer (oracle/_ref, built from
+            /root/reference) on the same batch with all host threads; its output is also the
+            parity check of the timed GPU batch.
+
+--impl reference times only that CPU arm and prints the same JSON shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+NSEQ, LO, HI, PADLEN = 65536, 50, 1022, 1024
+KEY, FLAGS = "PROTEIN", dict(bos=True, eos=True, padchar=True)
+ROT = 4
+WORKLOAD = ("configs[1]: PROTEIN pbeos batch_tokenize (BOS+EOS+PAD), 65536 ragged seqs len 50-1022, "
+            "padlen 1024, batch_first, 1-byte tokens, per GPU")
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def make_batch(seed):
+    from bioseq_b200.synth import gen, AA20
+    return gen(seed, NSEQ, LO, HI, AA20)
+
+
+def algorithmic_bytes(nbases, nseq, padlen, itemsize=1, ncols=1):
+    """residues + offsets + every output byte once; no memset term."""
+    return nbases + 8 * (nseq + 1) + padlen * nseq * ncols * itemsize
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed regions run."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            out, _ = self.p.communicate(timeout=5)
+        except Exception:
+            self.p.kill()
+            out = ""
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        hi = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm     # samples under load
+        return {"sm_mhz": statistics.median(hi), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def cpu_arm(buf, offs, steps, warmup, budget_s=20.0):
+    """The reference's CPU implementation on the host cores (oracle/_ref), else the C port."""
+    from bioseq_b200.synth import as_list
+    from oracle.oracle import load_ref, OracleTokenizer
+    nbases = int(offs[-1])
+    R = load_ref()
+    cores = os.cpu_count() or 1
+    if R is not None:
+        tok = R.Tokenizer(KEY, **FLAGS)
+        seqs = as_list(buf, offs)
+        fn = lambda: tok.batch_tokenize(seqs, padlen=PADLEN, destchar="B", batch_first=True, nthreads=cores)  # noqa: E731
+        kind, used = "reference", cores
+        how = f"oracle/_ref (reference src/tokenize.cpp, g++ -O3 -march=x86-64-v3 -fopenmp), nthreads={cores}, list[bytes] input"
+    else:
+        tok = OracleTokenizer(KEY, **FLAGS)
+        fn = lambda: tok.batch_tokenize((buf, offs), padlen=PADLEN, destchar="B", batch_first=True)  # noqa: E731
+        kind, used = "port", 1
+        how = "oracle/bsq_oracle.c (scalar C port), 1 thread, packed input"
+    out = None
+    for _ in range(max(1, warmup)):
+        out = fn()
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        out = fn()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    total = sum(times)
+    return {"value": nbases * len(times) / total / 1e9, "unit": "Gbases/s", "cores": used, "kind": kind,
+            "sample": f"{len(times)} full passes over the {NSEQ}-sequence batch ({nbases} bases each); {how}",
+            "ms_per_step": 1e3 * total / len(times), "best_ms": 1e3 * min(times)}, out
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    buf, offs = make_batch(102)
+    res, _ = cpu_arm(buf, offs, args.steps, args.warmup, budget_s=120.0)
+    line = {"impl": "reference", "metric": "tokenize_throughput", "value": res["value"], "unit": "Gbases/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU arm: one host, all threads; not sharded over GPUs"},
+            "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": res["value"], "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import ctypes as C
+    from bioseq_b200 import capi
+    import bioseq_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = local
+    L = capi.lib()
+    tok = capi.tokenizer(KEY, **FLAGS)
+    ptok = bioseq_b200.Tokenizer(KEY, **FLAGS)
+
+    # ---- inputs: ROT distinct batches per rank, resident in HBM ---------------------------------
+    sets = []
+    for r in range(ROT):
+        buf, offs = make_batch(102 + 1000 * rank + r)
+        sets.append({"buf": buf, "offs": offs, "nbases": int(offs[-1]),
+                     "d_bytes": torch.from_numpy(buf).cuda(), "d_offs": torch.from_numpy(offs).cuda(),
+                     "out": torch.empty((NSEQ, PADLEN), dtype=torch.uint8, device="cuda")})
+    st = torch.cuda.current_stream().cuda_stream
+    for s in sets:
+        capi.check_lengths_device(dev, st, s["d_offs"], NSEQ, PADLEN, tok)
+    calls = [(dev, st, s["d_bytes"].data_ptr(), s["d_offs"].data_ptr(), NSEQ, PADLEN, C.byref(tok), 1, capi.I8,
+              s["out"].data_ptr()) for s in sets]
+
+    def step(i):
+        rc = L.bsq_tokenize(*calls[i % ROT])
+        if rc:
+            capi.check(rc)
+
+    sampler = ClockSampler(local)
+    # clocks ramp from idle: keep the GPU busy for a moment before anything is timed
+    t_end = time.perf_counter() + 0.5
+    i = 0
+    while time.perf_counter() < t_end:
+        step(i); i += 1
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident, exactly K steps ------------------------------------------------
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    L.bsq_launch_count_reset()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for i in range(args.steps):
+        step(i)
+    ev[1].record()
+    barrier()
+    launches = int(L.bsq_launch_count())
+    ms_total = ev[0].elapsed_time(ev[1])
+    bases_timed = sum(sets[i % ROT]["nbases"] for i in range(args.steps))
+    alg_bytes = sum(algorithmic_bytes(sets[i % ROT]["nbases"], NSEQ, PADLEN) for i in range(args.steps))
+
+    # ---- e2e: public Python API, pinned host buffers, H2D inside the timed region ----------------
+    pinned = [(torch.from_numpy(s["buf"]).pin_memory(), torch.from_numpy(s["offs"]).pin_memory()) for s in sets]
+    last = torch.empty(PADLEN, dtype=torch.uint8).pin_memory()
+
+    def e2e_step(i):
+        hb, ho = pinned[i % ROT]
+        out = ptok.batch_tokenize_packed(hb, ho, padlen=PADLEN, destchar="B", batch_first=True)
+        last.copy_(out[NSEQ - 1], non_blocking=True)
+        return out
+
+    e2e_steps = max(3, min(args.steps, 50))
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        out = e2e_step(i)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_ok = bool(torch.equal(out, sets[(e2e_steps - 1) % ROT]["out"]))
+    e2e_bases = sum(sets[i % ROT]["nbases"] for i in range(e2e_steps))
+    h2d = int(np.mean([s["nbases"] + 8 * (NSEQ + 1) for s in sets]))
+
+    # ---- reduce over ranks: max time ------------------------------------------------------------
+    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(bases_timed), float(e2e_bases), float(alg_bytes), float(launches)], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms_total_max, e2e_ms_max = t.tolist()
+    bases_all, e2e_bases_all, alg_all, launches_all = tot.tolist()
+
+    extra = {}
+    cpu = None
+    parity = None
+    if rank == 0:
+        extra = secondary_measurements(torch, capi, L, dev, st)
+        clocks = sampler.stop()
+        if world == 1:
+            cpu, ref_out = cpu_arm(sets[0]["buf"], sets[0]["offs"], steps=10, warmup=1, budget_s=20.0)
+            step(0)
+            torch.cuda.synchronize()
+            parity = bool(np.array_equal(np.ascontiguousarray(ref_out).view(np.uint8), sets[0]["out"].cpu().numpy()))
+            if not parity:
+                raise SystemExit("bench.py: GPU output differs from the CPU reference -- refusing to report a number")
+        peak, peak_src = measured_peak()
+        per_launch_ms = ms_total / launches if launches else float("nan")          # this rank's launches
+        achieved = (alg_bytes / max(launches, 1)) / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("tokenize_bf_kernel")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": "tokenize_throughput", "value": bases_all / (ms_total_max * 1e-3) / 1e9, "unit": "Gbases/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "seqs_per_gpu": NSEQ, "padlen": PADLEN,
+                       "bases_per_step_per_gpu": int(np.mean([s["nbases"] for s in sets])),
+                       "l2": f"inputs+outputs rotate through {ROT} distinct 103 MB sets (> 126 MB L2)",
+                       "parallelism": f"{world} ranks, sequences sharded by index, no collective"},
+            "e2e": {"value": e2e_bases_all / (e2e_ms_max * 1e-3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": PADLEN, "steps": e2e_steps, "api": "Tokenizer.batch_tokenize_packed(pinned host)",
+                    "matches_device_resident": e2e_ok},
+            "gpu_launches": int(launches_all),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "tokenize_bf_kernel<int8>",
+                         "algorithmic_bytes_per_launch": int(alg_bytes / max(launches, 1)),
+                         "launch_us": per_launch_ms * 1e3},
+            "cpu_baseline": cpu, "parity_vs_cpu_reference": parity, "clocks": clocks, "extra": extra,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def secondary_measurements(torch, capi, L, dev, st):
+    """Other BASELINE.json configs, device-resident, reported under "extra" (not the headline)."""
+    import ctypes as C
+    from bioseq_b200.synth import gen
+    peak, _ = measured_peak()
+    res = {}
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn(0)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(reps):
+            fn(i)
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    def report(name, ms, nbases, nbytes):
+        res[name] = {"Gbases/s": nbases / ms / 1e6, "GB/s": nbytes / ms / 1e6, "frac_of_measured_hbm": nbytes / ms / 1e6 / peak,
+                     "us_per_call": ms * 1e3}
+
+    # C1: DNA 4096 x 1000, padlen 1024, batch-first; 8.3 MB per call, so stream 64 distinct batches
+    tok = capi.tokenizer("DNA")
+    nb = 64
+    buf, offs = gen(101, 4096 * nb, 1000, 1000, b"ACGT")
+    d_b, d_o = torch.from_numpy(buf).cuda(), torch.from_numpy(offs).cuda()
+    out = torch.empty((4096 * nb, 1024), dtype=torch.uint8, device="cuda")
+    def c1(i):
+        j = i % nb
+        L.bsq_tokenize(dev, st, d_b.data_ptr(), d_o.data_ptr() + 8 * 4096 * j, 4096, 1024, C.byref(tok), 1, capi.I8,
+                       out.data_ptr() + 4096 * 1024 * j)
+    ms = timed(c1, 256)
+    report("c1_dna_4096x1000_bf_u8_streamed", ms, 4096 * 1000, 4096 * 1000 + 8 * 4097 + 4096 * 1024)
+    def c1big(i):
+        L.bsq_tokenize(dev, st, d_b.data_ptr(), d_o.data_ptr(), 4096 * nb, 1024, C.byref(tok), 1, capi.I8, out.data_ptr())
+    ms = timed(c1big, 10)
+    report("c1x64_dna_262144x1000_bf_u8_one_launch", ms, 4096 * nb * 1000, 4096 * nb * (1000 + 8 + 1024))
+    out_sf = torch.empty((1024, 4096 * nb), dtype=torch.uint8, device="cuda")
+    def c1sf(i):
+        L.bsq_tokenize(dev, st, d_b.data_ptr(), d_o.data_ptr(), 4096 * nb, 1024, C.byref(tok), 0, capi.I8, out_sf.data_ptr())
+    ms = timed(c1sf, 10)
+    report("c1x64_dna_seqfirst_u8_one_launch", ms, 4096 * nb * 1000, 4096 * nb * (1000 + 8 + 1024))
+    del out, out_sf, d_b, d_o
+
+    # C3: DNA one-hot float32 seq-first, 16384 x 4096 -> (4096, 16384, 4): 1.14 GB per call (> L2)
+    buf, offs = gen(103, 16384, 4096, 4096, b"ACGT")
+    d_b, d_o = torch.from_numpy(buf).cuda(), torch.from_numpy(offs).cuda()
+    out = torch.empty((4096, 16384, 4), dtype=torch.float32, device="cuda")
+    def c3(i):
+        L.bsq_onehot(dev, st, d_b.data_ptr(), d_o.data_ptr(), None, 16384, 4096, C.byref(tok), capi.F32, out.data_ptr())
+    ms = timed(c3, 10)
+    report("c3_dna_onehot_f32_16384x4096", ms, 16384 * 4096, 16384 * 4096 + 8 * 16385 + 4096 * 16384 * 16)
+    del out, d_b, d_o
+
+    # C2 variants: seq-first, unaligned padlen, protein one-hot u8, decode
+    from bioseq_b200.synth import AA20
+    ptk = capi.tokenizer(KEY, **FLAGS)
+    buf, offs = gen(102, NSEQ * 4, LO, HI, AA20)
+    nbases = int(offs[-1])
+    n4 = NSEQ * 4
+    d_b, d_o = torch.from_numpy(buf).cuda(), torch.from_numpy(offs).cuda()
+    for name, padlen, bf in (("c2x4_protein_bf_u8", 1024, 1), ("c2x4_protein_seqfirst_u8", 1024, 0), ("c2x4_protein_bf_u8_padlen1026", 1026, 1)):
+        out = torch.empty(n4 * padlen, dtype=torch.uint8, device="cuda")
+        def c2(i):
+            L.bsq_tokenize(dev, st, d_b.data_ptr(), d_o.data_ptr(), n4, padlen, C.byref(ptk), bf, capi.I8, out.data_ptr())
+        ms = timed(c2, 10)
+        report(name, ms, nbases, nbases + 8 * (n4 + 1) + n4 * padlen)
+    out32 = torch.empty(n4 * 1024, dtype=torch.int32, device="cuda")
+    def c2i(i):
+        L.bsq_tokenize(dev, st, d_b.data_ptr(), d_o.data_ptr(), n4, 1024, C.byref(ptk), 1, capi.I32, out32.data_ptr())
+    ms = timed(c2i, 10)
+    report("c2x4_protein_bf_i32", ms, nbases, nbases + 8 * (n4 + 1) + n4 * 1024 * 4)
+    del out32
+    oh = torch.empty((1024, NSEQ, 23), dtype=torch.uint8, device="cuda")
+    nb1 = int(offs[NSEQ])
+    def c2o(i):
+        L.bsq_onehot(dev, st, d_b.data_ptr(), d_o.data_ptr(), None, NSEQ, 1024, C.byref(ptk), capi.I8, oh.data_ptr())
+    ms = timed(c2o, 10)
+    report("c2_protein_onehot_u8_C23", ms, nb1, nb1 + 8 * (NSEQ + 1) + 1024 * NSEQ * 23)
+    del oh
+    # decode of the batch-first tokens (device part only: lengths+scan, then characters)
+    toks = out[:n4 * 1024].view(n4, 1024)
+    L.bsq_tokenize(dev, st, d_b.data_ptr(), d_o.data_ptr(), n4, 1024, C.byref(ptk), 1, capi.I8, toks.data_ptr())
+    d_ro = torch.empty(n4 + 1, dtype=torch.int64, device="cuda")
+    total = capi.decode_lengths(dev, st, toks, 1, n4, 1024, 1024, 1, ptk, d_ro)
+    d_ch = torch.empty(total, dtype=torch.uint8, device="cuda")
+    def dec(i):
+        tot = C.c_int64()
+        L.bsq_decode_lengths(dev, st, toks.data_ptr(), 1, n4, 1024, 1024, 1, C.byref(ptk), d_ro.data_ptr(), C.byref(tot))
+        L.bsq_decode_chars(dev, st, toks.data_ptr(), 1, n4, 1024, 1024, 1, C.byref(ptk), d_ro.data_ptr(), d_ch.data_ptr())
+    ms = timed(dec, 5)
+    res["c2x4_decode_tokens_device"] = {"Gtokens/s": n4 * 1024 / ms / 1e6, "GB/s": (2 * n4 * 1024 + total) / ms / 1e6,
+                                        "us_per_call": ms * 1e3, "chars": int(total)}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

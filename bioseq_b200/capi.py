@@ -1,0 +1,207 @@
+"""ctypes binding of the C ABI in include/bsq.h (libbsq.so).
+
+This is the same boundary the ``cbioseq`` extension sits on; bench.py and the GPU parity tests
+use it to drive the kernels with raw device pointers (torch supplies the memory and the stream).
+Every wrapper raises the exception type the reference would (ValueError for
+``std::invalid_argument``, RuntimeError otherwise) with libbsq's message.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbsq.so")
+
+OK, ERR_ARG, ERR_TOO_LONG, ERR_BAD_TOKEN, ERR_KEY, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
+I8, I16, I32, I64, F32, F64 = range(6)
+
+
+class TokenizerDesc(C.Structure):
+    """struct bsq_tokenizer"""
+    _fields_ = [("lut", C.c_int8 * 256), ("nchars", C.c_int32), ("bos_id", C.c_int32), ("eos_id", C.c_int32),
+                ("pad_id", C.c_int32), ("padchar", C.c_int32), ("alphabet_size", C.c_int32), ("key", C.c_char * 16)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libbsq.so (fails loudly: there is no fallback implementation)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is missing: build it with `python -m bioseq_b200.build`")
+    L = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    tokp = C.POINTER(TokenizerDesc)
+    sigs = {
+        "bsq_abi_version": (i32, []),
+        "bsq_last_error": (C.c_char_p, []),
+        "bsq_launch_count": (i64, []),
+        "bsq_launch_count_reset": (None, []),
+        "bsq_kind_of_destchar": (i32, [C.c_char]),
+        "bsq_kind_size": (C.c_size_t, [i32]),
+        "bsq_alphabet_count": (i32, []),
+        "bsq_alphabet_key": (C.c_char_p, [i32]),
+        "bsq_tokenizer_init": (i32, [tokp, C.c_char_p, i32, i32, i32]),
+        "bsq_tokenizer_lookup": (i32, [tokp, C.c_int32, C.c_char_p, C.c_size_t]),
+        "bsq_pack_create": (i32, [C.POINTER(vp), i32]),
+        "bsq_pack_destroy": (None, [vp]),
+        "bsq_pack_gather": (i32, [vp, C.POINTER(vp), C.POINTER(i64), i64, i32]),
+        "bsq_pack_bytes": (vp, [vp]),
+        "bsq_pack_offsets": (vp, [vp]),
+        "bsq_pack_nseq": (i64, [vp]),
+        "bsq_pack_nbytes": (i64, [vp]),
+        "bsq_pack_maxlen": (i64, [vp]),
+        "bsq_check_lengths_host": (i32, [vp, i64, i64, tokp]),
+        "bsq_check_lengths_device": (i32, [i32, vp, vp, i64, i64, tokp]),
+        "bsq_tokenize": (i32, [i32, vp, vp, vp, i64, i64, tokp, i32, i32, vp]),
+        "bsq_onehot": (i32, [i32, vp, vp, vp, vp, i64, i64, tokp, i32, vp]),
+        "bsq_decode_lengths": (i32, [i32, vp, vp, i32, i64, i64, i64, i64, tokp, vp, C.POINTER(i64)]),
+        "bsq_decode_chars": (i32, [i32, vp, vp, i32, i64, i64, i64, i64, tokp, vp, vp]),
+        "bsq_stager_create": (i32, [C.POINTER(vp), i32]),
+        "bsq_stager_destroy": (None, [vp]),
+        "bsq_stager_sync_copies": (i32, [vp]),
+        "bsq_tokenize_host": (i32, [vp, vp, vp, vp, i64, i64, tokp, i32, i32, vp]),
+        "bsq_onehot_host": (i32, [vp, vp, vp, vp, vp, i64, i64, tokp, i32, vp]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+EXPORTS = ("bsq_abi_version bsq_last_error bsq_launch_count bsq_launch_count_reset bsq_kind_of_destchar bsq_kind_size "
+           "bsq_alphabet_count bsq_alphabet_key bsq_tokenizer_init bsq_tokenizer_lookup bsq_pack_create bsq_pack_destroy "
+           "bsq_pack_gather bsq_pack_bytes bsq_pack_offsets bsq_pack_nseq bsq_pack_nbytes bsq_pack_maxlen "
+           "bsq_check_lengths_host bsq_check_lengths_device bsq_tokenize bsq_onehot bsq_decode_lengths bsq_decode_chars "
+           "bsq_stager_create bsq_stager_destroy bsq_stager_sync_copies bsq_tokenize_host bsq_onehot_host").split()
+
+
+def last_error():
+    return lib().bsq_last_error().decode("latin-1")
+
+
+def check(rc, onehot=False):
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc == ERR_ARG or (rc == ERR_TOO_LONG and onehot):
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def tokenizer(key, eos=False, bos=False, padchar=False):
+    t = TokenizerDesc()
+    check(lib().bsq_tokenizer_init(C.byref(t), key.encode(), int(eos), int(bos), int(padchar)))
+    return t
+
+
+def kind_of(destchar):
+    k = lib().bsq_kind_of_destchar(destchar[:1].encode("latin-1") if destchar else b"\0")
+    check(min(k, 0))
+    return k
+
+
+def _ptr(x):
+    """Raw address of a torch tensor / numpy array / int / None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+def tokenize(device, stream, d_bytes, d_offsets, nseq, padlen, tok, batch_first, kind, d_out):
+    check(lib().bsq_tokenize(device, stream, _ptr(d_bytes), _ptr(d_offsets), nseq, padlen, C.byref(tok),
+                             int(batch_first), kind, _ptr(d_out)))
+
+
+def onehot(device, stream, d_bytes, d_offsets, d_mask, nseq, padlen, tok, kind, d_out):
+    check(lib().bsq_onehot(device, stream, _ptr(d_bytes), _ptr(d_offsets), _ptr(d_mask), nseq, padlen, C.byref(tok),
+                           kind, _ptr(d_out)), onehot=True)
+
+
+def check_lengths_host(h_offsets, nseq, padlen, tok, onehot=False):
+    check(lib().bsq_check_lengths_host(_ptr(h_offsets), nseq, padlen, C.byref(tok)), onehot)
+
+
+def check_lengths_device(device, stream, d_offsets, nseq, padlen, tok, onehot=False):
+    check(lib().bsq_check_lengths_device(device, stream, _ptr(d_offsets), nseq, padlen, C.byref(tok)), onehot)
+
+
+def decode_lengths(device, stream, d_tokens, itemsize, rows, cols, row_stride, col_stride, tok, d_row_offsets):
+    total = C.c_int64()
+    check(lib().bsq_decode_lengths(device, stream, _ptr(d_tokens), itemsize, rows, cols, row_stride, col_stride,
+                                   C.byref(tok), _ptr(d_row_offsets), C.byref(total)))
+    return total.value
+
+
+def decode_chars(device, stream, d_tokens, itemsize, rows, cols, row_stride, col_stride, tok, d_row_offsets, d_chars):
+    check(lib().bsq_decode_chars(device, stream, _ptr(d_tokens), itemsize, rows, cols, row_stride, col_stride,
+                                 C.byref(tok), _ptr(d_row_offsets), _ptr(d_chars)))
+
+
+class Stager:
+    """bsq_stager: per-device copy stream + staging buffers for the host-staged entry points."""
+
+    def __init__(self, device):
+        self.h = C.c_void_p()
+        check(lib().bsq_stager_create(C.byref(self.h), device))
+
+    def tokenize_host(self, stream, h_bytes, h_offsets, nseq, padlen, tok, batch_first, kind, d_out):
+        check(lib().bsq_tokenize_host(self.h, stream, _ptr(h_bytes), _ptr(h_offsets), nseq, padlen, C.byref(tok),
+                                      int(batch_first), kind, _ptr(d_out)))
+
+    def onehot_host(self, stream, h_bytes, h_offsets, h_mask, nseq, padlen, tok, kind, d_out):
+        check(lib().bsq_onehot_host(self.h, stream, _ptr(h_bytes), _ptr(h_offsets), _ptr(h_mask), nseq, padlen,
+                                    C.byref(tok), kind, _ptr(d_out)), onehot=True)
+
+    def sync_copies(self):
+        check(lib().bsq_stager_sync_copies(self.h))
+
+    def close(self):
+        if self.h:
+            lib().bsq_stager_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class Pack:
+    """bsq_pack: gather ragged host sequences into (pinned) bytes + offsets."""
+
+    def __init__(self, pinned=True):
+        self.h = C.c_void_p()
+        check(lib().bsq_pack_create(C.byref(self.h), int(pinned)))
+
+    def gather(self, seqs, nthreads=1):
+        n = len(seqs)
+        bufs = [bytes(s) if not isinstance(s, bytes) else s for s in seqs]
+        ptrs = (C.c_void_p * n)(*[C.cast(C.c_char_p(b), C.c_void_p) for b in bufs])
+        lens = (C.c_int64 * n)(*[len(b) for b in bufs])
+        check(lib().bsq_pack_gather(self.h, ptrs, lens, n, nthreads))
+        return self
+
+    @property
+    def nseq(self): return lib().bsq_pack_nseq(self.h)
+    @property
+    def nbytes(self): return lib().bsq_pack_nbytes(self.h)
+    @property
+    def maxlen(self): return lib().bsq_pack_maxlen(self.h)
+    @property
+    def bytes_ptr(self): return lib().bsq_pack_bytes(self.h)
+    @property
+    def offsets_ptr(self): return lib().bsq_pack_offsets(self.h)
+
+    def to_numpy(self):
+        import numpy as np
+        b = np.ctypeslib.as_array(C.cast(self.bytes_ptr, C.POINTER(C.c_uint8)), shape=(max(self.nbytes, 1),))[:self.nbytes]
+        o = np.ctypeslib.as_array(C.cast(self.offsets_ptr, C.POINTER(C.c_int64)), shape=(self.nseq + 1,))
+        return b.copy(), o.copy()
+
+    def close(self):
+        if self.h:
+            lib().bsq_pack_destroy(self.h)
+            self.h = C.c_void_p()

@@ -1,0 +1,34 @@
+// Internal helpers shared by the translation units of libbsq.so (not installed).
+#pragma once
+#include <cstdint>
+#include <string>
+
+#include "../../include/bsq.h"
+
+namespace bsq {
+
+// Records `msg` as the calling thread's last error and returns `code`.
+int fail(int code, const std::string &msg);
+// Kernel-launch bookkeeping for bsq_launch_count().
+void count_launch(int n = 1);
+
+
+#ifdef __CUDACC__
+// Launchers shared by the device entry points and the host-staged pipeline.  `nseq`
+// sequences starting at d_offs[0] are processed; `ld` is the batch extent of the whole
+// output array and d_out points at this range's first row (batch-first) / column.
+int launch_tokenize(cudaStream_t st, const uint8_t *d_bytes, const int64_t *d_offs, int64_t nseq, int64_t ld,
+                    int64_t padlen, const bsq_tokenizer &tok, int batch_first, int kind, void *d_out);
+int launch_onehot(cudaStream_t st, const uint8_t *d_bytes, const int64_t *d_offs, const uint8_t *d_mask, int64_t nseq,
+                  int64_t ld, int64_t padlen, const bsq_tokenizer &tok, int kind, void *d_out);
+int check_launch_args(int device, int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int kind, const void *d_out);
+#endif
+
+}  // namespace bsq
+
+#define BSQ_CUDA_TRY(expr)                                                                       \
+    do {                                                                                         \
+        cudaError_t err__ = (expr);                                                              \
+        if (err__ != cudaSuccess)                                                                \
+            return bsq::fail(BSQ_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(err__)); \
+    } while (0)

@@ -1,0 +1,646 @@
+// sm_100a kernels + launchers for batch_tokenize / batch_onehot_encode / decode_tokens.
+//
+//   K1 tokenize_bf_kernel   (nseq, padlen) batch-first tokens.  One thread = 16 output bytes
+//                           = one st.global.v4; BOS/EOS/PAD fused; ragged tails skip all loads.
+//   K2 seqfirst_kernel<..,false>  (padlen, nseq) tokens: 128 seq x 128 pos shared-memory tile,
+//                           coalesced reads along each sequence, coalesced stores along batch.
+//   K3 seqfirst_kernel<..,true>   (padlen, nseq, C) one-hot: same tile, then every warp streams
+//                           the contiguous C*sizeof(T)-expanded run of one position with
+//                           16-byte stores, zeros included (no memset pass).
+//   K4 decode_*             tokens -> characters (two passes: lengths+validation, chars).
+//   K0 maxlen_kernel        length validation for device-resident offsets.
+//
+// Reference semantics: src/tokenize.h:381-485 (K1/K2), :283-371 (K3), :131-179 (K4).
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+
+#include "bsq_internal.h"
+#include "bsq_kernels.cuh"
+
+namespace bsq {
+
+constexpr int kThreads = 256;
+constexpr int kTileSeqs = 128;
+constexpr int kTilePos = 128;
+constexpr int kTilePitch = kTilePos + 4;  // 33 words: conflict-free column reads
+
+template <typename T>
+__device__ __forceinline__ T cast_id(int32_t v) {
+    return static_cast<T>(v);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: batch-first tokens.  The output is treated as a flat array of nseq*padlen elements;
+// thread g owns elements [g*TPT, (g+1)*TPT) = 16 bytes.  When that range stays inside one
+// row and T is one byte the vector path (tokens16) is used, otherwise a per-element loop
+// that may cross into the next row (only when padlen*sizeof(T) is not a multiple of 16).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+tokenize_bf_kernel(SeqView v, int64_t nseq, int padlen, FastDiv div_padlen, LutParam lutp, Specials sp,
+                   Expand ex, T *__restrict__ out) {
+    constexpr int TPT = 16 / sizeof(T);
+    __shared__ __align__(16) uint8_t lut[256];
+    __shared__ int64_t s_row0;
+    __shared__ uint32_t s_col0;
+    load_lut(lut, lutp);
+    if (threadIdx.x == 0) {
+        const int64_t f0 = static_cast<int64_t>(blockIdx.x) * (kThreads * TPT);
+        const int64_t r0 = f0 / padlen;
+        s_row0 = r0;
+        s_col0 = static_cast<uint32_t>(f0 - r0 * padlen);
+    }
+    __syncthreads();
+    const uint32_t x = s_col0 + threadIdx.x * TPT;  // < padlen + 4096
+    const uint32_t dr = fd_div(x, div_padlen);
+    int64_t row = s_row0 + dr;
+    int c = static_cast<int>(x - dr * static_cast<uint32_t>(padlen));
+    const int64_t total = nseq * static_cast<int64_t>(padlen);
+    const int64_t f = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * TPT;
+    if (f >= total) return;
+
+    int64_t start = __ldg(v.offs + row);
+    int len = static_cast<int>(__ldg(v.offs + row + 1) - start);
+
+    if (sizeof(T) == 1 && c + 16 <= padlen) {
+        uint4 codes;
+        if (c >= sp.bos + len + sp.eos) {
+            codes = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
+        } else {
+            codes = tokens16(v, start, len, c, sp, lut);
+        }
+        __stcs(reinterpret_cast<uint4 *>(out + f), codes);
+        return;
+    }
+
+    T vals[TPT];
+    int nvalid = TPT;
+#pragma unroll
+    for (int j = 0; j < TPT; ++j) {
+        if (c >= padlen) {  // crossed into the next row
+            c = 0;
+            ++row;
+            if (row < nseq) {
+                start = __ldg(v.offs + row);
+                len = static_cast<int>(__ldg(v.offs + row + 1) - start);
+            } else if (nvalid == TPT) {
+                nvalid = j;
+            }
+        }
+        const uint32_t code = row < nseq ? token_at(v, start, len, c, sp, lut) : 0u;
+        vals[j] = sizeof(T) == 1 ? static_cast<T>(code) : cast_id<T>(expand_code(code, ex));
+        ++c;
+    }
+    if (nvalid == TPT) {
+        __stcs(reinterpret_cast<uint4 *>(out + f), *reinterpret_cast<const uint4 *>(vals));
+    } else {
+#pragma unroll
+        for (int j = 0; j < TPT; ++j)
+            if (j < nvalid) out[f + j] = vals[j];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2 / K3: sequence-first layouts through a shared-memory tile of byte codes.
+//   phase 1: tile[seq][pos] <- tokens16 (lanes run along the positions of a sequence, so the
+//            residue reads are coalesced); 4-byte shared stores, row pitch 33 words.
+//   phase 2: lanes run along the batch (tokens) or along the expanded C*sizeof(T) run
+//            (one-hot), so global stores are coalesced / 16-byte vectorised.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+struct OneVal;  // bit pattern of T(1) as two 32-bit halves
+template <> struct OneVal<int8_t> { static constexpr uint32_t lo = 1u, hi = 0u; };
+template <> struct OneVal<int16_t> { static constexpr uint32_t lo = 1u, hi = 0u; };
+template <> struct OneVal<int32_t> { static constexpr uint32_t lo = 1u, hi = 0u; };
+template <> struct OneVal<int64_t> { static constexpr uint32_t lo = 1u, hi = 0u; };
+template <> struct OneVal<float> { static constexpr uint32_t lo = 0x3f800000u, hi = 0u; };
+template <> struct OneVal<double> { static constexpr uint32_t lo = 0u, hi = 0x3ff00000u; };
+
+// Set element `e` (0 <= e < 16/sizeof(T)) of a 16-byte vector held in w[4] to T(1).
+template <typename T>
+__device__ __forceinline__ void set_one(uint32_t w[4], int e) {
+    if (sizeof(T) == 8) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k)
+            if (e == k) { w[2 * k] = OneVal<T>::lo; w[2 * k + 1] = OneVal<T>::hi; }
+    } else {
+        const int byte = e * static_cast<int>(sizeof(T));
+        const uint32_t pat = OneVal<T>::lo << (8 * (byte & 3));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if ((byte >> 2) == k) w[k] |= pat;
+    }
+}
+
+template <typename T, bool ONEHOT>
+__global__ void __launch_bounds__(kThreads)
+seqfirst_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, LutParam lutp, Specials sp, Expand ex, int ncols,
+                FastDiv div_ncols, int vec_ok, T *__restrict__ out) {
+    // nseq sequences are processed; ld (>= nseq) is the batch extent of the output array, so a
+    // sub-range of a larger batch can be written in place (out already points at its first column).
+    __shared__ __align__(16) uint8_t lut[256];
+    __shared__ __align__(16) uint8_t tile[kTileSeqs * kTilePitch];
+    load_lut(lut, lutp);
+    __syncthreads();
+    const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kTileSeqs;
+    const int p0 = blockIdx.y * kTilePos;
+    const int nseq_tile = static_cast<int>(min(static_cast<int64_t>(kTileSeqs), nseq - i0));
+    const int npos_tile = min(kTilePos, padlen - p0);
+
+    // ---- phase 1 ----
+#pragma unroll
+    for (int u = 0; u < (kTileSeqs * kTilePos / 16) / kThreads; ++u) {
+        const int ch = threadIdx.x + u * kThreads;
+        const int q = ch & 7, il = ch >> 3;
+        const int c0 = p0 + 16 * q;
+        if (il < nseq_tile && c0 < padlen) {
+            const int64_t start = __ldg(v.offs + i0 + il);
+            const int len = static_cast<int>(__ldg(v.offs + i0 + il + 1) - start);
+            uint4 codes;
+            if (c0 >= sp.bos + len + sp.eos) codes = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
+            else codes = tokens16(v, start, len, c0, sp, lut);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(tile + il * kTilePitch + 16 * q);
+            dst[0] = codes.x; dst[1] = codes.y; dst[2] = codes.z; dst[3] = codes.w;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2 ----
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (!ONEHOT) {
+        for (int pp = warp; pp < npos_tile; pp += kThreads / 32) {
+            T *orow = out + (static_cast<int64_t>(p0 + pp) * ld + i0);
+#pragma unroll
+            for (int m = 0; m < kTileSeqs / 32; ++m) {
+                const int il = lane + 32 * m;
+                if (il < nseq_tile) {
+                    const uint32_t code = tile[il * kTilePitch + pp];
+                    __stcs(orow + il, cast_id<T>(expand_code(code, ex)));
+                }
+            }
+        }
+    } else {
+        constexpr int EPV = 16 / sizeof(T);  // elements per 16-byte vector
+        const int run_elems = nseq_tile * ncols;
+        for (int pp = warp; pp < npos_tile; pp += kThreads / 32) {
+            T *orow = out + (static_cast<int64_t>(p0 + pp) * ld + i0) * ncols;
+            if (vec_ok) {
+                const int nvec = run_elems / EPV;  // exact: the host checked divisibility
+                for (int vec = lane; vec < nvec; vec += 32) {
+                    const int e0 = vec * EPV;
+                    int il = static_cast<int>(fd_div(static_cast<uint32_t>(e0), div_ncols));
+                    int base = il * ncols - e0;  // vector-relative element index of column 0 of seq il
+                    uint32_t w[4] = {0u, 0u, 0u, 0u};
+                    while (base < EPV) {
+                        const int col = expand_code(tile[il * kTilePitch + pp], ex);
+                        const int e = base + col;
+                        if (col >= 0 && e >= 0 && e < EPV) set_one<T>(w, e);
+                        base += ncols;
+                        ++il;
+                    }
+                    __stcs(reinterpret_cast<uint4 *>(orow) + vec, make_uint4(w[0], w[1], w[2], w[3]));
+                }
+            } else {
+                for (int e = lane; e < run_elems; e += 32) {
+                    const int il = static_cast<int>(fd_div(static_cast<uint32_t>(e), div_ncols));
+                    const int col = e - il * ncols;
+                    const int hot = expand_code(tile[il * kTilePitch + pp], ex);
+                    orow[e] = hot == col ? cast_id<T>(1) : cast_id<T>(0);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K0: longest sequence of a device-resident offsets array.
+// ------------------------------------------------------------------------------------------
+__global__ void maxlen_kernel(const int64_t *__restrict__ offs, int64_t nseq, unsigned long long *out) {
+    long long best = 0;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nseq;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        best = max(best, static_cast<long long>(offs[i + 1] - offs[i]));
+    }
+    for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(out, static_cast<unsigned long long>(best));
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: decode.  inv[key + 128] for key in [-128, 384): 0..255 = character, 0x100 + k = the
+// 5-character special k (0 <BOS>, 1 <EOS>, 2 <PAD>), 0xFFFF = no entry.
+// ------------------------------------------------------------------------------------------
+struct InvParam {
+    uint16_t e[512];
+};
+constexpr uint16_t kInvNone = 0xFFFF;
+
+__device__ __forceinline__ int32_t load_key(const uint8_t *p, int itemsize) {
+    switch (itemsize) {  // src/tokenize.h:107-124 + the uint32 truncation at :145/:167
+        case 1: return static_cast<int32_t>(*p);
+        case 2: return static_cast<int32_t>(*reinterpret_cast<const uint16_t *>(p));
+        case 4: return *reinterpret_cast<const int32_t *>(p);
+        default: return static_cast<int32_t>(*reinterpret_cast<const uint64_t *>(p));
+    }
+}
+
+__device__ __forceinline__ uint32_t inv_lookup(const uint16_t *inv, int32_t key) {
+    return (key >= -128 && key < 384) ? inv[key + 128] : kInvNone;
+}
+
+// pass 1: one CTA per row.  row_len[r] = decoded length; first_bad = min flat index of a
+// token without an entry.
+__global__ void __launch_bounds__(128)
+decode_len_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t cols, int64_t row_stride,
+                  int64_t col_stride, InvParam invp, int64_t *__restrict__ row_len,
+                  unsigned long long *first_bad) {
+    __shared__ uint16_t inv[512];
+    __shared__ int s_cnt[4];
+    for (int i = threadIdx.x; i < 512; i += 128) inv[i] = invp.e[i];
+    __syncthreads();
+    const int64_t r = blockIdx.x;
+    const uint8_t *rp = tokens + r * row_stride;
+    int specials = 0;
+    unsigned long long bad = ~0ull;
+    for (int64_t c = threadIdx.x; c < cols; c += 128) {
+        const uint32_t e = inv_lookup(inv, load_key(rp + c * col_stride, itemsize));
+        if (e == kInvNone) bad = min(bad, static_cast<unsigned long long>(r * cols + c));
+        else specials += (e >> 8) & 1;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        specials += __shfl_xor_sync(0xffffffffu, specials, o);
+        bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_cnt[threadIdx.x >> 5] = specials;
+        if (bad != ~0ull) atomicMin(first_bad, bad);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) row_len[r] = cols + 4ll * (s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3]);
+}
+
+// exclusive scan of row_len (three small kernels; rows can be millions)
+constexpr int kScanBlock = 1024;
+__device__ __forceinline__ int64_t block_exclusive_scan(int64_t x, int64_t *s_warp, int64_t *total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t incl = x;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t wv = lane < (blockDim.x >> 5) ? s_warp[lane] : 0;
+        int64_t wi = wv;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t y = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += y;
+        }
+        s_warp[lane] = wi - wv;  // exclusive prefix of the warp totals
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    return s_warp[warp] + incl - x;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+scan_local_kernel(int64_t *__restrict__ data, int64_t n, int64_t *__restrict__ block_tot) {
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_total;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x;
+    const int64_t x = i < n ? data[i] : 0;
+    const int64_t ex = block_exclusive_scan(x, s_warp, &s_total);
+    if (i < n) data[i] = ex;
+    if (threadIdx.x == 0) block_tot[blockIdx.x] = s_total;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+scan_totals_kernel(int64_t *__restrict__ block_tot, int64_t nblocks, int64_t *__restrict__ grand_total) {
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_total;
+    int64_t carry = 0;
+    for (int64_t base = 0; base < nblocks; base += kScanBlock) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t x = i < nblocks ? block_tot[i] : 0;
+        const int64_t ex = block_exclusive_scan(x, s_warp, &s_total);
+        if (i < nblocks) block_tot[i] = carry + ex;
+        carry += s_total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *grand_total = carry;
+}
+
+__global__ void __launch_bounds__(kScanBlock)
+scan_add_kernel(int64_t *__restrict__ data, int64_t n, const int64_t *__restrict__ block_pre,
+                const int64_t *__restrict__ grand_total) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x;
+    if (i < n) data[i] += block_pre[blockIdx.x];
+    if (i == 0) data[n] = *grand_total;
+}
+
+// pass 2: one CTA per row; threads take 8 consecutive tokens, a CTA-wide scan of the
+// decoded lengths gives every thread its write position.
+constexpr int kDecTok = 8;
+__global__ void __launch_bounds__(128)
+decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t cols, int64_t row_stride,
+                    int64_t col_stride, InvParam invp, const int64_t *__restrict__ row_offs,
+                    uint8_t *__restrict__ chars) {
+    __shared__ uint16_t inv[512];
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_total;
+    for (int i = threadIdx.x; i < 512; i += 128) inv[i] = invp.e[i];
+    if (threadIdx.x < 32) s_warp[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t r = blockIdx.x;
+    const uint8_t *rp = tokens + r * row_stride;
+    uint8_t *dst = chars + row_offs[r];
+    for (int64_t seg = 0; seg < cols; seg += 128 * kDecTok) {
+        uint32_t e[kDecTok];
+        int mylen = 0;
+#pragma unroll
+        for (int j = 0; j < kDecTok; ++j) {
+            const int64_t c = seg + static_cast<int64_t>(threadIdx.x) * kDecTok + j;
+            e[j] = c < cols ? inv_lookup(inv, load_key(rp + c * col_stride, itemsize)) : kInvNone;
+            mylen += e[j] == kInvNone ? 0 : ((e[j] & 0x100u) ? 5 : 1);
+        }
+        // 128 threads = 4 warps; block_exclusive_scan is written for any warp count <= 32
+        int64_t pos = block_exclusive_scan(mylen, s_warp, &s_total);
+#pragma unroll
+        for (int j = 0; j < kDecTok; ++j) {
+            if (e[j] == kInvNone) continue;
+            if (e[j] & 0x100u) {
+                const uint32_t k = e[j] & 3u;  // <BOS> <EOS> <PAD>
+                dst[pos] = '<';
+                dst[pos + 1] = k == 0 ? 'B' : (k == 1 ? 'E' : 'P');
+                dst[pos + 2] = k == 2 ? 'A' : 'O';
+                dst[pos + 3] = k == 2 ? 'D' : 'S';
+                dst[pos + 4] = '>';
+                pos += 5;
+            } else {
+                dst[pos++] = static_cast<uint8_t>(e[j]);
+            }
+        }
+        dst += s_total;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side launch helpers
+// ------------------------------------------------------------------------------------------
+namespace {
+
+inline uint32_t rep4(uint32_t b) { return (b & 0xffu) * 0x01010101u; }
+
+struct Prepared {
+    LutParam lut;
+    Specials sp;
+    Expand ex;
+};
+
+// mode 0: batch-first one-byte tokens (codes are the output bytes: ids wrap to 8 bits like
+//         the reference's int -> int8 store);
+// mode 1: tokens through Expand (wide element types / tile kernels);
+// mode 2: one-hot columns through Expand.
+Prepared prepare(const bsq_tokenizer &tok, int mode) {
+    Prepared p;
+    uint8_t codes[256];
+    const bool onehot = mode == 2;
+    for (int b = 0; b < 256; ++b) {
+        const int id = b < 0x80 ? tok.lut[b] : -1;  // bytes >= 0x80: undefined in the reference, invalid here
+        codes[b] = id >= 0 ? static_cast<uint8_t>(id) : (onehot ? kCodeInvalid : 0);
+    }
+    std::memcpy(p.lut.w, codes, 256);
+    p.sp.bos = tok.bos_id >= 0;
+    p.sp.eos = tok.eos_id >= 0;
+    const bool fits = tok.pad_id < 0x80;  // every special id is a valid direct code
+    uint32_t bos_c, eos_c, pad_c;
+    if (mode == 0) {
+        bos_c = static_cast<uint32_t>(tok.bos_id);
+        eos_c = static_cast<uint32_t>(tok.eos_id);
+        pad_c = tok.padchar ? static_cast<uint32_t>(tok.pad_id) : 0u;
+    } else {
+        bos_c = fits ? static_cast<uint32_t>(tok.bos_id) : kCodeBos;
+        eos_c = fits ? static_cast<uint32_t>(tok.eos_id) : kCodeEos;
+        if (tok.padchar) pad_c = fits ? static_cast<uint32_t>(tok.pad_id) : kCodePad;
+        else pad_c = onehot ? kCodeInvalid : 0u;
+    }
+    p.sp.bos_w = rep4(bos_c);
+    p.sp.eos_w = rep4(eos_c);
+    p.sp.pad_w = rep4(pad_c);
+    p.ex.map[0] = tok.padchar ? tok.pad_id : (onehot ? -1 : 0);
+    p.ex.map[1] = tok.eos_id;
+    p.ex.map[2] = tok.bos_id;
+    p.ex.map[3] = onehot ? -1 : 0;
+    return p;
+}
+
+int check_common(int device, int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int kind, const void *d_out) {
+    if (tok == nullptr) return fail(BSQ_ERR_ARG, "null tokenizer");
+    if (padlen <= 0) return fail(BSQ_ERR_ARG, "batch tokenize requires padlen is provded.");  // src/tokenize.h:383
+    if (padlen > (1ll << 30)) return fail(BSQ_ERR_ARG, "padlen above 2^30 is not supported");
+    if (nseq < 0) return fail(BSQ_ERR_ARG, "negative batch size");
+    if (bsq_kind_size(kind) == 0) return fail(BSQ_ERR_ARG, "invalid element kind");
+    if (nseq > 0 && (d_out == nullptr || (reinterpret_cast<uintptr_t>(d_out) & 15u)))
+        return fail(BSQ_ERR_ARG, "output pointer must be non-null and 16-byte aligned");
+    BSQ_CUDA_TRY(cudaSetDevice(device));
+    return BSQ_OK;
+}
+
+template <typename T>
+int launch_bf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t /*ld*/, int64_t padlen, const bsq_tokenizer &tok, void *d_out) {
+    constexpr int TPT = 16 / sizeof(T);
+    const Prepared p = prepare(tok, sizeof(T) == 1 ? 0 : 1);
+    const int64_t total = nseq * padlen;
+    const int64_t per_block = static_cast<int64_t>(kThreads) * TPT;
+    const int64_t blocks = (total + per_block - 1) / per_block;
+    if (blocks > 0x7fffffffll) return fail(BSQ_ERR_ARG, "batch too large for one launch");
+    tokenize_bf_kernel<T><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(
+        v, nseq, static_cast<int>(padlen), make_fastdiv(static_cast<uint32_t>(padlen)), p.lut, p.sp, p.ex,
+        static_cast<T *>(d_out));
+    count_launch();
+    BSQ_CUDA_TRY(cudaGetLastError());
+    return BSQ_OK;
+}
+
+template <typename T, bool ONEHOT>
+int launch_sf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t ld, int64_t padlen, const bsq_tokenizer &tok, void *d_out) {
+    const Prepared p = prepare(tok, ONEHOT ? 2 : 1);
+    const int64_t gx = (nseq + kTileSeqs - 1) / kTileSeqs, gy = (padlen + kTilePos - 1) / kTilePos;
+    if (gx > 0x7fffffffll || gy > 65535) return fail(BSQ_ERR_ARG, "batch too large for one launch");
+    const int ncols = ONEHOT ? tok.alphabet_size : 1;
+    // 16-byte stores need every row of the (padlen, ld, ncols) array and this launch's first
+    // column to start on a 16-byte boundary
+    const int vec_ok = ((ld * ncols * static_cast<int64_t>(sizeof(T))) % 16) == 0 &&
+                       (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0 &&
+                       ((nseq * ncols * static_cast<int64_t>(sizeof(T))) % 16) == 0;
+    seqfirst_kernel<T, ONEHOT><<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(gy)), kThreads, 0, st>>>(
+        v, nseq, ld, static_cast<int>(padlen), p.lut, p.sp, p.ex, ncols, make_fastdiv(static_cast<uint32_t>(ncols)),
+        vec_ok, static_cast<T *>(d_out));
+    count_launch();
+    BSQ_CUDA_TRY(cudaGetLastError());
+    return BSQ_OK;
+}
+
+InvParam make_inv(const bsq_tokenizer &tok) {
+    InvParam inv;
+    for (int i = 0; i < 512; ++i) inv.e[i] = kInvNone;
+    for (int b = 255; b >= 0; --b) inv.e[static_cast<int>(tok.lut[b]) + 128] = static_cast<uint16_t>(b);  // lowest byte wins
+    if (tok.bos_id >= 0) inv.e[tok.bos_id + 128] = 0x100;
+    if (tok.eos_id >= 0) inv.e[tok.eos_id + 128] = 0x101;
+    if (tok.padchar) inv.e[tok.pad_id + 128] = 0x102;
+    // Negative ids of the BYTES alphabet would decode to single bytes >= 0x80, which the
+    // reference then fails to turn into a Python str (invalid UTF-8); treated as invalid.
+    if (tok.nchars == 256)
+        for (int i = 0; i < 128; ++i) inv.e[i] = kInvNone;
+    return inv;
+}
+
+}  // namespace
+
+#define BSQ_DISPATCH(FN, ...)                                                               \
+    switch (kind) {                                                                         \
+        case BSQ_I8: return FN<int8_t __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out);    \
+        case BSQ_I16: return FN<int16_t __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out);  \
+        case BSQ_I32: return FN<int32_t __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out);  \
+        case BSQ_I64: return FN<int64_t __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out);  \
+        case BSQ_F32: return FN<float __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out);    \
+        default: return FN<double __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out);        \
+    }
+#define BSQ_COMMA_FALSE , false
+#define BSQ_COMMA_TRUE , true
+
+int launch_tokenize(cudaStream_t st, const uint8_t *d_bytes, const int64_t *d_offs, int64_t nseq, int64_t ld,
+                    int64_t padlen, const bsq_tokenizer &tok, int batch_first, int kind, void *d_out) {
+    if (nseq <= 0) return BSQ_OK;
+    const SeqView v{d_bytes, d_offs, nullptr};
+    if (batch_first) {
+        BSQ_DISPATCH(launch_bf)
+    } else {
+        BSQ_DISPATCH(launch_sf, BSQ_COMMA_FALSE)
+    }
+}
+
+int launch_onehot(cudaStream_t st, const uint8_t *d_bytes, const int64_t *d_offs, const uint8_t *d_mask, int64_t nseq,
+                  int64_t ld, int64_t padlen, const bsq_tokenizer &tok, int kind, void *d_out) {
+    if (nseq <= 0) return BSQ_OK;
+    if (static_cast<int64_t>(kTileSeqs) * tok.alphabet_size > 0x7fffffffll) return fail(BSQ_ERR_ARG, "alphabet too large");
+    const SeqView v{d_bytes, d_offs, d_mask};
+    BSQ_DISPATCH(launch_sf, BSQ_COMMA_TRUE)
+}
+
+int check_launch_args(int device, int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int kind, const void *d_out) {
+    return check_common(device, nseq, padlen, tok, kind, d_out);
+}
+
+}  // namespace bsq
+
+using namespace bsq;
+
+extern "C" {
+
+int bsq_tokenize(int device, void *stream, const uint8_t *d_bytes, const int64_t *d_offsets, int64_t nseq,
+                 int64_t padlen, const bsq_tokenizer *tok, int batch_first, int kind, void *d_out) {
+    if (int rc = check_common(device, nseq, padlen, tok, kind, d_out)) return rc;
+    if (nseq == 0) return BSQ_OK;
+    if (d_offsets == nullptr) return fail(BSQ_ERR_ARG, "null offsets");
+    return launch_tokenize(static_cast<cudaStream_t>(stream), d_bytes, d_offsets, nseq, nseq, padlen, *tok, batch_first,
+                           kind, d_out);
+}
+
+int bsq_onehot(int device, void *stream, const uint8_t *d_bytes, const int64_t *d_offsets, const uint8_t *d_mask,
+               int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out) {
+    if (int rc = check_common(device, nseq, padlen, tok, kind, d_out)) return rc;
+    if (nseq == 0) return BSQ_OK;
+    if (d_offsets == nullptr) return fail(BSQ_ERR_ARG, "null offsets");
+    return launch_onehot(static_cast<cudaStream_t>(stream), d_bytes, d_offsets, d_mask, nseq, nseq, padlen, *tok, kind,
+                         d_out);
+}
+
+int bsq_check_lengths_device(int device, void *stream, const int64_t *d_offsets, int64_t nseq, int64_t padlen,
+                             const bsq_tokenizer *tok) {
+    if (tok == nullptr) return fail(BSQ_ERR_ARG, "null tokenizer");
+    if (padlen <= 0) return fail(BSQ_ERR_ARG, "batch tokenize requires padlen is provded.");
+    if (nseq <= 0) return BSQ_OK;
+    BSQ_CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned long long *d_max = nullptr;
+    BSQ_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_max), sizeof(*d_max), st));
+    BSQ_CUDA_TRY(cudaMemsetAsync(d_max, 0, sizeof(*d_max), st));
+    const int blocks = static_cast<int>(std::min<int64_t>((nseq + 255) / 256, 148 * 8));
+    maxlen_kernel<<<blocks, 256, 0, st>>>(d_offsets, nseq, d_max);
+    count_launch();
+    unsigned long long h_max = 0;
+    BSQ_CUDA_TRY(cudaMemcpyAsync(&h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, st));
+    BSQ_CUDA_TRY(cudaFreeAsync(d_max, st));
+    BSQ_CUDA_TRY(cudaStreamSynchronize(st));
+    const int64_t tl = static_cast<int64_t>(h_max) + (tok->bos_id >= 0) + (tok->eos_id >= 0);
+    if (tl > padlen)
+        return fail(BSQ_ERR_TOO_LONG, "seq len + bos + eos > padlen: " + std::to_string(tl) + ", vs padlen " + std::to_string(padlen));
+    return BSQ_OK;
+}
+
+int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows, int64_t cols,
+                       int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok, int64_t *d_row_offsets,
+                       int64_t *total_chars) {
+    if (tok == nullptr || total_chars == nullptr) return fail(BSQ_ERR_ARG, "null argument");
+    if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8)
+        return fail(BSQ_ERR_ARG, "Unexpected itemsize: expected 1, 2, 4, or 8. Found " + std::to_string(itemsize));  // src/tokenize.h:123
+    if (rows < 0 || cols < 0 || rows > 0x7fffffffll) return fail(BSQ_ERR_ARG, "bad decode shape");
+    *total_chars = 0;
+    BSQ_CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (rows == 0) {
+        BSQ_CUDA_TRY(cudaMemsetAsync(d_row_offsets, 0, sizeof(int64_t), st));
+        return BSQ_OK;
+    }
+    if (d_tokens == nullptr && cols > 0) return fail(BSQ_ERR_ARG, "Empty array cannot yield a decoded string");  // src/tokenize.h:133
+    const int64_t nblocks = (rows + kScanBlock - 1) / kScanBlock;
+    int64_t *d_work = nullptr;  // [0] first_bad, [1] grand total, [2..] block totals
+    BSQ_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_work), sizeof(int64_t) * (2 + nblocks), st));
+    BSQ_CUDA_TRY(cudaMemsetAsync(d_work, 0xff, sizeof(int64_t), st));
+    const InvParam inv = make_inv(*tok);
+    decode_len_kernel<<<static_cast<unsigned>(rows), 128, 0, st>>>(
+        static_cast<const uint8_t *>(d_tokens), itemsize, cols, row_stride, col_stride, inv, d_row_offsets,
+        reinterpret_cast<unsigned long long *>(d_work));
+    scan_local_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2);
+    scan_totals_kernel<<<1, kScanBlock, 0, st>>>(d_work + 2, nblocks, d_work + 1);
+    scan_add_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2, d_work + 1);
+    count_launch(4);
+    BSQ_CUDA_TRY(cudaGetLastError());
+    int64_t h[2] = {0, 0};
+    BSQ_CUDA_TRY(cudaMemcpyAsync(h, d_work, sizeof(h), cudaMemcpyDeviceToHost, st));
+    BSQ_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h[0] != -1) {  // fetch the offending value for the reference's message
+        const int64_t r = h[0] / cols, c = h[0] % cols;
+        uint64_t raw = 0;
+        BSQ_CUDA_TRY(cudaMemcpy(&raw, static_cast<const uint8_t *>(d_tokens) + r * row_stride + c * col_stride, itemsize,
+                                cudaMemcpyDeviceToHost));
+        BSQ_CUDA_TRY(cudaFreeAsync(d_work, st));
+        return fail(BSQ_ERR_BAD_TOKEN, "Unexpected/invalid token " + std::to_string(static_cast<uint32_t>(raw)));
+    }
+    BSQ_CUDA_TRY(cudaFreeAsync(d_work, st));
+    *total_chars = h[1];
+    return BSQ_OK;
+}
+
+int bsq_decode_chars(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows, int64_t cols,
+                     int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok, const int64_t *d_row_offsets,
+                     uint8_t *d_chars) {
+    if (tok == nullptr) return fail(BSQ_ERR_ARG, "null tokenizer");
+    if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8) return fail(BSQ_ERR_ARG, "bad itemsize");
+    if (rows <= 0 || cols <= 0) return BSQ_OK;
+    if (rows > 0x7fffffffll) return fail(BSQ_ERR_ARG, "bad decode shape");
+    BSQ_CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const InvParam inv = make_inv(*tok);
+    decode_chars_kernel<<<static_cast<unsigned>(rows), 128, 0, st>>>(
+        static_cast<const uint8_t *>(d_tokens), itemsize, cols, row_stride, col_stride, inv, d_row_offsets, d_chars);
+    count_launch();
+    BSQ_CUDA_TRY(cudaGetLastError());
+    return BSQ_OK;
+}
+
+}  // extern "C"

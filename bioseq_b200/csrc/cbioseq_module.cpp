@@ -1,0 +1,574 @@
+// cbioseq -- the drop-in Python extension.  Same module name, class name, method names,
+// keyword arguments and defaults as the reference's pybind11 module
+// (/root/reference/src/bioseq.cpp:6-11, src/tokenize.cpp:21-113, src/omp.cpp:43-49), but the
+// batch methods run on the GPU through the C ABI in include/bsq.h and return torch CUDA
+// tensors.  This file holds only host glue: walking the Python items, calling bsq_*, and
+// turning decoded characters into Python strings.  torch is used from here through its
+// Python API for device memory and the current stream only (no libtorch link).
+//
+// Deviations from the reference that a caller can observe:
+//   * results are torch CUDA tensors, not numpy arrays;
+//   * destchar 'B' gives torch.uint8 and 'b' torch.int8 (the reference binary returns int8
+//     for both because it lower-cases first, src/tokenize.cpp:66,83; the bytes are the same);
+//     l/L/q/Q give torch.int64 (reference: uint64, same bytes);
+//   * a sequence longer than padlen raises instead of aborting the interpreter;
+//   * numpy-array items are rejected with the reference's ValueError (src/tokenize.h:406-416).
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/bsq.h"
+
+namespace py = pybind11;
+
+namespace bsqpy {
+
+// ------------------------------------------------------------------ errors
+[[noreturn]] void raise_status(int rc, bool onehot = false) {
+    const std::string msg = bsq_last_error();
+    switch (rc) {
+        case BSQ_ERR_ARG: throw py::value_error(msg);
+        case BSQ_ERR_TOO_LONG:  // tokens: runtime_error (tokenize.h:458); one-hot: invalid_argument (:361)
+            if (onehot) throw py::value_error(msg);
+            throw std::runtime_error(msg);
+        default: throw std::runtime_error(msg);
+    }
+}
+inline void check(int rc, bool onehot = false) {
+    if (rc != BSQ_OK) raise_status(rc, onehot);
+}
+
+// ------------------------------------------------------------------ host thread knob (src/omp.cpp)
+int g_num_threads = 0;
+py::ssize_t get_num_threads() {
+    if (g_num_threads > 0) return g_num_threads;
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc ? hc : 1;
+}
+void set_num_threads(py::ssize_t n) {
+    if (n > 0) g_num_threads = static_cast<int>(n);
+}
+struct Threading {
+    explicit Threading(py::ssize_t n = -1) { set_num_threads(n); }
+    py::ssize_t get() const { return get_num_threads(); }
+    void set(py::ssize_t n) const { set_num_threads(n); }
+};
+
+// ------------------------------------------------------------------ torch plumbing
+struct Torch {
+    py::object mod, empty, device, cuda, uint8, int8, int16, int32, int64, float32, float64;
+    static Torch &get() {
+        static Torch *t = nullptr;  // leaked on purpose: must outlive interpreter teardown order
+        if (t == nullptr) {
+            t = new Torch();
+            t->mod = py::module_::import("torch");
+            t->empty = t->mod.attr("empty");
+            t->device = t->mod.attr("device");
+            t->cuda = t->mod.attr("cuda");
+            t->uint8 = t->mod.attr("uint8");
+            t->int8 = t->mod.attr("int8");
+            t->int16 = t->mod.attr("int16");
+            t->int32 = t->mod.attr("int32");
+            t->int64 = t->mod.attr("int64");
+            t->float32 = t->mod.attr("float32");
+            t->float64 = t->mod.attr("float64");
+        }
+        return *t;
+    }
+    py::object dtype_of(char destchar, int kind) const {
+        switch (kind) {
+            case BSQ_I8: return destchar == 'B' ? uint8 : int8;
+            case BSQ_I16: return int16;
+            case BSQ_I32: return int32;
+            case BSQ_I64: return int64;
+            case BSQ_F32: return float32;
+            default: return float64;
+        }
+    }
+};
+
+// Resolve the `device` keyword (None -> current CUDA device).  There is no CPU path.
+int resolve_device(const py::object &device) {
+    Torch &t = Torch::get();
+    if (!t.cuda.attr("is_available")().cast<bool>())
+        throw std::runtime_error("bioseq_b200: no CUDA device available -- this build has no CPU fallback");
+    if (device.is_none()) return t.cuda.attr("current_device")().cast<int>();
+    if (py::isinstance<py::int_>(device)) return device.cast<int>();
+    py::object dev = t.device(device);
+    if (dev.attr("type").cast<std::string>() != "cuda")
+        throw py::value_error("bioseq_b200: device must be a CUDA device");
+    py::object idx = dev.attr("index");
+    return idx.is_none() ? t.cuda.attr("current_device")().cast<int>() : idx.cast<int>();
+}
+
+void *current_stream(int device) {
+    Torch &t = Torch::get();
+    return reinterpret_cast<void *>(t.cuda.attr("current_stream")(device).attr("cuda_stream").cast<uintptr_t>());
+}
+
+py::object new_tensor(const std::vector<int64_t> &shape, const py::object &dtype, int device) {
+    Torch &t = Torch::get();
+    return t.empty(py::cast(shape), py::arg("dtype") = dtype, py::arg("device") = t.device("cuda", device));
+}
+
+inline void *data_ptr(const py::object &tensor) {
+    return reinterpret_cast<void *>(tensor.attr("data_ptr")().cast<uintptr_t>());
+}
+
+// ------------------------------------------------------------------ per-device staging context
+struct DeviceCtx {
+    std::mutex mu;
+    bsq_stager *stager = nullptr;
+    bsq_pack *pack = nullptr;
+};
+DeviceCtx &device_ctx(int device) {
+    static std::mutex map_mu;
+    static std::map<int, DeviceCtx *> *ctxs = new std::map<int, DeviceCtx *>();  // leaked: CUDA teardown order
+    std::lock_guard<std::mutex> g(map_mu);
+    DeviceCtx *&c = (*ctxs)[device];
+    if (c == nullptr) {
+        c = new DeviceCtx();
+        check(bsq_stager_create(&c->stager, device));
+        check(bsq_pack_create(&c->pack, /*pinned=*/1));
+    }
+    return *c;
+}
+
+// ------------------------------------------------------------------ item unpacking (src/tokenize.h:389-419)
+struct Unpacked {
+    py::object keepalive;  // the PySequence_Fast view: holds the items (and so their buffers) alive
+    std::vector<const void *> ptrs;
+    std::vector<int64_t> lens;
+};
+
+void unpack_items(const py::sequence &batch, Unpacked &u) {
+    PyObject *fast = PySequence_Fast(batch.ptr(), "batch must be a sequence");
+    if (fast == nullptr) throw py::error_already_set();
+    u.keepalive = py::reinterpret_steal<py::object>(fast);
+    const Py_ssize_t n = PySequence_Fast_GET_SIZE(fast);
+    PyObject **items = PySequence_Fast_ITEMS(fast);
+    u.ptrs.resize(static_cast<size_t>(n));
+    u.lens.resize(static_cast<size_t>(n));
+    for (Py_ssize_t i = 0; i < n; ++i) {
+        PyObject *it = items[i];
+        if (PyUnicode_Check(it)) {
+            Py_ssize_t size;
+            const char *s = PyUnicode_AsUTF8AndSize(it, &size);
+            if (s == nullptr) throw py::error_already_set();
+            u.ptrs[i] = s;
+            u.lens[i] = size;
+        } else if (PyBytes_Check(it)) {
+            u.ptrs[i] = PyBytes_AS_STRING(it);
+            u.lens[i] = PyBytes_GET_SIZE(it);
+        } else if (PyByteArray_Check(it)) {
+            u.ptrs[i] = PyByteArray_AS_STRING(it);
+            u.lens[i] = PyByteArray_GET_SIZE(it);
+        } else {
+            throw py::value_error("item was none of string, bytes, or numpy array of 8-bit integers. ");
+        }
+    }
+}
+
+// A host or device array argument of the *_packed entry points.
+struct ArrayArg {
+    py::object keepalive;
+    const void *ptr = nullptr;
+    int64_t count = 0;
+    bool on_device = false;
+    int device = -1;
+};
+
+ArrayArg array_arg(const py::object &obj, const char *what, int itemsize, const char *np_dtype, const py::object &torch_dtype) {
+    ArrayArg a;
+    Torch &t = Torch::get();
+    if (py::isinstance(obj, t.mod.attr("Tensor"))) {
+        if (!py::object(obj.attr("dtype")).equal(torch_dtype)) throw py::value_error(std::string(what) + ": wrong dtype");
+        py::object c = obj.attr("contiguous")();
+        a.keepalive = c;
+        a.ptr = data_ptr(c);
+        a.count = c.attr("numel")().cast<int64_t>();
+        a.on_device = c.attr("is_cuda").cast<bool>();
+        if (a.on_device) a.device = c.attr("get_device")().cast<int>();
+        return a;
+    }
+    py::array arr = py::array::ensure(obj, py::array::c_style);
+    if (!arr) throw py::value_error(std::string(what) + ": expected a numpy array or torch tensor");
+    if (arr.itemsize() != itemsize || !arr.dtype().equal(py::dtype(np_dtype)))
+        throw py::value_error(std::string(what) + ": wrong dtype, expected " + np_dtype);
+    a.keepalive = arr;
+    a.ptr = arr.data();
+    a.count = arr.size();
+    return a;
+}
+
+// ------------------------------------------------------------------ the Tokenizer class
+class Tokenizer {
+public:
+    Tokenizer(const std::string &key, bool eos, bool bos, bool padchar) : eos_(eos), bos_(bos), padchar_(padchar) {
+        const int rc = bsq_tokenizer_init(&tok_, key.c_str(), eos, bos, padchar);
+        if (rc != BSQ_OK) throw std::runtime_error(bsq_last_error());  // src/tokenize.h:78
+    }
+
+    // ---- introspection (src/tokenize.cpp:52-63, :99-106)
+    std::string key() const { return tok_.key; }
+    int nchars() const { return tok_.nchars; }
+    size_t alphabet_size() const { return static_cast<size_t>(tok_.alphabet_size); }
+    int bos() const { return tok_.bos_id; }
+    int eos() const { return tok_.eos_id; }
+    int pad() const { return tok_.pad_id; }
+    bool is_padded() const { return padchar_; }
+    bool includes_bos() const { return bos_; }
+    bool includes_eos() const { return eos_; }
+
+    std::vector<int32_t> ids() const {
+        std::vector<int32_t> out;
+        char buf[8];
+        for (int32_t id = -128; id < tok_.nchars + 3; ++id)
+            if (bsq_tokenizer_lookup(&tok_, id, buf, sizeof(buf)) > 0) out.push_back(id);
+        return out;
+    }
+    py::dict lut() const {  // id -> decoded text
+        py::dict d;
+        char buf[8];
+        for (int32_t id : ids()) {
+            const int n = bsq_tokenizer_lookup(&tok_, id, buf, sizeof(buf));
+            d[py::int_(id)] = py::reinterpret_steal<py::str>(PyUnicode_DecodeLatin1(buf, n, nullptr));
+        }
+        return d;
+    }
+    std::string token_map() const {  // "id:text;id:text" (reference order is unordered_map order)
+        std::string s;
+        char buf[8];
+        for (int32_t id : ids()) {
+            const int n = bsq_tokenizer_lookup(&tok_, id, buf, sizeof(buf));
+            if (!s.empty()) s += ';';
+            s += std::to_string(id) + ':' + std::string(buf, static_cast<size_t>(n));
+        }
+        return s;
+    }
+    py::dict token_decoder() const {  // id -> every byte that maps to it (src/tokenize.h:65-71)
+        std::map<int, std::string> sets;
+        for (int b = 0; b < 256; ++b) sets[tok_.lut[b]] += static_cast<char>(b);
+        py::dict d;
+        for (const auto &kv : sets) d[py::int_(kv.first)] = py::bytes(kv.second);
+        return d;
+    }
+    py::tuple getstate() const { return py::make_tuple(key(), eos_, bos_, padchar_); }
+
+    // ---- batch_tokenize (src/tokenize.cpp:82-98)
+    py::object batch_tokenize(const py::sequence &batch, py::ssize_t padlen, const std::string &destchar, bool batch_first,
+                              int nthreads, const py::object &device) const {
+        const char dc = destchar.empty() ? '\0' : destchar[0];
+        const int kind = bsq_kind_of_destchar(dc);
+        if (kind < 0) raise_status(kind);
+        if (padlen <= 0) throw py::value_error("batch tokenize requires padlen is provded.");
+        Unpacked u;
+        unpack_items(batch, u);
+        return run_host(u.ptrs.data(), u.lens.data(), static_cast<int64_t>(u.lens.size()), nullptr, padlen, dc, kind,
+                        /*onehot=*/false, batch_first, nthreads, device);
+    }
+
+    // ---- batch_onehot_encode (src/tokenize.cpp:65-81); always (padlen, batch, alphabet_size)
+    py::object batch_onehot_encode(const py::sequence &batch, py::ssize_t padlen, const std::string &destchar, int nthreads,
+                                   const py::object &mask, const py::object &device) const {
+        const char dc = destchar.empty() ? '\0' : destchar[0];
+        const int kind = bsq_kind_of_destchar(dc);
+        if (kind < 0) raise_status(kind);
+        if (padlen <= 0) throw py::value_error("batch tokenize requires padlen is provded.");
+        Unpacked u;
+        unpack_items(batch, u);
+        // mask: a list with one uint8 array per sequence; entries that are not arrays mean
+        // "no mask for this sequence" (getmaskptr, src/tokenize.h:372-380).
+        std::vector<uint8_t> maskbuf;
+        const uint8_t *maskptr = nullptr;
+        if (py::isinstance<py::list>(mask)) {
+            const py::list ml = mask.cast<py::list>();
+            if (ml.size() < u.lens.size()) throw py::index_error("mask list is shorter than the batch");
+            int64_t total = 0;
+            for (int64_t l : u.lens) total += l;
+            maskbuf.assign(static_cast<size_t>(total) + 32, 1);
+            int64_t pos = 0;
+            for (size_t i = 0; i < u.lens.size(); ++i) {
+                py::object m = ml[i];
+                if (py::isinstance<py::array>(m)) {
+                    py::array_t<uint8_t, py::array::forcecast | py::array::c_style> arr(m);
+                    if (arr.size() < u.lens[i]) throw py::value_error("mask entry shorter than its sequence");
+                    std::memcpy(maskbuf.data() + pos, arr.data(), static_cast<size_t>(u.lens[i]));
+                }
+                pos += u.lens[i];
+            }
+            maskptr = maskbuf.data();
+        }
+        return run_host(u.ptrs.data(), u.lens.data(), static_cast<int64_t>(u.lens.size()), maskptr, padlen, dc, kind,
+                        /*onehot=*/true, false, nthreads, device);
+    }
+
+    // ---- additive: already-packed input (host numpy / torch CPU, or torch CUDA = device resident)
+    py::object tokenize_packed(const py::object &bytes, const py::object &offsets, py::ssize_t padlen,
+                               const std::string &destchar, bool batch_first, const py::object &device, bool check_len) const {
+        return run_packed(bytes, offsets, py::none(), padlen, destchar, false, batch_first, device, check_len);
+    }
+    py::object onehot_packed(const py::object &bytes, const py::object &offsets, py::ssize_t padlen, const std::string &destchar,
+                             const py::object &mask, const py::object &device, bool check_len) const {
+        return run_packed(bytes, offsets, mask, padlen, destchar, true, false, device, check_len);
+    }
+
+    // ---- single-sequence onehot_encode (src/tokenize.cpp:8-48, src/tokenize.h:188-216)
+    py::object onehot_encode(const py::object &seq, py::ssize_t padlen, const py::object &destchar, const py::object &device) const {
+        // the reference registers three overloads whose default destchar differs: "f" for str
+        // and bytearray, "B" for bytes (src/tokenize.cpp:31,39,48)
+        const std::string dt = destchar.is_none() ? (PyBytes_Check(seq.ptr()) ? "B" : "f") : destchar.cast<std::string>();
+        const void *ptr;
+        int64_t len;
+        Py_ssize_t size;
+        if (PyUnicode_Check(seq.ptr())) {
+            ptr = PyUnicode_AsUTF8AndSize(seq.ptr(), &size);
+            if (ptr == nullptr) throw py::error_already_set();
+            len = size;
+        } else if (PyBytes_Check(seq.ptr())) {
+            ptr = PyBytes_AS_STRING(seq.ptr());
+            len = PyBytes_GET_SIZE(seq.ptr());
+        } else if (PyByteArray_Check(seq.ptr())) {
+            ptr = PyByteArray_AS_STRING(seq.ptr());
+            len = PyByteArray_GET_SIZE(seq.ptr());
+        } else {
+            throw py::type_error("onehot_encode(): expected str, bytes or bytearray");
+        }
+        char dc;
+        switch (dt.empty() ? 0 : (dt[0] & 223)) {  // src/tokenize.cpp:10-16: B H I F D only
+            case 'B': dc = 'B'; break;
+            case 'H': dc = 'h'; break;
+            case 'I': dc = 'i'; break;
+            case 'F': dc = 'f'; break;
+            case 'D': dc = 'd'; break;
+            default: throw py::value_error("Unsupported dtype: " + dt);
+        }
+        if (padlen > 0 && len > padlen) throw std::runtime_error("padlen is too short to accommodate sequence\n");
+        // rows = max(len, padlen) + bos + eos (src/tokenize.h:195); pad rows only up to padlen (:210-214)
+        const int64_t rows = std::max<int64_t>(len, padlen) + bos_ + eos_;
+        if (rows == 0) return new_tensor({0, tok_.alphabet_size}, Torch::get().dtype_of(dc, bsq_kind_of_destchar(dc)), resolve_device(device));
+        py::object out = run_host(&ptr, &len, 1, nullptr, rows, dc, bsq_kind_of_destchar(dc), true, false, 1, device);
+        out = out.attr("reshape")(rows, tok_.alphabet_size);
+        if (padchar_ && padlen > len) out[py::slice(padlen, rows, 1)].attr("zero_")();
+        return out;
+    }
+
+    // ---- decode_tokens (src/tokenize.cpp:49-51, src/tokenize.h:131-183)
+    py::object decode_tokens(const py::object &array, const py::object &device) const {
+        Torch &t = Torch::get();
+        py::object tens;  // device tensor viewed as raw bytes
+        std::vector<int64_t> shape, strides;
+        int itemsize;
+        if (py::isinstance(array, t.mod.attr("Tensor"))) {
+            py::object src = array;
+            itemsize = src.attr("element_size")().cast<int>();
+            shape = src.attr("shape").cast<std::vector<int64_t>>();
+            strides = src.attr("stride")().cast<std::vector<int64_t>>();
+            for (auto &s : strides) s *= itemsize;
+            if (!src.attr("is_cuda").cast<bool>()) {
+                const int dev = resolve_device(device);
+                src = src.attr("contiguous")().attr("to")(t.device("cuda", dev));
+                strides.assign(shape.size(), itemsize);
+                for (int d = static_cast<int>(shape.size()) - 2; d >= 0; --d) strides[d] = strides[d + 1] * shape[d + 1];
+            }
+            tens = src;
+        } else {
+            py::array arr = py::array::ensure(array);
+            if (!arr) throw py::type_error("decode_tokens(): expected a numpy array or torch tensor");
+            itemsize = static_cast<int>(arr.itemsize());
+            for (py::ssize_t d = 0; d < arr.ndim(); ++d) shape.push_back(arr.shape(d));
+            const int nd = static_cast<int>(shape.size());
+            if (nd > 2 || nd == 0) throw py::value_error("Currently supported: 1 or 2 dimensions for decoding tokens.");
+            py::array flat = py::module_::import("numpy").attr("ascontiguousarray")(arr).attr("reshape")(-1).attr("view")("uint8");
+            const int dev = resolve_device(device);
+            tens = t.mod.attr("from_numpy")(flat.attr("copy")()).attr("to")(t.device("cuda", dev));
+            strides.assign(shape.size(), itemsize);
+            for (int d = nd - 2; d >= 0; --d) strides[d] = strides[d + 1] * shape[d + 1];
+        }
+        const int nd = static_cast<int>(shape.size());
+        if (nd > 2 || nd == 0) throw py::value_error("Currently supported: 1 or 2 dimensions for decoding tokens.");
+        const int64_t rows = nd == 1 ? 1 : shape[0], cols = nd == 1 ? shape[0] : shape[1];
+        const int64_t rs = nd == 1 ? 0 : strides[0], cs = nd == 1 ? strides[0] : strides[1];
+        const int dev = tens.attr("get_device")().cast<int>();
+        void *st = current_stream(dev);
+        py::object d_offs = new_tensor({rows + 1}, t.int64, dev);
+        int64_t total = 0;
+        check(bsq_decode_lengths(dev, st, data_ptr(tens), itemsize, rows, cols, rs, cs, &tok_,
+                                 static_cast<int64_t *>(data_ptr(d_offs)), &total));
+        py::object d_chars = new_tensor({total}, t.uint8, dev);
+        check(bsq_decode_chars(dev, st, data_ptr(tens), itemsize, rows, cols, rs, cs, &tok_,
+                               static_cast<const int64_t *>(data_ptr(d_offs)), static_cast<uint8_t *>(data_ptr(d_chars))));
+        py::array_t<uint8_t> h_chars = d_chars.attr("cpu")().attr("numpy")();
+        py::array_t<int64_t> h_offs = d_offs.attr("cpu")().attr("numpy")();
+        const char *c = reinterpret_cast<const char *>(h_chars.data());
+        const int64_t *o = h_offs.data();
+        auto make_str = [&](int64_t r) {
+            // every decoded character is < 0x80 (ids of bytes >= 0x80 are rejected), so ASCII
+            PyObject *s = PyUnicode_New(o[r + 1] - o[r], 127);
+            if (s == nullptr) throw py::error_already_set();
+            std::memcpy(PyUnicode_1BYTE_DATA(s), c + o[r], static_cast<size_t>(o[r + 1] - o[r]));
+            return py::reinterpret_steal<py::object>(s);
+        };
+        if (nd == 1) return make_str(0);
+        py::list out(static_cast<size_t>(rows));
+        for (int64_t r = 0; r < rows; ++r) PyList_SET_ITEM(out.ptr(), r, make_str(r).release().ptr());
+        return out;
+    }
+
+private:
+    // pack (pinned) -> stage -> launch.  ptrs/lens describe n host sequences.
+    py::object run_host(const void *const *ptrs, const int64_t *lens, int64_t n, const uint8_t *mask, int64_t padlen, char dc,
+                        int kind, bool onehot, bool batch_first, int nthreads, const py::object &device) const {
+        const int dev = resolve_device(device);
+        const int64_t extra = bos_ + eos_;
+        for (int64_t i = 0; i < n; ++i)
+            if (lens[i] + extra > padlen) {
+                const std::string msg = "seq len + bos + eos > padlen: " + std::to_string(lens[i] + extra) + ", vs padlen " +
+                                        std::to_string(padlen);
+                if (onehot) throw py::value_error(msg);
+                throw std::runtime_error(msg);
+            }
+        std::vector<int64_t> shape;
+        if (onehot) shape = {padlen, n, tok_.alphabet_size};
+        else if (batch_first) shape = {n, padlen};
+        else shape = {padlen, n};
+        py::object out = new_tensor(shape, Torch::get().dtype_of(dc, kind), dev);
+        if (n == 0) return out;
+        void *st = current_stream(dev);
+        void *optr = data_ptr(out);
+        DeviceCtx &ctx = device_ctx(dev);
+        int rc;
+        {
+            py::gil_scoped_release nogil;
+            std::lock_guard<std::mutex> g(ctx.mu);
+            rc = bsq_stager_sync_copies(ctx.stager);  // the pinned pack buffer may still be in flight
+            if (rc == BSQ_OK) rc = bsq_pack_gather(ctx.pack, ptrs, lens, n, nthreads > 0 ? nthreads : 1);
+            if (rc == BSQ_OK) {
+                if (onehot)
+                    rc = bsq_onehot_host(ctx.stager, st, bsq_pack_bytes(ctx.pack), bsq_pack_offsets(ctx.pack), mask, n, padlen,
+                                         &tok_, kind, optr);
+                else
+                    rc = bsq_tokenize_host(ctx.stager, st, bsq_pack_bytes(ctx.pack), bsq_pack_offsets(ctx.pack), n, padlen, &tok_,
+                                           batch_first, kind, optr);
+            }
+            if (rc == BSQ_OK && mask != nullptr) rc = bsq_stager_sync_copies(ctx.stager);  // mask is a local buffer
+        }
+        check(rc, onehot);
+        return out;
+    }
+
+    py::object run_packed(const py::object &bytes, const py::object &offsets, const py::object &mask, py::ssize_t padlen,
+                          const std::string &destchar, bool onehot, bool batch_first, const py::object &device,
+                          bool check_len) const {
+        Torch &t = Torch::get();
+        const char dc = destchar.empty() ? '\0' : destchar[0];
+        const int kind = bsq_kind_of_destchar(dc);
+        if (kind < 0) raise_status(kind);
+        if (padlen <= 0) throw py::value_error("batch tokenize requires padlen is provded.");
+        ArrayArg b = array_arg(bytes, "bytes", 1, "uint8", t.uint8);
+        ArrayArg o = array_arg(offsets, "offsets", 8, "int64", t.int64);
+        ArrayArg m;
+        if (!mask.is_none()) m = array_arg(mask, "mask", 1, "uint8", t.uint8);
+        if (o.count < 1) throw py::value_error("offsets needs at least one entry");
+        if (b.on_device != o.on_device || (!mask.is_none() && m.on_device != b.on_device))
+            throw py::value_error("bytes, offsets and mask must live on the same side (all host or all CUDA)");
+        const int64_t n = o.count - 1;
+        const int dev = b.on_device ? b.device : resolve_device(device);
+        std::vector<int64_t> shape;
+        if (onehot) shape = {padlen, n, tok_.alphabet_size};
+        else if (batch_first) shape = {n, padlen};
+        else shape = {padlen, n};
+        void *st = current_stream(dev);
+        int rc;
+        py::object out;
+        if (b.on_device) {
+            if (check_len) check(bsq_check_lengths_device(dev, st, static_cast<const int64_t *>(o.ptr), n, padlen, &tok_), onehot);
+            out = new_tensor(shape, t.dtype_of(dc, kind), dev);
+            if (onehot)
+                rc = bsq_onehot(dev, st, static_cast<const uint8_t *>(b.ptr), static_cast<const int64_t *>(o.ptr),
+                                static_cast<const uint8_t *>(m.ptr), n, padlen, &tok_, kind, data_ptr(out));
+            else
+                rc = bsq_tokenize(dev, st, static_cast<const uint8_t *>(b.ptr), static_cast<const int64_t *>(o.ptr), n, padlen,
+                                  &tok_, batch_first, kind, data_ptr(out));
+        } else {
+            const int64_t *ho = static_cast<const int64_t *>(o.ptr);
+            if (n > 0 && ho[n] - ho[0] > b.count - ho[0]) throw py::value_error("offsets run past the end of bytes");
+            if (!mask.is_none() && m.count < b.count) throw py::value_error("mask shorter than bytes");
+            check(bsq_check_lengths_host(ho, n, padlen, &tok_), onehot);
+            out = new_tensor(shape, t.dtype_of(dc, kind), dev);
+            DeviceCtx &ctx = device_ctx(dev);
+            void *optr = data_ptr(out);
+            py::gil_scoped_release nogil;
+            std::lock_guard<std::mutex> g(ctx.mu);
+            if (onehot)
+                rc = bsq_onehot_host(ctx.stager, st, static_cast<const uint8_t *>(b.ptr), ho, static_cast<const uint8_t *>(m.ptr), n,
+                                     padlen, &tok_, kind, optr);
+            else
+                rc = bsq_tokenize_host(ctx.stager, st, static_cast<const uint8_t *>(b.ptr), ho, n, padlen, &tok_, batch_first, kind,
+                                       optr);
+            // the caller's arrays are only borrowed for the duration of the call
+            if (rc == BSQ_OK) rc = bsq_stager_sync_copies(ctx.stager);
+        }
+        check(rc, onehot);
+        return out;
+    }
+
+    bsq_tokenizer tok_;
+    bool eos_, bos_, padchar_;
+};
+
+}  // namespace bsqpy
+
+PYBIND11_MODULE(cbioseq, m) {
+    using bsqpy::Tokenizer;
+    m.doc() = "B200-native drop-in for bioseq's cbioseq tokenizer module (GPU batch tokenisation)";
+    m.attr("__bsq_abi_version__") = bsq_abi_version();
+
+    py::class_<Tokenizer>(m, "Tokenizer")
+        .def(py::init<std::string, bool, bool, bool>(), py::arg("key"), py::arg("eos") = false, py::arg("bos") = false,
+             py::arg("padchar") = false)
+        .def("onehot_encode", &Tokenizer::onehot_encode, py::arg("str"), py::arg("padlen") = 0, py::arg("destchar") = py::none(),
+             py::arg("device") = py::none())
+        .def("decode_tokens", &Tokenizer::decode_tokens, py::arg("tokenizer"), py::arg("device") = py::none())
+        .def("lut", &Tokenizer::lut)
+        .def("token_map", &Tokenizer::token_map)
+        .def("token_decoder", &Tokenizer::token_decoder)
+        .def("nchars", &Tokenizer::nchars)
+        .def("batch_onehot_encode", &Tokenizer::batch_onehot_encode, py::arg("batch"), py::arg("padlen") = -1,
+             py::arg("destchar") = "B", py::arg("nthreads") = 1, py::arg("mask") = py::none(), py::arg("device") = py::none())
+        .def("batch_tokenize", &Tokenizer::batch_tokenize, py::arg("batch"), py::arg("padlen") = -1, py::arg("destchar") = "B",
+             py::arg("batch_first") = false, py::arg("nthreads") = 1, py::arg("device") = py::none())
+        .def("batch_tokenize_packed", &Tokenizer::tokenize_packed, py::arg("bytes"), py::arg("offsets"), py::arg("padlen") = -1,
+             py::arg("destchar") = "B", py::arg("batch_first") = false, py::arg("device") = py::none(),
+             py::arg("check_lengths") = true)
+        .def("batch_onehot_encode_packed", &Tokenizer::onehot_packed, py::arg("bytes"), py::arg("offsets"), py::arg("padlen") = -1,
+             py::arg("destchar") = "B", py::arg("mask") = py::none(), py::arg("device") = py::none(),
+             py::arg("check_lengths") = true)
+        .def("alphabet_size", &Tokenizer::alphabet_size)
+        .def("bos", &Tokenizer::bos)
+        .def("eos", &Tokenizer::eos)
+        .def("pad", &Tokenizer::pad)
+        .def_property_readonly("key", &Tokenizer::key)
+        .def("is_padded", &Tokenizer::is_padded)
+        .def("includes_bos", &Tokenizer::includes_bos)
+        .def("includes_eos", &Tokenizer::includes_eos)
+        .def(py::pickle([](const Tokenizer &t) { return t.getstate(); },
+                        [](py::tuple s) {
+                            return Tokenizer(s[0].cast<std::string>(), s[1].cast<bool>(), s[2].cast<bool>(), s[3].cast<bool>());
+                        }));
+
+    m.def("set_num_threads", &bsqpy::set_num_threads);
+    m.def("get_num_threads", &bsqpy::get_num_threads);
+    py::class_<bsqpy::Threading>(m, "Threading")
+        .def(py::init<>())
+        .def(py::init<py::ssize_t>())
+        .def_property("nthreads", &bsqpy::Threading::get, &bsqpy::Threading::set)
+        .def_property("p", &bsqpy::Threading::get, &bsqpy::Threading::set);
+}

@@ -1,0 +1,188 @@
+/*
+ * bsq.h -- C ABI of the B200-native batch tokeniser (libbsq.so).
+ *
+ * This is the drop-in boundary for the hot path of dnbaker/bioseq: everything the
+ * reference's pybind11 class `cbioseq.Tokenizer` (src/tokenize.cpp:21-113) computes for
+ *     batch_tokenize       (src/tokenize.cpp:82-98  -> Tokenizer::transencode<T>, src/tokenize.h:381-485)
+ *     batch_onehot_encode  (src/tokenize.cpp:65-81  -> Tokenizer::tokenize<T>,    src/tokenize.h:283-371)
+ *     decode_tokens        (src/tokenize.cpp:49-51  -> Tokenizer::decode_tokens,  src/tokenize.h:131-179)
+ * is reachable through the plain-C entry points below.  The reference has no FFI of its
+ * own (the Python class *is* its interface); these are the functions a maintainer's
+ * pybind11 shim binds instead of the CPU loops, and they are what
+ * bioseq_b200's own `cbioseq` module, the GPU parity tests and bench.py call.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch/Python types cross the boundary;
+ *   - every function returns 0 (BSQ_OK) or a negative BSQ_ERR_* code and never throws;
+ *     bsq_last_error() returns the message of the calling thread's last failure -- where
+ *     the reference raises, the text is the reference's text (file:line cited per code);
+ *   - "d_" pointers are device memory on `device`, "h_" pointers are host memory;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream);
+ *     device entry points only enqueue work, they do not synchronise unless stated;
+ *   - sequences travel packed: one byte buffer + int64 offsets, offsets[i]..offsets[i+1]
+ *     delimiting sequence i (nseq+1 entries).  This is what the pack layer produces from
+ *     the Python str/bytes/bytearray items the reference unpacks at src/tokenize.h:389-419;
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails
+ *     with BSQ_ERR_CUDA.
+ */
+#ifndef BSQ_H_
+#define BSQ_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BSQ_ABI_VERSION 1
+
+/* ---- status codes ---------------------------------------------------------------- */
+#define BSQ_OK 0
+#define BSQ_ERR_ARG (-1)       /* std::invalid_argument in the reference -> ValueError          */
+#define BSQ_ERR_TOO_LONG (-2)  /* "seq len + bos + eos > padlen: N, vs padlen P" (tokenize.h:458 runtime_error, :361 invalid_argument) */
+#define BSQ_ERR_BAD_TOKEN (-3) /* "Unexpected/invalid token N" (tokenize.h:148,170) -> RuntimeError */
+#define BSQ_ERR_KEY (-4)       /* "Invalid tokenizer type; select one from..." (tokenize.h:78) -> RuntimeError */
+#define BSQ_ERR_CUDA (-5)      /* CUDA runtime failure / no device -> RuntimeError              */
+#define BSQ_ERR_NOMEM (-6)
+
+/* ---- element kinds of the output array (src/tokenize.cpp:66-79, :83-96) ------------ */
+typedef enum bsq_kind {
+    BSQ_I8 = 0,  /* destchar b/B : 1-byte integer (reference: int8)            */
+    BSQ_I16 = 1, /* destchar h/H */
+    BSQ_I32 = 2, /* destchar i/I */
+    BSQ_I64 = 3, /* destchar l/L/q/Q : 8-byte integer (reference: uint64)      */
+    BSQ_F32 = 4, /* destchar f/F */
+    BSQ_F64 = 5  /* destchar d/D */
+} bsq_kind;
+
+/* tolower(destchar) dispatch of src/tokenize.cpp:66,83.  Returns a bsq_kind, or
+ * BSQ_ERR_ARG ("Unsupported dtype: X", tokenize.cpp:80,97). */
+int bsq_kind_of_destchar(char destchar);
+/* bytes per element of a kind (1,2,4,8,4,8); 0 for an invalid kind. */
+size_t bsq_kind_size(int kind);
+
+/* ---- tokenizer descriptor ---------------------------------------------------------- */
+/* Plain data; filled by bsq_tokenizer_init and passed by pointer to the compute calls.
+ * Mirrors struct Tokenizer's state (src/tokenize.h:10-38). */
+typedef struct bsq_tokenizer {
+    int8_t lut[256];        /* alphabet.h:32-61 make_lut: byte -> id, -1 = invalid            */
+    int32_t nchars;         /* alphabet.h:27   number of groups                                */
+    int32_t bos_id;         /* tokenize.h:23-26  nchars, or -1 when BOS is not included        */
+    int32_t eos_id;         /* tokenize.h:27-30  nchars + bos, or -1                           */
+    int32_t pad_id;         /* tokenize.h:31-33  nchars + bos + eos (defined even if !padchar) */
+    int32_t padchar;        /* tokenize.h:13   zero_onehot_pad_: pad id is a real symbol       */
+    int32_t alphabet_size;  /* tokenize.h:22   nchars + eos + bos + padchar                    */
+    char key[16];           /* upper-cased key (tokenize.h:73)                                 */
+} bsq_tokenizer;
+
+/* Registry of alphabet keys (CAMAP, src/alphabet.h:198-222), in map order. */
+int bsq_alphabet_count(void);
+const char *bsq_alphabet_key(int index);
+
+/* Tokenizer(key, eos, bos, padchar) -- src/tokenize.h:72-106.  Key lookup is
+ * case-insensitive.  BSQ_ERR_KEY on an unknown key. */
+int bsq_tokenizer_init(bsq_tokenizer *tok, const char *key, int eos, int bos, int padchar);
+
+/* id -> decoded text, the reference's `lookup` map (src/tokenize.h:83-99): for ids
+ * -128..127 the first byte value whose LUT entry is that id; "<BOS>", "<EOS>", "<PAD>"
+ * for the specials.  Writes up to cap-1 chars + NUL to buf and returns the length
+ * (1 or 5), or 0 when the id has no entry. */
+int bsq_tokenizer_lookup(const bsq_tokenizer *tok, int32_t id, char *buf, size_t cap);
+
+/* ---- pack layer (host) -------------------------------------------------------------- */
+/* Gathers ragged host sequences into one pinned byte buffer + int64 offsets: the form
+ * the kernels read and the form cudaMemcpyAsync can stage without a bounce.  Replaces
+ * the reference's vector<pair<const char*, size_t>> of borrowed pointers
+ * (src/tokenize.h:386-419). */
+typedef struct bsq_pack bsq_pack;
+
+/* pinned != 0: cudaHostAlloc'ed storage (needs a CUDA device); 0: pageable (malloc). */
+int bsq_pack_create(bsq_pack **out, int pinned);
+void bsq_pack_destroy(bsq_pack *p);
+/* Replace the contents with n sequences given as pointer/length arrays; the copy is
+ * split over up to nthreads host threads.  Also records the longest length. */
+int bsq_pack_gather(bsq_pack *p, const void *const *ptrs, const int64_t *lens, int64_t n, int nthreads);
+const uint8_t *bsq_pack_bytes(const bsq_pack *p);
+const int64_t *bsq_pack_offsets(const bsq_pack *p); /* n+1 entries */
+int64_t bsq_pack_nseq(const bsq_pack *p);
+int64_t bsq_pack_nbytes(const bsq_pack *p);
+int64_t bsq_pack_maxlen(const bsq_pack *p);
+
+/* Host-side length check done before any launch: the reference aborts the process when
+ * len + bos + eos > padlen (exception inside an OpenMP region, src/tokenize.h:456-459);
+ * here the call fails with BSQ_ERR_TOO_LONG and the reference's message.
+ * padlen <= 0 -> BSQ_ERR_ARG "batch tokenize requires padlen is provded." (tokenize.h:383). */
+int bsq_check_lengths_host(const int64_t *h_offsets, int64_t nseq, int64_t padlen, const bsq_tokenizer *tok);
+/* Same check for device-resident offsets: one reduction kernel + an 8-byte read-back
+ * (synchronises `stream`). */
+int bsq_check_lengths_device(int device, void *stream, const int64_t *d_offsets, int64_t nseq,
+                             int64_t padlen, const bsq_tokenizer *tok);
+
+/* ---- device compute ------------------------------------------------------------------ */
+/* batch_tokenize: tokens with BOS/EOS/PAD fused in one pass.
+ *   d_out: (nseq, padlen) if batch_first else (padlen, nseq), C-contiguous, `kind`
+ *   elements, 16-byte aligned; every element is written exactly once (no memset).
+ *   Row i = [bos?] lut[residues] (invalid -> 0) [eos?] then pad_id if padchar else 0
+ *   (src/tokenize.h:460-478).  Lengths must already have been checked. */
+int bsq_tokenize(int device, void *stream, const uint8_t *d_bytes, const int64_t *d_offsets,
+                 int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int batch_first,
+                 int kind, void *d_out);
+
+/* batch_onehot_encode: d_out is (padlen, nseq, alphabet_size), always sequence-first
+ * (src/tokenize.h:323-326); one 1 per position, all-zero rows for invalid or masked-out
+ * residues and -- unless padchar -- for the tail (src/tokenize.h:345-368).
+ * d_mask: optional, packed like d_bytes (one uint8 per residue, 0 = zero row). */
+int bsq_onehot(int device, void *stream, const uint8_t *d_bytes, const int64_t *d_offsets,
+               const uint8_t *d_mask, int64_t nseq, int64_t padlen, const bsq_tokenizer *tok,
+               int kind, void *d_out);
+
+/* decode_tokens on a (rows, cols) device array of `itemsize`-byte integers with byte
+ * strides (a 1-D array is rows = 1).  Two steps so the caller can size the output:
+ *   bsq_decode_lengths: validates every token, fills d_row_offsets[rows+1] (exclusive
+ *     prefix sum of the decoded row lengths) and returns the total through *total_chars
+ *     (synchronises `stream`).  BSQ_ERR_BAD_TOKEN carries the reference's message with
+ *     the first offending value in row-major order (src/tokenize.h:148,170).
+ *   bsq_decode_chars: writes the decoded characters of row r to
+ *     d_chars[d_row_offsets[r] .. d_row_offsets[r+1]). */
+int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows,
+                       int64_t cols, int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok,
+                       int64_t *d_row_offsets, int64_t *total_chars);
+int bsq_decode_chars(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows,
+                     int64_t cols, int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok,
+                     const int64_t *d_row_offsets, uint8_t *d_chars);
+
+/* ---- host-staged entry points (the end-to-end path) ------------------------------------ */
+/* A stager owns, for one device: a copy stream, device staging buffers for residues /
+ * offsets / mask, and a pinned bounce ring for pageable sources.  The *_host calls split
+ * the batch into sequence ranges, cudaMemcpyAsync each range host->device on the copy
+ * stream and launch its kernel on `stream` as soon as it lands, so the transfer of
+ * range k+1 overlaps the compute of range k.  Inputs may be pinned (copied directly) or
+ * pageable (bounced through the ring).  Lengths are checked first (bsq_check_lengths_host).
+ * The calls return once all work is enqueued; the staging buffers stay owned by the
+ * stager and are reused by the next call on it (which waits for the previous one). */
+typedef struct bsq_stager bsq_stager;
+int bsq_stager_create(bsq_stager **out, int device);
+void bsq_stager_destroy(bsq_stager *s);
+/* Block the host until every host->device copy enqueued by earlier *_host calls on this
+ * stager has finished, i.e. until the caller may overwrite the host buffers it passed. */
+int bsq_stager_sync_copies(bsq_stager *s);
+int bsq_tokenize_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const int64_t *h_offsets,
+                      int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int batch_first,
+                      int kind, void *d_out);
+int bsq_onehot_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const int64_t *h_offsets,
+                    const uint8_t *h_mask, int64_t nseq, int64_t padlen, const bsq_tokenizer *tok,
+                    int kind, void *d_out);
+
+/* ---- misc -------------------------------------------------------------------------- */
+int bsq_abi_version(void);
+const char *bsq_last_error(void);
+/* number of kernel launches issued by this library on the calling thread since the last
+ * reset (bench.py's gpu_launches counter). */
+int64_t bsq_launch_count(void);
+void bsq_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BSQ_H_ */

@@ -1,0 +1,424 @@
+"""GPU parity: the CUDA path, driven through the C ABI (bioseq_b200.capi -> libbsq.so) and
+through the drop-in Python class, against the oracle (oracle/bsq_oracle.c, pinned to the
+reference by tests/test_oracle.py) and the committed golden fixtures.  Bit-exact everywhere:
+raw bytes + shape for arrays, string equality for decoded text."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import bioseq_b200  # noqa: E402
+from bioseq_b200 import capi  # noqa: E402
+from oracle.oracle import OracleTokenizer, alphabet_keys, load_ref  # noqa: E402
+from helpers import sha, sha_strs, assert_same_bits, golden_inputs, gen, gen_mask, as_list  # noqa: E402
+
+TORCH_DT = {0: torch.int8, 1: torch.int16, 2: torch.int32, 3: torch.int64, 4: torch.float32, 5: torch.float64}
+MIX = b"ACDEFGHIKLMNPQRSTVWYacdefghiklmnpqrstvwyXBZOUJ*-NnUu .\x00\x7f\x80\xc3\xff"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests selected but no CUDA device is visible")
+
+
+def to_dev(a):
+    a = np.ascontiguousarray(a)
+    return torch.from_numpy(a.copy()).cuda() if a.size else torch.empty(0, dtype=torch.from_numpy(a).dtype, device="cuda")
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def abi_tokenize(tok, buf, offs, padlen, batch_first, destchar, d_bytes=None):
+    kind = capi.kind_of(destchar)
+    n = len(offs) - 1
+    d_bytes = to_dev(buf) if d_bytes is None else d_bytes
+    d_offs = to_dev(offs)
+    out = torch.empty((n, padlen) if batch_first else (padlen, n), dtype=TORCH_DT[kind], device="cuda")
+    capi.tokenize(0, stream(), d_bytes, d_offs, n, padlen, tok, batch_first, kind, out)
+    torch.cuda.synchronize()
+    return out
+
+
+def abi_onehot(tok, buf, offs, mask, padlen, destchar):
+    kind = capi.kind_of(destchar)
+    n = len(offs) - 1
+    out = torch.empty((padlen, n, tok.alphabet_size), dtype=TORCH_DT[kind], device="cuda")
+    capi.onehot(0, stream(), to_dev(buf), to_dev(offs), None if mask is None else to_dev(mask), n, padlen, tok, kind, out)
+    torch.cuda.synchronize()
+    return out
+
+
+def abi_decode(tok, d_tokens):
+    """decode a 1-D/2-D CUDA tensor through bsq_decode_lengths + bsq_decode_chars."""
+    nd = d_tokens.dim()
+    es = d_tokens.element_size()
+    rows, cols = (1, d_tokens.shape[0]) if nd == 1 else d_tokens.shape
+    rs, cs = (0, d_tokens.stride(0) * es) if nd == 1 else (d_tokens.stride(0) * es, d_tokens.stride(1) * es)
+    d_offs = torch.empty(rows + 1, dtype=torch.int64, device="cuda")
+    total = capi.decode_lengths(0, stream(), d_tokens, es, rows, cols, rs, cs, tok, d_offs)
+    d_chars = torch.empty(total, dtype=torch.uint8, device="cuda")
+    capi.decode_chars(0, stream(), d_tokens, es, rows, cols, rs, cs, tok, d_offs, d_chars)
+    raw = d_chars.cpu().numpy().tobytes()
+    o = d_offs.cpu().numpy()
+    out = [raw[o[i]:o[i + 1]].decode("latin-1") for i in range(rows)]
+    return out[0] if nd == 1 else out
+
+
+def split_mask(mask, offs):
+    return None if mask is None else [mask[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+
+
+# ------------------------------------------------------------------------------------- golden
+def test_golden_kats_python_api(golden):
+    for rec in golden["kats"]:
+        t = bioseq_b200.Tokenizer(rec["key"], **rec["flags"])
+        if rec["op"] == "tokenize":
+            out = t.batch_tokenize(rec["seqs"], padlen=rec["padlen"], **rec["kw"])
+            assert out.is_cuda
+            assert out.cpu().numpy().tolist() == rec["out"], rec
+            assert t.decode_tokens(out) == rec["decoded"], rec
+            assert t.decode_tokens(out.cpu().numpy()) == rec["decoded"], rec
+        else:
+            out = t.batch_onehot_encode(rec["seqs"], padlen=rec["padlen"], **rec["kw"])
+            assert out.cpu().numpy().tolist() == rec["out"], rec
+        assert out.element_size() == np.dtype(rec["dtype"]).itemsize
+
+
+def test_readme_example():
+    # /root/reference/README.md:38-44
+    t = bioseq_b200.pbeos_tokenizers["DNA"]
+    out = t.batch_tokenize(["ACGT", "GGGG"], padlen=7, batch_first=True)
+    assert out.dtype == torch.uint8 and out.device.type == "cuda"
+    assert out.cpu().tolist() == [[4, 0, 1, 2, 3, 5, 6], [4, 2, 2, 2, 2, 5, 6]]
+    assert t.decode_tokens(out) == ["<BOS>ACGT<EOS><PAD>", "<BOS>GGGG<EOS><PAD>"]
+
+
+def test_golden_hashes_all_entry_points(golden):
+    stager = capi.Stager(0)
+    for rec in golden["hashes"]:
+        buf, offs, mask = golden_inputs(rec)
+        n = len(offs) - 1
+        tok = capi.tokenizer(rec["key"], **rec["flags"])
+        pt = bioseq_b200.Tokenizer(rec["key"], **rec["flags"])
+        dc = rec["kw"].get("destchar", "B")
+        kind = capi.kind_of(dc)
+        if rec["op"] == "tokenize":
+            bf = rec["kw"]["batch_first"]
+            a = abi_tokenize(tok, buf, offs, rec["padlen"], bf, dc)
+            b = torch.empty_like(a)
+            stager.tokenize_host(stream(), buf, offs, n, rec["padlen"], tok, bf, kind, b)
+            c = pt.batch_tokenize(as_list(buf, offs), padlen=rec["padlen"], **rec["kw"])
+            d = pt.batch_tokenize_packed(buf, offs, padlen=rec["padlen"], **rec["kw"])
+            e = pt.batch_tokenize_packed(to_dev(buf), to_dev(offs), padlen=rec["padlen"], **rec["kw"])
+            if "decode_sha" in rec:
+                assert sha_strs(abi_decode(tok, a)) == rec["decode_sha"], rec["name"]
+                assert sha_strs(pt.decode_tokens(c)) == rec["decode_sha"], rec["name"]
+        else:
+            a = abi_onehot(tok, buf, offs, mask, rec["padlen"], dc)
+            b = torch.empty_like(a)
+            stager.onehot_host(stream(), buf, offs, mask, n, rec["padlen"], tok, kind, b)
+            kw = dict(rec["kw"])
+            c = pt.batch_onehot_encode(as_list(buf, offs), padlen=rec["padlen"], mask=split_mask(mask, offs), **kw)
+            d = pt.batch_onehot_encode_packed(buf, offs, padlen=rec["padlen"], mask=mask, **kw)
+            e = pt.batch_onehot_encode_packed(to_dev(buf), to_dev(offs), padlen=rec["padlen"],
+                                              mask=None if mask is None else to_dev(mask), **kw)
+        torch.cuda.synchronize()
+        for name, x in (("abi", a), ("staged", b), ("py-list", c), ("py-packed-host", d), ("py-packed-dev", e)):
+            x = x.cpu().numpy()
+            assert list(x.shape) == rec["shape"] and x.itemsize == rec["itemsize"], (rec["name"], name)
+            assert sha(x) == rec["sha"], (rec["name"], name)
+    stager.close()
+
+
+# ------------------------------------------------------------------------------------- differential
+@pytest.mark.parametrize("seed", range(8))
+def test_random_batches_vs_oracle(seed):
+    rng = np.random.default_rng(4200 + seed)
+    keys = alphabet_keys()
+    for trial in range(10):
+        key = keys[int(rng.integers(len(keys)))]
+        flags = dict(bos=bool(rng.integers(2)), eos=bool(rng.integers(2)), padchar=bool(rng.integers(2)))
+        n = int(rng.choice([0, 1, 2, 15, 16, 17, 127, 128, 129, 200, 333]))
+        hi = int(rng.choice([0, 1, 5, 15, 16, 17, 31, 64, 100, 257]))
+        buf, offs = gen(int(rng.integers(1 << 30)), n, 0, hi, MIX)
+        padlen = max(1, hi + 2 + int(rng.choice([0, 0, 1, 3, 14, 16, 30])))
+        dc = "bBhilqfd"[int(rng.integers(8))]
+        bf = bool(rng.integers(2))
+        tok, orc = capi.tokenizer(key, **flags), OracleTokenizer(key, **flags)
+        want = orc.batch_tokenize((buf, offs), padlen=padlen, destchar=dc, batch_first=bf)
+        got = abi_tokenize(tok, buf, offs, padlen, bf, dc)
+        assert_same_bits(want, got.cpu().numpy())
+        if dc not in "fd" and n:
+            assert abi_decode(tok, got) == orc.decode_tokens(want)
+            assert abi_decode(tok, got.t()) == orc.decode_tokens(want.T)
+            assert abi_decode(tok, got[::2, 1::3]) == orc.decode_tokens(want[::2, 1::3])
+            assert abi_decode(tok, got[0]) == orc.decode_tokens(want[0])
+        mask = gen_mask(int(rng.integers(1 << 30)), buf.size, 0.7) if rng.integers(2) else None
+        want = orc.batch_onehot_encode((buf, offs), padlen=padlen, destchar=dc, mask=split_mask(mask, offs))
+        got = abi_onehot(tok, buf, offs, mask, padlen, dc)
+        assert_same_bits(want, got.cpu().numpy())
+
+
+def test_every_alphabet_every_dtype_both_layouts():
+    buf, offs = gen(99, 261, 0, 140, MIX)
+    for key in alphabet_keys():
+        for flags in (dict(), dict(bos=True, eos=True, padchar=True), dict(eos=True), dict(bos=True, padchar=True)):
+            tok, orc = capi.tokenizer(key, **flags), OracleTokenizer(key, **flags)
+            for dc in "bhiqfd":
+                for padlen in (144, 147):
+                    for bf in (True, False):
+                        want = orc.batch_tokenize((buf, offs), padlen=padlen, destchar=dc, batch_first=bf)
+                        assert_same_bits(want, abi_tokenize(tok, buf, offs, padlen, bf, dc).cpu().numpy())
+                want = orc.batch_onehot_encode((buf, offs), padlen=143, destchar=dc)
+                assert_same_bits(want, abi_onehot(tok, buf, offs, None, 143, dc).cpu().numpy())
+
+
+def test_unaligned_device_buffers_and_offset_base():
+    # residues starting at every byte alignment, offsets that do not start at zero
+    buf, offs = gen(5, 300, 0, 70, MIX)
+    tok, orc = capi.tokenizer("PROTEIN", bos=True, eos=True, padchar=True), OracleTokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    want_t = orc.batch_tokenize((buf, offs), padlen=80, batch_first=True)
+    want_s = orc.batch_tokenize((buf, offs), padlen=80, batch_first=False)
+    want_o = orc.batch_onehot_encode((buf, offs), padlen=80, destchar="f")
+    for shift in range(0, 18):
+        big = torch.zeros(buf.size + 64, dtype=torch.uint8, device="cuda")
+        big[shift:shift + buf.size] = to_dev(buf)
+        view = big[shift:]
+        n = len(offs) - 1
+        assert_same_bits(want_t, abi_tokenize(tok, buf, offs, 80, True, "B", d_bytes=view).cpu().numpy())
+        assert_same_bits(want_s, abi_tokenize(tok, buf, offs, 80, False, "B", d_bytes=view).cpu().numpy())
+        # same bytes, but offsets carry a base: pass a pointer moved back by `shift`
+        out = torch.empty((80, n, 23), dtype=torch.float32, device="cuda")
+        capi.onehot(0, stream(), big.data_ptr(), to_dev(offs + shift), None, n, 80, tok, capi.F32, out)
+        torch.cuda.synchronize()
+        assert_same_bits(want_o, out.cpu().numpy())
+
+
+def test_staged_pipeline_multi_chunk_and_reuse():
+    # > 4 MiB of residues so the host-staged path runs several pipeline stages; odd batch size so the
+    # last range is not a whole tile; pageable and pinned sources; back-to-back reuse of one stager.
+    buf, offs = gen(11, 20011, 100, 1000, b"ACDEFGHIKLMNPQRSTVWYX")
+    n = len(offs) - 1
+    assert buf.size > 10 * (1 << 20)
+    orc = OracleTokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    tok = capi.tokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    stager = capi.Stager(0)
+    pin_b = torch.from_numpy(buf.copy()).pin_memory()
+    pin_o = torch.from_numpy(offs.copy()).pin_memory()
+    for bf, dc in ((True, "B"), (False, "B"), (False, "i"), (True, "h")):
+        want = orc.batch_tokenize((buf, offs), padlen=1002, destchar=dc, batch_first=bf)
+        for hb, ho in ((buf, offs), (pin_b, pin_o)):
+            out = torch.empty(want.shape, dtype=TORCH_DT[capi.kind_of(dc)], device="cuda")
+            stager.tokenize_host(stream(), hb, ho, n, 1002, tok, bf, capi.kind_of(dc), out)
+            torch.cuda.synchronize()
+            assert_same_bits(want, out.cpu().numpy())
+    mask = gen_mask(3, buf.size)
+    want = orc.batch_onehot_encode((buf[:offs[3001]], offs[:3002]), padlen=1002, destchar="b", mask=split_mask(mask, offs[:3002]))
+    out = torch.empty(want.shape, dtype=torch.int8, device="cuda")
+    stager.onehot_host(stream(), buf, offs, mask, 3001, 1002, tok, capi.I8, out)
+    torch.cuda.synchronize()
+    assert_same_bits(want, out.cpu().numpy())
+    stager.close()
+
+
+def test_non_default_stream_and_python_list_inputs():
+    t = bioseq_b200.pbeos_tokenizers["protein"]
+    orc = OracleTokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    buf, offs = gen(21, 5000, 0, 400, MIX)
+    seqs = as_list(buf, offs)
+    mixed = [s if i % 3 else bytearray(s) for i, s in enumerate(seqs)]
+    want = orc.batch_tokenize((buf, offs), padlen=402, batch_first=True)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        got = t.batch_tokenize(mixed, padlen=402, batch_first=True, nthreads=4)
+        got2 = t.batch_tokenize(tuple(seqs), padlen=402, batch_first=False)
+    s.synchronize()
+    assert_same_bits(want, got.cpu().numpy())
+    assert_same_bits(want.T, got2.cpu().numpy())
+    # str items are taken as UTF-8 (src/tokenize.h:397)
+    strs = ["ACGT", "ACéGT", "", "中N"]
+    want = OracleTokenizer("DNA", bos=True, padchar=True).batch_tokenize(strs, padlen=9, batch_first=True)
+    got = bioseq_b200.Tokenizer("DNA", bos=True, padchar=True).batch_tokenize(strs, padlen=9, batch_first=True)
+    assert_same_bits(want, got.cpu().numpy())
+
+
+def test_dtypes_returned_by_python_api():
+    t = bioseq_b200.Tokenizer("DNA")
+    want = {"B": torch.uint8, "b": torch.int8, "h": torch.int16, "H": torch.int16, "i": torch.int32, "I": torch.int32,
+            "l": torch.int64, "q": torch.int64, "L": torch.int64, "Q": torch.int64, "f": torch.float32, "d": torch.float64}
+    for dc, dt in want.items():
+        assert t.batch_tokenize(["ACGT"], padlen=5, destchar=dc).dtype == dt
+        assert t.batch_onehot_encode(["ACGT"], padlen=5, destchar=dc).dtype == dt
+    assert t.batch_tokenize(["ACGT"], padlen=5).shape == (5, 1)                      # batch_first defaults to False
+    assert t.batch_tokenize([], padlen=5, batch_first=True).shape == (0, 5)
+    assert t.batch_tokenize([], padlen=5).shape == (5, 0)
+    assert t.batch_onehot_encode([], padlen=5).shape == (5, 0, 4)
+
+
+# ------------------------------------------------------------------------------------- errors
+def test_errors_raise_instead_of_aborting():
+    t = bioseq_b200.Tokenizer("DNA", bos=True, eos=True)
+    with pytest.raises(RuntimeError, match=r"seq len \+ bos \+ eos > padlen: 6, vs padlen 5"):
+        t.batch_tokenize(["AC", "ACGT"], padlen=5, batch_first=True)
+    with pytest.raises(ValueError, match=r"seq len \+ bos \+ eos > padlen: 6, vs padlen 5"):
+        t.batch_onehot_encode(["AC", "ACGT"], padlen=5)
+    offs = np.array([0, 2, 6], dtype=np.int64)
+    buf = np.frombuffer(b"ACACGT", dtype=np.uint8)
+    with pytest.raises(RuntimeError, match=r"seq len \+ bos \+ eos > padlen: 6, vs padlen 5"):
+        t.batch_tokenize_packed(to_dev(buf), to_dev(offs), padlen=5)
+    with pytest.raises(RuntimeError, match=r"seq len \+ bos \+ eos > padlen: 6, vs padlen 5"):
+        t.batch_tokenize_packed(buf, offs, padlen=5)
+    tok = capi.tokenizer("DNA")
+    out = torch.empty(64, dtype=torch.int8, device="cuda")
+    with pytest.raises(ValueError, match="16-byte aligned"):
+        capi.tokenize(0, stream(), to_dev(buf), to_dev(offs), 2, 8, tok, True, 0, out.data_ptr() + 1)
+    with pytest.raises(ValueError, match="batch tokenize requires padlen is provded."):
+        capi.tokenize(0, stream(), to_dev(buf), to_dev(offs), 2, 0, tok, True, 0, out)
+
+
+def test_decode_errors_and_itemsizes():
+    t = bioseq_b200.pbeos_tokenizers["PROTEIN"]
+    orc = OracleTokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    base = np.array([[20, 0, 5, 19, 21, 22, 22], [20, 21, 22, 22, 22, 22, 22]])
+    for dt in (np.uint8, np.int8, np.int16, np.int32, np.int64, np.uint16, np.uint32, np.uint64):
+        x = base.astype(dt)
+        assert t.decode_tokens(x) == orc.decode_tokens(x)
+        assert t.decode_tokens(x[1]) == orc.decode_tokens(x[1])
+        if dt in (np.uint8, np.int8, np.int16, np.int32, np.int64):
+            assert t.decode_tokens(torch.from_numpy(x).cuda()) == orc.decode_tokens(x)
+            assert t.decode_tokens(torch.from_numpy(x)) == orc.decode_tokens(x)
+    for bad, dt in ((23, np.uint8), (-1, np.int8), (-1, np.int16), (300, np.int32), (1.0, np.float32), (70000, np.int64)):
+        x = np.array([[0, 1], [0, bad], [bad, 0]], dtype=dt)
+        with pytest.raises(RuntimeError) as e1:
+            orc.decode_tokens(x)
+        with pytest.raises(RuntimeError) as e2:
+            t.decode_tokens(x)
+        assert str(e1.value) == str(e2.value)
+    for dt in (np.int32, np.int64):                     # -1 -> "\0" entry (src/tokenize.h:83-88)
+        assert t.decode_tokens(np.array([0, -1, 3], dtype=dt)) == "A\x00E"
+    with pytest.raises(ValueError, match="Currently supported: 1 or 2 dimensions"):
+        t.decode_tokens(np.zeros((2, 2, 2), dtype=np.uint8))
+    assert t.decode_tokens(np.zeros((0, 4), dtype=np.uint8)) == []
+    assert t.decode_tokens(np.zeros((3, 0), dtype=np.uint8)) == ["", "", ""]
+    assert t.decode_tokens(np.zeros(0, dtype=np.uint8)) == ""
+
+
+def test_single_sequence_onehot_encode():
+    R = load_ref()
+    if R is None:
+        pytest.skip("oracle/_ref not present")
+    for key, flags in (("DNA", {}), ("DNA", dict(bos=True, eos=True, padchar=True)), ("PROTEIN", dict(eos=True, padchar=True))):
+        ref_t, t = R.Tokenizer(key, **flags), bioseq_b200.Tokenizer(key, **flags)
+        for seq in ("ACGT", "", "ACGTACGTAC", b"GATTACA", bytearray(b"CCGG")):
+            for padlen in (0, 3, 12):
+                if padlen and len(seq) > padlen:
+                    with pytest.raises(RuntimeError, match="padlen is too short"):
+                        t.onehot_encode(seq, padlen)
+                    continue
+                for dc in ("f", "B", "H", "i", "d"):
+                    want = ref_t.onehot_encode(seq, padlen, dc)
+                    got = t.onehot_encode(seq, padlen, dc).cpu().numpy()
+                    assert_same_bits(want, got)
+                assert_same_bits(ref_t.onehot_encode(seq, padlen), t.onehot_encode(seq, padlen).cpu().numpy())
+
+
+# ------------------------------------------------------------------------------------- BASELINE.json sizes
+def test_config1_dna_full_size():
+    buf, offs = gen(101, 4096, 1000, 1000, b"ACGT")
+    tok, orc = capi.tokenizer("DNA"), OracleTokenizer("DNA")
+    want = orc.batch_tokenize((buf, offs), padlen=1024, batch_first=True)
+    got = abi_tokenize(tok, buf, offs, 1024, True, "B")
+    assert_same_bits(want, got.cpu().numpy())
+    assert_same_bits(want.T, abi_tokenize(tok, buf, offs, 1024, False, "B").cpu().numpy())
+
+
+@pytest.mark.parametrize("hi,padlen", [(1022, 1024), (1024, 1026)])
+def test_config2_protein_ragged_full_size(hi, padlen):
+    buf, offs = gen(102, 65536, 50, hi, b"ACDEFGHIKLMNPQRSTVWY")
+    tok = capi.tokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    orc = OracleTokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    want = orc.batch_tokenize((buf, offs), padlen=padlen, batch_first=True)
+    got = abi_tokenize(tok, buf, offs, padlen, True, "B")
+    assert_same_bits(want, got.cpu().numpy())
+    # properties that do not need the oracle: row structure and a checksum of checksums
+    g = got.long()
+    lens = torch.from_numpy(np.diff(offs)).cuda()
+    assert bool((g[:, 0] == 20).all())
+    assert bool((g.gather(1, (lens + 1).unsqueeze(1)).squeeze(1) == 21).all())
+    assert bool(((g == 22).sum(1) == padlen - lens - 2).all())
+    assert int(g.sum()) == int(want.astype(np.int64).sum())
+    got_sf = abi_tokenize(tok, buf, offs, padlen, False, "B")
+    assert torch.equal(got_sf, got.t())
+    dec = abi_decode(tok, got[:2048])
+    assert dec == orc.decode_tokens(want[:2048])
+
+
+def test_config3_onehot_f32_full_size():
+    buf, offs = gen(103, 16384, 4096, 4096, b"ACGT")
+    tok, orc = capi.tokenizer("DNA"), OracleTokenizer("DNA")
+    got = abi_onehot(tok, buf, offs, None, 4096, "f")          # (4096, 16384, 4) float32, 1 GiB
+    assert got.shape == (4096, 16384, 4)
+    toks = abi_tokenize(tok, buf, offs, 4096, False, "B")
+    assert torch.equal(got.argmax(2).to(torch.uint8), toks)     # one-hot <-> tokens
+    assert bool((got.sum(2) == 1).all())
+    assert float(got.sum()) == 4096 * 16384
+    want = orc.batch_onehot_encode((buf[:offs[2048]], offs[:2049]), padlen=4096, destchar="f")
+    assert_same_bits(want, got[:, :2048].contiguous().cpu().numpy())
+    del got
+    torch.cuda.empty_cache()
+
+
+def test_config4_reduced_alphabets_roundtrip():
+    buf, offs = gen(104, 200_000, 50, 1024, b"ACDEFGHIKLMNPQRSTVWY")
+    rng = np.random.default_rng(4)
+    noisy = buf.copy()                                            # 5 % lower-case / invalid residues
+    idx = rng.random(buf.size) < 0.05
+    noisy[idx] = np.frombuffer(b"acdefghiklmnpqrstvwyXBZOU*-", dtype=np.uint8)[rng.integers(0, 27, int(idx.sum()))]
+    d_bytes, d_noisy = to_dev(buf), to_dev(noisy)
+    n = len(offs) - 1
+    for key in ("SEB6", "SEB8", "SEB10", "SEB14", "SEV10", "MURPHY", "LIA10", "LIB10", "DAYHOFF"):
+        for flags, padlen in ((dict(padchar=True), 1024), (dict(bos=True, eos=True, padchar=True), 1026)):
+            tok, orc = capi.tokenizer(key, **flags), OracleTokenizer(key, **flags)
+            got = abi_tokenize(tok, buf, offs, padlen, True, "B", d_bytes=d_bytes)
+            # decode o tokenize maps every residue to its group representative (not the identity)
+            rep = np.zeros(256, dtype=np.uint8)
+            first = {}
+            for b in range(256):
+                first.setdefault(int(orc.lut[b]), b)
+            for b in range(256):
+                rep[b] = first[int(orc.lut[b])] if orc.lut[b] >= 0 else first[0]
+            sub = slice(0, 20000)
+            dec = abi_decode(tok, got[sub])
+            want_tok = orc.batch_tokenize((buf[:offs[20000]], offs[:20001]), padlen=padlen, batch_first=True)
+            assert_same_bits(want_tok, got[sub].cpu().numpy())
+            assert dec == orc.decode_tokens(want_tok)
+            bos = "<BOS>" if flags.get("bos") else ""
+            eos = "<EOS>" if flags.get("eos") else ""
+            for i in (0, 1, 19999):
+                body = rep[buf[offs[i]:offs[i + 1]]].tobytes().decode()
+                npad = padlen - len(body) - (len(bos) > 0) - (len(eos) > 0)
+                assert dec[i] == bos + body + eos + "<PAD>" * npad
+            if key in ("SEB10", "DAYHOFF"):
+                gn = abi_tokenize(tok, noisy, offs, padlen, True, "B", d_bytes=d_noisy)
+                wn = orc.batch_tokenize((noisy[:offs[20000]], offs[:20001]), padlen=padlen, batch_first=True)
+                assert_same_bits(wn, gn[sub].cpu().numpy())
+                # whole-batch checksum against the oracle
+                wfull = orc.batch_tokenize((noisy, offs), padlen=padlen, batch_first=True)
+                assert int(gn.long().sum()) == int(wfull.astype(np.int64).sum())
+                assert_same_bits(wfull, gn.cpu().numpy())
+    del d_bytes, d_noisy
+    torch.cuda.empty_cache()
+
+
+def test_python_decode_many_rows():
+    t = bioseq_b200.pbeos_tokenizers["SEB10"]
+    orc = OracleTokenizer("SEB10", bos=True, eos=True, padchar=True)
+    buf, offs = gen(44, 50_000, 1, 300, b"ACDEFGHIKLMNPQRSTVWY")
+    toks = t.batch_tokenize_packed(buf, offs, padlen=304, batch_first=True)
+    want = orc.decode_tokens(orc.batch_tokenize((buf, offs), padlen=304, batch_first=True))
+    assert t.decode_tokens(toks) == want
+    assert t.decode_tokens(toks.to(torch.int32)) == want
