@@ -206,7 +206,7 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     # clocks ramp from idle: keep the GPU busy for a moment before anything is timed
-    t_end = time.perf_counter() + 0.5
+    t_end = time.perf_counter() + (0.5 if "extra" in args.sections else 0.0)
     i = 0
     while time.perf_counter() < t_end:
         step(i); i += 1
@@ -245,8 +245,9 @@ def run_ours(args):
         last.copy_(out[NSEQ - 1], non_blocking=True)
         return out
 
-    e2e_steps = max(3, min(args.steps, 50))
-    for i in range(3):
+    sections = set(args.sections.split(","))
+    e2e_steps = max(3, min(args.steps, 50)) if "e2e" in sections else 1
+    for i in range(3 if "e2e" in sections else 0):
         e2e_step(i)
     barrier()
     t0 = time.perf_counter()
@@ -272,9 +273,10 @@ def run_ours(args):
     cpu = None
     parity = None
     if rank == 0:
-        extra = secondary_measurements(torch, capi, L, dev, st)
+        if "extra" in sections:
+            extra = secondary_measurements(torch, capi, L, dev, st)
         clocks = sampler.stop()
-        if world == 1:
+        if world == 1 and "cpu" in sections:
             cpu, ref_out = cpu_arm(sets[0]["buf"], sets[0]["offs"], steps=10, warmup=1, budget_s=20.0)
             step(0)
             torch.cuda.synchronize()
@@ -419,6 +421,8 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sections", default="value,e2e,extra,cpu",
+                    help="comma list of measurement sections to run (profiling runs use --sections value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -1,7 +1,8 @@
 // sm_100a kernels + launchers for batch_tokenize / batch_onehot_encode / decode_tokens.
 //
-//   K1 tokenize_bf_kernel   (nseq, padlen) batch-first tokens.  One thread = 16 output bytes
-//                           = one st.global.v4; BOS/EOS/PAD fused; ragged tails skip all loads.
+//   K1 tokenize_rows_kernel (nseq, padlen) batch-first tokens.  One warp per row, one lane =
+//                           16 output bytes = one st.global.v4 per iteration; BOS/EOS/PAD fused;
+//                           ragged tails skip all loads.
 //   K2 seqfirst_kernel<..,false>  (padlen, nseq) tokens: 128 seq x 128 pos shared-memory tile,
 //                           coalesced reads along each sequence, coalesced stores along batch.
 //   K3 seqfirst_kernel<..,true>   (padlen, nseq, C) one-hot: same tile, then every warp streams
@@ -32,15 +33,99 @@ __device__ __forceinline__ T cast_id(int32_t v) {
 }
 
 // ------------------------------------------------------------------------------------------
-// K1: batch-first tokens.  The output is treated as a flat array of nseq*padlen elements;
-// thread g owns elements [g*TPT, (g+1)*TPT) = 16 bytes.  When that range stays inside one
-// row and T is one byte the vector path (tokens16) is used, otherwise a per-element loop
-// that may cross into the next row (only when padlen*sizeof(T) is not a multiple of 16).
+// K1: batch-first tokens, one warp per row (or per group of rows when padlen < 512).
+//
+// Lane `sub` of a row owns the 16-byte output chunks sub, sub+L, sub+2L, ... of that row
+// (L = lanes per row), so a warp streams 512 contiguous output bytes per iteration.  All
+// per-row state -- offsets, length, source alignment -- is loaded/derived once per row and is
+// warp-uniform when L = 32, which keeps the realignment switch and the pad-only shortcut
+// free of divergence.  Chunks are aligned to 16 bytes in the *flat* output, so rows whose
+// padlen is not a multiple of 16 still use vector stores; only the (at most two) partial
+// chunks at the ends of such a row fall back to byte stores.
+//
+// Element types wider than a byte go through a per-warp 512-byte shared-memory stage so that
+// every st.global.v4 of the expanded values is contiguous across the warp.
 // ------------------------------------------------------------------------------------------
 template <typename T>
+__device__ __forceinline__ uint4 expand_vec(const uint8_t *codes, const Expand &ex) {
+    constexpr int EPV = 16 / sizeof(T);
+    T vals[EPV];
+#pragma unroll
+    for (int j = 0; j < EPV; ++j) vals[j] = cast_id<T>(expand_code(codes[j], ex));
+    return *reinterpret_cast<const uint4 *>(vals);
+}
+
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-tokenize_bf_kernel(SeqView v, int64_t nseq, int padlen, FastDiv div_padlen, LutParam lutp, Specials sp,
-                   Expand ex, T *__restrict__ out) {
+tokenize_rows_kernel(SeqView v, int64_t nseq, int padlen, int lanes_log2, LutParam lutp, Specials sp, Expand ex,
+                     T *__restrict__ out) {
+    constexpr int S = sizeof(T);
+    __shared__ __align__(16) uint8_t lut[256];
+    __shared__ __align__(16) uint8_t stage[S == 1 ? 16 : (kThreads / 32) * 512];
+    load_lut(lut, lutp);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int L = 1 << lanes_log2;
+    const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (kThreads / 32) + warp) * (32 >> lanes_log2);
+    const int64_t row = row0 + (lane >> lanes_log2);
+    const int sub = lane & (L - 1);
+    const bool row_ok = row < nseq;
+    int64_t start = 0;
+    int len = 0;
+    if (row_ok) {
+        start = __ldg(v.offs + row);
+        len = static_cast<int>(__ldg(v.offs + row + 1) - start);
+    }
+    const RowSrc rs = make_rowsrc(v.bytes, start, sp.bos, len);
+    const int npos = sp.bos + len + sp.eos;
+    const int64_t rowbase = row * padlen;  // flat element index of column 0
+    const uint4 padv = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
+
+    if (S == 1) {
+        const int r = static_cast<int>(rowbase & 15);  // misalignment of the row in the flat output
+        if (!row_ok) return;
+        uint8_t *orow = reinterpret_cast<uint8_t *>(out) + rowbase;
+        for (int c0 = 16 * sub - r; c0 < padlen; c0 += 16 * L) {
+            const uint4 codes = c0 >= npos ? padv : tokens16(rs, nullptr, len, c0, sp, lut);
+            if (c0 >= 0 && c0 + 16 <= padlen) {
+                __stcs(reinterpret_cast<uint4 *>(orow + c0), codes);
+            } else {  // partial chunk at either end of an unaligned row
+                const uint32_t w[4] = {codes.x, codes.y, codes.z, codes.w};
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (c0 + j >= 0 && c0 + j < padlen) orow[c0 + j] = static_cast<uint8_t>(w[j >> 2] >> (8 * (j & 3)));
+            }
+        }
+    } else {
+        // rows are 16-byte aligned here (the host checked padlen * sizeof(T) % 16 == 0)
+        constexpr int EPV = 16 / S;
+        uint8_t *wstage = stage + warp * 512;
+        for (int cb = 0; cb < padlen; cb += 16 * L) {  // warp-uniform trip count
+            const int c0 = cb + 16 * sub;
+            uint4 codes = padv;
+            if (row_ok && c0 < padlen && c0 < npos) codes = tokens16(rs, nullptr, len, c0, sp, lut);
+            *reinterpret_cast<uint4 *>(wstage + 16 * lane) = codes;
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < S; ++q) {
+                const int e = EPV * (lane + 32 * q);  // first of this lane's EPV codes within the 512 staged
+                const int src_lane = e >> 4;
+                const int64_t srow = row0 + (src_lane >> lanes_log2);
+                const int scol = cb + 16 * (src_lane & (L - 1)) + (e & 15);
+                if (srow < nseq && scol < padlen)
+                    __stcs(reinterpret_cast<uint4 *>(out + srow * padlen + scol), expand_vec<T>(wstage + e, ex));
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// Fallback for wide element types whose rows are not 16-byte aligned (padlen * sizeof(T) % 16
+// != 0): flat element indexing, one 16-byte output vector per thread, per-element tokens.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+tokenize_flat_kernel(SeqView v, int64_t nseq, int padlen, FastDiv div_padlen, LutParam lutp, Specials sp,
+                     Expand ex, T *__restrict__ out) {
     constexpr int TPT = 16 / sizeof(T);
     __shared__ __align__(16) uint8_t lut[256];
     __shared__ int64_t s_row0;
@@ -60,21 +145,8 @@ tokenize_bf_kernel(SeqView v, int64_t nseq, int padlen, FastDiv div_padlen, LutP
     const int64_t total = nseq * static_cast<int64_t>(padlen);
     const int64_t f = (static_cast<int64_t>(blockIdx.x) * kThreads + threadIdx.x) * TPT;
     if (f >= total) return;
-
     int64_t start = __ldg(v.offs + row);
     int len = static_cast<int>(__ldg(v.offs + row + 1) - start);
-
-    if (sizeof(T) == 1 && c + 16 <= padlen) {
-        uint4 codes;
-        if (c >= sp.bos + len + sp.eos) {
-            codes = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
-        } else {
-            codes = tokens16(v, start, len, c, sp, lut);
-        }
-        __stcs(reinterpret_cast<uint4 *>(out + f), codes);
-        return;
-    }
-
     T vals[TPT];
     int nvalid = TPT;
 #pragma unroll
@@ -90,7 +162,7 @@ tokenize_bf_kernel(SeqView v, int64_t nseq, int padlen, FastDiv div_padlen, LutP
             }
         }
         const uint32_t code = row < nseq ? token_at(v, start, len, c, sp, lut) : 0u;
-        vals[j] = sizeof(T) == 1 ? static_cast<T>(code) : cast_id<T>(expand_code(code, ex));
+        vals[j] = cast_id<T>(expand_code(code, ex));
         ++c;
     }
     if (nvalid == TPT) {
@@ -159,8 +231,17 @@ seqfirst_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, LutParam lutp, 
             const int64_t start = __ldg(v.offs + i0 + il);
             const int len = static_cast<int>(__ldg(v.offs + i0 + il + 1) - start);
             uint4 codes;
-            if (c0 >= sp.bos + len + sp.eos) codes = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
-            else codes = tokens16(v, start, len, c0, sp, lut);
+            if (c0 >= sp.bos + len + sp.eos) {
+                codes = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
+            } else {
+                const RowSrc rs = make_rowsrc(v.bytes, start, sp.bos, len);
+                if (ONEHOT && v.mask != nullptr) {
+                    const RowSrc ms = make_rowsrc(v.mask, start, sp.bos, len);
+                    codes = tokens16(rs, &ms, len, c0, sp, lut);
+                } else {
+                    codes = tokens16(rs, nullptr, len, c0, sp, lut);
+                }
+            }
             uint32_t *dst = reinterpret_cast<uint32_t *>(tile + il * kTilePitch + 16 * q);
             dst[0] = codes.x; dst[1] = codes.y; dst[2] = codes.z; dst[3] = codes.w;
         }
@@ -451,15 +532,27 @@ int check_common(int device, int64_t nseq, int64_t padlen, const bsq_tokenizer *
 
 template <typename T>
 int launch_bf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t /*ld*/, int64_t padlen, const bsq_tokenizer &tok, void *d_out) {
-    constexpr int TPT = 16 / sizeof(T);
+    // one-byte tokens: the codes are the output bytes (ids wrap to 8 bits like the reference's
+    // int -> int8 store); wider types expand codes through Expand.
     const Prepared p = prepare(tok, sizeof(T) == 1 ? 0 : 1);
-    const int64_t total = nseq * padlen;
-    const int64_t per_block = static_cast<int64_t>(kThreads) * TPT;
-    const int64_t blocks = (total + per_block - 1) / per_block;
-    if (blocks > 0x7fffffffll) return fail(BSQ_ERR_ARG, "batch too large for one launch");
-    tokenize_bf_kernel<T><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(
-        v, nseq, static_cast<int>(padlen), make_fastdiv(static_cast<uint32_t>(padlen)), p.lut, p.sp, p.ex,
-        static_cast<T *>(d_out));
+    if (sizeof(T) == 1 || (padlen * sizeof(T)) % 16 == 0) {
+        int lanes_log2 = 0;  // lanes per row: smallest power of two covering the row, at most a warp
+        while (lanes_log2 < 5 && (16ll << lanes_log2) < padlen + (sizeof(T) == 1 ? 15 : 0)) ++lanes_log2;
+        const int64_t rows_per_block = static_cast<int64_t>(kThreads / 32) * (32 >> lanes_log2);
+        const int64_t blocks = (nseq + rows_per_block - 1) / rows_per_block;
+        if (blocks > 0x7fffffffll) return fail(BSQ_ERR_ARG, "batch too large for one launch");
+        tokenize_rows_kernel<T><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(
+            v, nseq, static_cast<int>(padlen), lanes_log2, p.lut, p.sp, p.ex, static_cast<T *>(d_out));
+    } else {
+        constexpr int TPT = 16 / sizeof(T);
+        const int64_t total = nseq * padlen;
+        const int64_t per_block = static_cast<int64_t>(kThreads) * TPT;
+        const int64_t blocks = (total + per_block - 1) / per_block;
+        if (blocks > 0x7fffffffll) return fail(BSQ_ERR_ARG, "batch too large for one launch");
+        tokenize_flat_kernel<T><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(
+            v, nseq, static_cast<int>(padlen), make_fastdiv(static_cast<uint32_t>(padlen)), p.lut, p.sp, p.ex,
+            static_cast<T *>(d_out));
+    }
     count_launch();
     BSQ_CUDA_TRY(cudaGetLastError());
     return BSQ_OK;

@@ -5,9 +5,10 @@
 //   * a 256-entry byte LUT staged in shared memory (ASCII inputs never bank-conflict:
 //     bytes 0..127 live in 32 distinct 4-byte words),
 //   * `tokens16`: 16 consecutive output codes of one row -- two 16-byte aligned
-//     ld.global.nc loads of the packed residues, an in-register realignment (sequence
-//     starts are arbitrary byte offsets and BOS shifts the row by one), 16 LUT look-ups,
-//     and BOS / EOS / PAD synthesised by byte masks on the boundary chunks only,
+//     ld.global.nc loads of the packed residues (clamped to the words that hold the row),
+//     an in-register realignment (sequence starts are arbitrary byte offsets and BOS shifts
+//     the row by one), 16 LUT look-ups, and BOS / EOS / PAD synthesised by byte masks on the
+//     boundary chunks only,
 //   * a scalar `token_at` for ragged edges and multi-byte element types.
 #pragma once
 #include <cuda_runtime.h>
@@ -67,77 +68,110 @@ __device__ __forceinline__ void load_lut(uint8_t *lut_smem, const LutParam &p) {
     if (threadIdx.x < 64) reinterpret_cast<uint32_t *>(lut_smem)[threadIdx.x] = p.w[threadIdx.x];
 }
 
-// Mask of the bytes j < k of a 16-byte chunk that fall in 32-bit word `w` (j = 4w..4w+3).
+// Mask of the bytes j < k of a 16-byte chunk that fall in 32-bit word `w` (j = 4w..4w+3):
+// the high word of (0:ffffffff) << clamp(8*(k-4w), 0, 32) -- one VIADDMNMX + one SHF.L.W.
+// k must already be clamped to [0, 16].
 __device__ __forceinline__ uint32_t lt_mask(int k, int w) {
-    const int kk = min(max(k - 4 * w, 0), 4);
-    return kk >= 4 ? 0xffffffffu : ((1u << (8 * kk)) - 1u);
+    return __funnelshift_lc(0xffffffffu, 0u, static_cast<uint32_t>(max(8 * k - 32 * w, 0)));
 }
+__device__ __forceinline__ int clamp16(int k) { return min(max(k, 0), 16); }
 
+// Four LUT look-ups: byte extraction with PRMT (one ALU op each), LDS.U8, and the re-packing as
+// integer multiply-adds so it lands on the FMA pipe instead of the (half-rate) ALU pipe.
 __device__ __forceinline__ uint32_t translate4(uint32_t x, const uint8_t *lut) {
-    const uint32_t b0 = lut[x & 0xffu];
-    const uint32_t b1 = lut[(x >> 8) & 0xffu];
-    const uint32_t b2 = lut[(x >> 16) & 0xffu];
-    const uint32_t b3 = lut[x >> 24];
-    return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+    const uint32_t b0 = lut[__byte_perm(x, 0u, 0x4440)];
+    const uint32_t b1 = lut[__byte_perm(x, 0u, 0x4441)];
+    const uint32_t b2 = lut[__byte_perm(x, 0u, 0x4442)];
+    const uint32_t b3 = lut[__byte_perm(x, 0u, 0x4443)];
+    return b0 + b1 * 0x100u + b2 * 0x10000u + b3 * 0x1000000u;
 }
 
-// The 16 bytes base[first .. first+16) as four little-endian words, fetched with at most
-// two aligned 16-byte loads.  Only aligned words that overlap the needed index range
-// [lo, hi) are touched, so nothing outside the pages holding valid bytes is ever read
-// (first may be lo-1 when a BOS column precedes the residues).
-__device__ __forceinline__ void fetch16(const uint8_t *base, int64_t first, int64_t lo, int64_t hi, uint32_t out[4]) {
-    const uintptr_t a = reinterpret_cast<uintptr_t>(base) + first;
-    const uintptr_t a0 = a & ~static_cast<uintptr_t>(15);
-    const uintptr_t need_lo = reinterpret_cast<uintptr_t>(base) + lo;
-    const uintptr_t need_hi = reinterpret_cast<uintptr_t>(base) + hi;
-    uint4 v0 = make_uint4(0, 0, 0, 0), v1 = make_uint4(0, 0, 0, 0);
-    if (a0 + 16 > need_lo) v0 = ldg16(a0);
-    if (a0 + 16 < need_hi) v1 = ldg16(a0 + 16);
+// Where the bytes of one row live: column c of the row (BOS shift included) is al[off + c].
+// `al` is 16-byte aligned; fw/lw are the byte offsets (multiples of 16, relative to al) of the
+// first and last aligned 16-byte words that hold a residue of this row.  Loads are clamped to
+// [fw, lw], so nothing outside words containing valid residues is ever touched, whatever
+// column range is asked for (a clamped word only ever replaces bytes that are masked out).
+struct RowSrc {
+    const uint8_t *al;
+    int off, fw, lw;
+};
+__device__ __forceinline__ RowSrc make_rowsrc(const uint8_t *base, int64_t start, int bos, int len) {
+    const uint8_t *src = base + start - bos;
+    RowSrc r;
+    r.off = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
+    r.al = src - r.off;
+    r.fw = (r.off + bos) & ~15;
+    r.lw = (r.off + bos + len - 1) & ~15;
+    return r;
+}
+
+// The 16 bytes of columns c0 .. c0+15 as four little-endian words: two aligned 16-byte
+// ld.global.nc loads + a funnel-shift realignment.  The byte shift (off + c0) & 15 is the same
+// for every chunk of a row, so when a warp works on one row the switch is warp-uniform.
+__device__ __forceinline__ void fetch16(const RowSrc &rs, int c0, uint32_t out[4]) {
+    const int a = rs.off + c0;
+    const int a0 = a & ~15;
     const uint32_t s = static_cast<uint32_t>(a) & 15u;
-    uint32_t x0 = v0.x, x1 = v0.y, x2 = v0.z, x3 = v0.w, x4 = v1.x, x5 = v1.y;
-    if (s & 8u) { x0 = x2; x1 = x3; x2 = v1.x; x3 = v1.y; x4 = v1.z; x5 = v1.w; }
-    if (s & 4u) { x0 = x1; x1 = x2; x2 = x3; x3 = x4; x4 = x5; }
+    const uint4 v0 = ldg16(reinterpret_cast<uintptr_t>(rs.al + min(max(a0, rs.fw), rs.lw)));
+    uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
+    if (s != 0u) v1 = ldg16(reinterpret_cast<uintptr_t>(rs.al + min(max(a0 + 16, rs.fw), rs.lw)));
     const uint32_t sh = (s & 3u) * 8u;
-    out[0] = __funnelshift_r(x0, x1, sh);
-    out[1] = __funnelshift_r(x1, x2, sh);
-    out[2] = __funnelshift_r(x2, x3, sh);
-    out[3] = __funnelshift_r(x3, x4, sh);
+    switch (s >> 2) {
+        case 0:
+            out[0] = __funnelshift_r(v0.x, v0.y, sh); out[1] = __funnelshift_r(v0.y, v0.z, sh);
+            out[2] = __funnelshift_r(v0.z, v0.w, sh); out[3] = __funnelshift_r(v0.w, v1.x, sh);
+            break;
+        case 1:
+            out[0] = __funnelshift_r(v0.y, v0.z, sh); out[1] = __funnelshift_r(v0.z, v0.w, sh);
+            out[2] = __funnelshift_r(v0.w, v1.x, sh); out[3] = __funnelshift_r(v1.x, v1.y, sh);
+            break;
+        case 2:
+            out[0] = __funnelshift_r(v0.z, v0.w, sh); out[1] = __funnelshift_r(v0.w, v1.x, sh);
+            out[2] = __funnelshift_r(v1.x, v1.y, sh); out[3] = __funnelshift_r(v1.y, v1.z, sh);
+            break;
+        default:
+            out[0] = __funnelshift_r(v0.w, v1.x, sh); out[1] = __funnelshift_r(v1.x, v1.y, sh);
+            out[2] = __funnelshift_r(v1.y, v1.z, sh); out[3] = __funnelshift_r(v1.z, v1.w, sh);
+            break;
+    }
 }
 
-// Codes of columns c0 .. c0+15 (c0 >= 0) of the row whose residues are
-// bytes[start .. start+len).  Column layout (src/tokenize.h:460-478):
+// Codes of columns c0 .. c0+15 (c0 may be negative or run past padlen; such bytes are
+// don't-care) of a row with `len` residues.  Column layout (src/tokenize.h:460-478):
 //   [0, bos)            BOS
 //   [bos, bos+len)      lut[residue]
 //   bos+len             EOS (if eos)
 //   beyond              pad code
-// Columns past the row's padlen come out as pad and are ignored by the callers.
-__device__ __forceinline__ uint4 tokens16(const SeqView &v, int64_t start, int len, int c0,
+// `ms` is the row's mask source (one-hot only) or nullptr.
+__device__ __forceinline__ uint4 tokens16(const RowSrc &rs, const RowSrc *ms, int len, int c0,
                                           const Specials &sp, const uint8_t *lut) {
-    const int r0 = c0 - sp.bos;  // residue index of the chunk's first column (may be -1)
-    const int lo = max(r0, 0), hi = min(r0 + 16, len);
+    const int r0 = c0 - sp.bos;  // residue index of the chunk's first column
     uint32_t t[4] = {0u, 0u, 0u, 0u};
-    if (hi > lo) {
+    if (min(r0 + 16, len) > max(r0, 0)) {
         uint32_t raw[4];
-        fetch16(v.bytes, start + r0, start + lo, start + hi, raw);
+        fetch16(rs, c0, raw);
 #pragma unroll
         for (int w = 0; w < 4; ++w) t[w] = translate4(raw[w], lut);
-        if (v.mask != nullptr) {  // one-hot only: masked-out residues become kCodeInvalid
+        if (ms != nullptr) {  // masked-out residues become kCodeInvalid (0xFF)
             uint32_t m[4];
-            fetch16(v.mask, start + r0, start + lo, start + hi, m);
+            fetch16(*ms, c0, m);
 #pragma unroll
             for (int w = 0; w < 4; ++w) t[w] |= __vcmpeq4(m[w], 0u);
         }
     }
     const int n = sp.bos + len;  // column of EOS
-    if (c0 < sp.bos || c0 + 16 > n) {
-        const int kr0 = sp.bos - c0, kr1 = n - c0;
+    if (c0 + 16 > n || c0 < 0) {
+        // chunk holds the end of the row (EOS / pad) or starts before column 0 (unaligned rows)
+        const int kr0 = clamp16(sp.bos - c0), kr1 = clamp16(n - c0), kr2 = clamp16(n + sp.eos - c0);
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
             const uint32_t m_bos = lt_mask(kr0, w);
             const uint32_t m_res = lt_mask(kr1, w);
-            const uint32_t m_eos = lt_mask(kr1 + sp.eos, w);
+            const uint32_t m_eos = lt_mask(kr2, w);
             t[w] = (sp.bos_w & m_bos) | (t[w] & m_res & ~m_bos) | (sp.eos_w & m_eos & ~m_res) | (sp.pad_w & ~m_eos);
         }
+    } else if (c0 < sp.bos) {
+        t[0] = __byte_perm(t[0], sp.bos_w, 0x3214);  // c0 == 0: column 0 is BOS, the rest are residues
     }
     return make_uint4(t[0], t[1], t[2], t[3]);
 }
