@@ -3,11 +3,13 @@
 //   K1 tokenize_rows_kernel (nseq, padlen) batch-first tokens.  One warp per row, one lane =
 //                           16 output bytes = one st.global.v4 per iteration; BOS/EOS/PAD fused;
 //                           ragged tails skip all loads.
-//   K2 seqfirst_kernel<..,false>  (padlen, nseq) tokens: 128 seq x 128 pos shared-memory tile,
-//                           coalesced reads along each sequence, coalesced stores along batch.
-//   K3 seqfirst_kernel<..,true>   (padlen, nseq, C) one-hot: same tile, then every warp streams
-//                           the contiguous C*sizeof(T)-expanded run of one position with
-//                           16-byte stores, zeros included (no memset pass).
+//   K2 seqfirst_kernel<..,kTok*>  (padlen, nseq) tokens: 128 seq x 128 pos shared-memory tile,
+//                           coalesced reads along each sequence; one-byte tokens leave through
+//                           register 4x4 byte transposes and 16-byte stores along the batch.
+//   K3 seqfirst_kernel<..,kOneHot> (padlen, nseq, C) one-hot: same tile, then every (pos, seq)
+//                           row is written with one 4/8/16-byte store when C*sizeof(T) allows,
+//                           else the run is zero-filled with 16-byte stores and the ones are
+//                           scattered after a barrier (no separate memset pass).
 //   K4 decode_*             tokens -> characters (two passes: lengths+validation, chars).
 //   K0 maxlen_kernel        length validation for device-resident offsets.
 //
@@ -55,24 +57,39 @@ __device__ __forceinline__ uint4 expand_vec(const uint8_t *codes, const Expand &
     return *reinterpret_cast<const uint4 *>(vals);
 }
 
-template <typename T>
+// ROWWARP: a whole warp works on one row (padlen > 256): the row index is warp-uniform, and the
+//          row's offsets are broadcast from lane 0 so that the per-row arithmetic can live in the
+//          uniform datapath.  Otherwise 32 >> lanes_log2 rows share a warp.
+// ALIGNED: padlen % 16 == 0, i.e. every row starts 16-byte aligned in the output and has no
+//          partial chunk (always true for the wide element types handled here).
+template <typename T, bool ROWWARP, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads)
 tokenize_rows_kernel(SeqView v, int64_t nseq, int padlen, int lanes_log2, LutParam lutp, Specials sp, Expand ex,
                      T *__restrict__ out) {
     constexpr int S = sizeof(T);
     __shared__ __align__(16) uint8_t lut[256];
+    __shared__ TailTab tab;
     __shared__ __align__(16) uint8_t stage[S == 1 ? 16 : (kThreads / 32) * 512];
     load_lut(lut, lutp);
+    init_tailtab(tab, sp);
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // tell the compiler it is uniform
+    if (ROWWARP) lanes_log2 = 5;
     const int L = 1 << lanes_log2;
     const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (kThreads / 32) + warp) * (32 >> lanes_log2);
-    const int64_t row = row0 + (lane >> lanes_log2);
+    const int64_t row = ROWWARP ? row0 : row0 + (lane >> lanes_log2);
     const int sub = lane & (L - 1);
     const bool row_ok = row < nseq;
     int64_t start = 0;
     int len = 0;
-    if (row_ok) {
+    if (ROWWARP) {
+        if (!row_ok) return;  // whole warp
+        int64_t o = 0;
+        if (lane < 2) o = __ldg(v.offs + row + lane);
+        start = __shfl_sync(0xffffffffu, o, 0);
+        len = static_cast<int>(__shfl_sync(0xffffffffu, o, 1) - start);
+    } else if (row_ok) {
         start = __ldg(v.offs + row);
         len = static_cast<int>(__ldg(v.offs + row + 1) - start);
     }
@@ -82,12 +99,12 @@ tokenize_rows_kernel(SeqView v, int64_t nseq, int padlen, int lanes_log2, LutPar
     const uint4 padv = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
 
     if (S == 1) {
-        const int r = static_cast<int>(rowbase & 15);  // misalignment of the row in the flat output
+        const int r = ALIGNED ? 0 : static_cast<int>(rowbase & 15);  // misalignment of the row in the flat output
         if (!row_ok) return;
         uint8_t *orow = reinterpret_cast<uint8_t *>(out) + rowbase;
         for (int c0 = 16 * sub - r; c0 < padlen; c0 += 16 * L) {
-            const uint4 codes = c0 >= npos ? padv : tokens16(rs, nullptr, len, c0, sp, lut);
-            if (c0 >= 0 && c0 + 16 <= padlen) {
+            const uint4 codes = c0 >= npos ? padv : tokens16<!ALIGNED>(rs, nullptr, len, c0, sp, lut, tab);
+            if (ALIGNED || (c0 >= 0 && c0 + 16 <= padlen)) {
                 __stcs(reinterpret_cast<uint4 *>(orow + c0), codes);
             } else {  // partial chunk at either end of an unaligned row
                 const uint32_t w[4] = {codes.x, codes.y, codes.z, codes.w};
@@ -103,7 +120,7 @@ tokenize_rows_kernel(SeqView v, int64_t nseq, int padlen, int lanes_log2, LutPar
         for (int cb = 0; cb < padlen; cb += 16 * L) {  // warp-uniform trip count
             const int c0 = cb + 16 * sub;
             uint4 codes = padv;
-            if (row_ok && c0 < padlen && c0 < npos) codes = tokens16(rs, nullptr, len, c0, sp, lut);
+            if (row_ok && c0 < padlen && c0 < npos) codes = tokens16<false>(rs, nullptr, len, c0, sp, lut, tab);
             *reinterpret_cast<uint4 *>(wstage + 16 * lane) = codes;
             __syncwarp();
 #pragma unroll
@@ -206,22 +223,46 @@ __device__ __forceinline__ void set_one(uint32_t w[4], int e) {
     }
 }
 
-template <typename T, bool ONEHOT>
+// 4x4 byte transpose: x[r] holds 4 consecutive positions of sequence r; y[j] gets position j of
+// the 4 sequences.  8 PRMT.
+__device__ __forceinline__ void transpose4x4(const uint32_t x[4], uint32_t y[4]) {
+    const uint32_t t0 = __byte_perm(x[0], x[1], 0x5140), t1 = __byte_perm(x[2], x[3], 0x5140);
+    const uint32_t t2 = __byte_perm(x[0], x[1], 0x7362), t3 = __byte_perm(x[2], x[3], 0x7362);
+    y[0] = __byte_perm(t0, t1, 0x5410);
+    y[1] = __byte_perm(t0, t1, 0x7632);
+    y[2] = __byte_perm(t2, t3, 0x5410);
+    y[3] = __byte_perm(t2, t3, 0x7632);
+}
+
+// MODE: how phase 2 leaves the tile.
+constexpr int kTokFast = 0;     // one-byte tokens, batch extent a multiple of 16: register 4x4 transposes + st.v4
+constexpr int kTokGeneric = 1;  // any element type / alignment: one element per lane, coalesced along the batch
+constexpr int kOneHot = 2;      // one-hot expansion (regime picked at run time, see below)
+// one-hot regimes
+constexpr int kOhRow = 0;      // C*sizeof(T) is 4, 8 or 16: one store writes the whole one-hot row of a (pos, seq)
+constexpr int kOhScatter = 1;  // 16-byte zero fill of the run, barrier, then one scalar store per (pos, seq)
+constexpr int kOhScalar = 2;   // unaligned runs: one element per lane
+
+template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreads)
 seqfirst_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, LutParam lutp, Specials sp, Expand ex, int ncols,
-                FastDiv div_ncols, int vec_ok, T *__restrict__ out) {
+                FastDiv div_ncols, int regime, T *__restrict__ out) {
     // nseq sequences are processed; ld (>= nseq) is the batch extent of the output array, so a
     // sub-range of a larger batch can be written in place (out already points at its first column).
+    constexpr bool ONEHOT = MODE == kOneHot;
+    constexpr int PITCH = MODE == kTokFast ? kTilePos : kTilePitch;
     __shared__ __align__(16) uint8_t lut[256];
-    __shared__ __align__(16) uint8_t tile[kTileSeqs * kTilePitch];
+    __shared__ __align__(16) uint8_t tile[kTileSeqs * PITCH];
+    __shared__ TailTab tab;
     load_lut(lut, lutp);
+    init_tailtab(tab, sp);
     __syncthreads();
     const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kTileSeqs;
     const int p0 = blockIdx.y * kTilePos;
     const int nseq_tile = static_cast<int>(min(static_cast<int64_t>(kTileSeqs), nseq - i0));
     const int npos_tile = min(kTilePos, padlen - p0);
 
-    // ---- phase 1 ----
+    // ---- phase 1: tile[seq][pos] <- codes; lanes run along the positions of a sequence ----
 #pragma unroll
     for (int u = 0; u < (kTileSeqs * kTilePos / 16) / kThreads; ++u) {
         const int ch = threadIdx.x + u * kThreads;
@@ -237,59 +278,111 @@ seqfirst_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, LutParam lutp, 
                 const RowSrc rs = make_rowsrc(v.bytes, start, sp.bos, len);
                 if (ONEHOT && v.mask != nullptr) {
                     const RowSrc ms = make_rowsrc(v.mask, start, sp.bos, len);
-                    codes = tokens16(rs, &ms, len, c0, sp, lut);
+                    codes = tokens16<false>(rs, &ms, len, c0, sp, lut, tab);
                 } else {
-                    codes = tokens16(rs, nullptr, len, c0, sp, lut);
+                    codes = tokens16<false>(rs, nullptr, len, c0, sp, lut, tab);
                 }
             }
-            uint32_t *dst = reinterpret_cast<uint32_t *>(tile + il * kTilePitch + 16 * q);
-            dst[0] = codes.x; dst[1] = codes.y; dst[2] = codes.z; dst[3] = codes.w;
+            if (MODE == kTokFast) {
+                // 16-byte chunks XOR-swizzled by the sequence group, so that phase 2's column-of-words
+                // reads (16 sequences apart) hit 32 distinct banks
+                *reinterpret_cast<uint4 *>(tile + il * PITCH + 16 * (q ^ ((il >> 4) & 7))) = codes;
+            } else {
+                uint32_t *dst = reinterpret_cast<uint32_t *>(tile + il * PITCH + 16 * q);
+                dst[0] = codes.x; dst[1] = codes.y; dst[2] = codes.z; dst[3] = codes.w;
+            }
         }
     }
     __syncthreads();
 
     // ---- phase 2 ----
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (!ONEHOT) {
+    if (MODE == kTokFast) {
+        // thread = 16 sequences (group A) x 4 positions (word pw): 16 LDS.32, four 4x4 transposes,
+        // then one 16-byte store per position; lanes A = 0..7 make 128 contiguous bytes per row.
+        const int A = lane & 7, pw = 4 * warp + (lane >> 3);
+        const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tile);
+        uint32_t y[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            uint32_t x[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) x[k] = t32[(16 * A + 4 * a + k) * (PITCH / 4) + (pw ^ (4 * A))];
+            transpose4x4(x, y[a]);
+        }
+        const int nvalid = nseq_tile - 16 * A;  // sequences of this group that exist
+        uint8_t *obase = reinterpret_cast<uint8_t *>(out) + i0 + 16 * A;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int pos = p0 + 4 * pw + j;
+            if (pos >= padlen || nvalid <= 0) continue;
+            uint8_t *o = obase + static_cast<int64_t>(pos) * ld;
+            if (nvalid >= 16) {
+                __stcs(reinterpret_cast<uint4 *>(o), make_uint4(y[0][j], y[1][j], y[2][j], y[3][j]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (k < nvalid) o[k] = static_cast<uint8_t>(y[k >> 2][j] >> (8 * (k & 3)));
+            }
+        }
+    } else if (MODE == kTokGeneric) {
         for (int pp = warp; pp < npos_tile; pp += kThreads / 32) {
             T *orow = out + (static_cast<int64_t>(p0 + pp) * ld + i0);
 #pragma unroll
             for (int m = 0; m < kTileSeqs / 32; ++m) {
                 const int il = lane + 32 * m;
                 if (il < nseq_tile) {
-                    const uint32_t code = tile[il * kTilePitch + pp];
+                    const uint32_t code = tile[il * PITCH + pp];
                     __stcs(orow + il, cast_id<T>(expand_code(code, ex)));
                 }
             }
         }
+    } else if (regime == kOhRow) {
+        const int row_bytes = ncols * static_cast<int>(sizeof(T));
+        for (int pp = warp; pp < npos_tile; pp += kThreads / 32) {
+            uint8_t *orow = reinterpret_cast<uint8_t *>(out + (static_cast<int64_t>(p0 + pp) * ld + i0) * ncols);
+#pragma unroll
+            for (int m = 0; m < kTileSeqs / 32; ++m) {
+                const int il = lane + 32 * m;
+                if (il < nseq_tile) {
+                    const int col = expand_code(tile[il * PITCH + pp], ex);
+                    uint32_t w[4] = {0u, 0u, 0u, 0u};
+                    if (col >= 0) set_one<T>(w, col);
+                    uint8_t *o = orow + il * row_bytes;
+                    if (row_bytes == 16) __stcs(reinterpret_cast<uint4 *>(o), make_uint4(w[0], w[1], w[2], w[3]));
+                    else if (row_bytes == 8) __stcs(reinterpret_cast<uint2 *>(o), make_uint2(w[0], w[1]));
+                    else __stcs(reinterpret_cast<uint32_t *>(o), w[0]);
+                }
+            }
+        }
+    } else if (regime == kOhScatter) {
+        constexpr int EPV = 16 / sizeof(T);
+        const int nvec = nseq_tile * ncols / EPV;  // exact: the host checked divisibility
+        for (int pp = warp; pp < npos_tile; pp += kThreads / 32) {
+            uint4 *orow = reinterpret_cast<uint4 *>(out + (static_cast<int64_t>(p0 + pp) * ld + i0) * ncols);
+            for (int vec = lane; vec < nvec; vec += 32) orow[vec] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();  // orders the zero fill before the ones (same addresses, different threads)
+        for (int pp = warp; pp < npos_tile; pp += kThreads / 32) {
+            T *orow = out + (static_cast<int64_t>(p0 + pp) * ld + i0) * ncols;
+#pragma unroll
+            for (int m = 0; m < kTileSeqs / 32; ++m) {
+                const int il = lane + 32 * m;
+                if (il < nseq_tile) {
+                    const int col = expand_code(tile[il * PITCH + pp], ex);
+                    if (col >= 0) orow[il * ncols + col] = cast_id<T>(1);
+                }
+            }
+        }
     } else {
-        constexpr int EPV = 16 / sizeof(T);  // elements per 16-byte vector
         const int run_elems = nseq_tile * ncols;
         for (int pp = warp; pp < npos_tile; pp += kThreads / 32) {
             T *orow = out + (static_cast<int64_t>(p0 + pp) * ld + i0) * ncols;
-            if (vec_ok) {
-                const int nvec = run_elems / EPV;  // exact: the host checked divisibility
-                for (int vec = lane; vec < nvec; vec += 32) {
-                    const int e0 = vec * EPV;
-                    int il = static_cast<int>(fd_div(static_cast<uint32_t>(e0), div_ncols));
-                    int base = il * ncols - e0;  // vector-relative element index of column 0 of seq il
-                    uint32_t w[4] = {0u, 0u, 0u, 0u};
-                    while (base < EPV) {
-                        const int col = expand_code(tile[il * kTilePitch + pp], ex);
-                        const int e = base + col;
-                        if (col >= 0 && e >= 0 && e < EPV) set_one<T>(w, e);
-                        base += ncols;
-                        ++il;
-                    }
-                    __stcs(reinterpret_cast<uint4 *>(orow) + vec, make_uint4(w[0], w[1], w[2], w[3]));
-                }
-            } else {
-                for (int e = lane; e < run_elems; e += 32) {
-                    const int il = static_cast<int>(fd_div(static_cast<uint32_t>(e), div_ncols));
-                    const int col = e - il * ncols;
-                    const int hot = expand_code(tile[il * kTilePitch + pp], ex);
-                    orow[e] = hot == col ? cast_id<T>(1) : cast_id<T>(0);
-                }
+            for (int e = lane; e < run_elems; e += 32) {
+                const int il = static_cast<int>(fd_div(static_cast<uint32_t>(e), div_ncols));
+                const int col = e - il * ncols;
+                const int hot = expand_code(tile[il * PITCH + pp], ex);
+                orow[e] = hot == col ? cast_id<T>(1) : cast_id<T>(0);
             }
         }
     }
@@ -541,8 +634,18 @@ int launch_bf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t /*ld*/, i
         const int64_t rows_per_block = static_cast<int64_t>(kThreads / 32) * (32 >> lanes_log2);
         const int64_t blocks = (nseq + rows_per_block - 1) / rows_per_block;
         if (blocks > 0x7fffffffll) return fail(BSQ_ERR_ARG, "batch too large for one launch");
-        tokenize_rows_kernel<T><<<static_cast<unsigned>(blocks), kThreads, 0, st>>>(
-            v, nseq, static_cast<int>(padlen), lanes_log2, p.lut, p.sp, p.ex, static_cast<T *>(d_out));
+        const bool aligned = sizeof(T) != 1 || padlen % 16 == 0;
+        const unsigned nb = static_cast<unsigned>(blocks);
+        T *o = static_cast<T *>(d_out);
+        const int pl = static_cast<int>(padlen);
+        if (lanes_log2 == 5 && aligned)
+            tokenize_rows_kernel<T, true, true><<<nb, kThreads, 0, st>>>(v, nseq, pl, lanes_log2, p.lut, p.sp, p.ex, o);
+        else if (lanes_log2 == 5)
+            tokenize_rows_kernel<T, true, false><<<nb, kThreads, 0, st>>>(v, nseq, pl, lanes_log2, p.lut, p.sp, p.ex, o);
+        else if (aligned)
+            tokenize_rows_kernel<T, false, true><<<nb, kThreads, 0, st>>>(v, nseq, pl, lanes_log2, p.lut, p.sp, p.ex, o);
+        else
+            tokenize_rows_kernel<T, false, false><<<nb, kThreads, 0, st>>>(v, nseq, pl, lanes_log2, p.lut, p.sp, p.ex, o);
     } else {
         constexpr int TPT = 16 / sizeof(T);
         const int64_t total = nseq * padlen;
@@ -563,15 +666,29 @@ int launch_sf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t ld, int64
     const Prepared p = prepare(tok, ONEHOT ? 2 : 1);
     const int64_t gx = (nseq + kTileSeqs - 1) / kTileSeqs, gy = (padlen + kTilePos - 1) / kTilePos;
     if (gx > 0x7fffffffll || gy > 65535) return fail(BSQ_ERR_ARG, "batch too large for one launch");
+    const dim3 grid(static_cast<unsigned>(gx), static_cast<unsigned>(gy));
     const int ncols = ONEHOT ? tok.alphabet_size : 1;
-    // 16-byte stores need every row of the (padlen, ld, ncols) array and this launch's first
-    // column to start on a 16-byte boundary
-    const int vec_ok = ((ld * ncols * static_cast<int64_t>(sizeof(T))) % 16) == 0 &&
-                       (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0 &&
-                       ((nseq * ncols * static_cast<int64_t>(sizeof(T))) % 16) == 0;
-    seqfirst_kernel<T, ONEHOT><<<dim3(static_cast<unsigned>(gx), static_cast<unsigned>(gy)), kThreads, 0, st>>>(
-        v, nseq, ld, static_cast<int>(padlen), p.lut, p.sp, p.ex, ncols, make_fastdiv(static_cast<uint32_t>(ncols)),
-        vec_ok, static_cast<T *>(d_out));
+    const FastDiv dc = make_fastdiv(static_cast<uint32_t>(ncols));
+    const bool aligned = (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0;
+    T *o = static_cast<T *>(d_out);
+    if (!ONEHOT) {
+        // the register-transpose path needs one-byte elements whose rows start 16-byte aligned and
+        // codes that are the output bytes (every alphabet but BYTES, whose special ids exceed 8 bits)
+        if (sizeof(T) == 1 && aligned && ld % 16 == 0 && tok.pad_id < 0x80)
+            seqfirst_kernel<T, kTokFast><<<grid, kThreads, 0, st>>>(v, nseq, ld, static_cast<int>(padlen), p.lut, p.sp, p.ex, 1, dc, 0, o);
+        else
+            seqfirst_kernel<T, kTokGeneric><<<grid, kThreads, 0, st>>>(v, nseq, ld, static_cast<int>(padlen), p.lut, p.sp, p.ex, 1, dc, 0, o);
+    } else {
+        const int64_t row_bytes = static_cast<int64_t>(ncols) * sizeof(T);
+        // 16-byte stores need every row of the (padlen, ld, ncols) array and this launch's first
+        // column to start on a 16-byte boundary, and whole vectors per tile run
+        const bool vec_ok = aligned && (ld * row_bytes) % 16 == 0 && (nseq * row_bytes) % 16 == 0;
+        int regime = kOhScalar;
+        if (aligned && (row_bytes == 4 || row_bytes == 8 || row_bytes == 16)) regime = kOhRow;
+        else if (vec_ok) regime = kOhScatter;
+        seqfirst_kernel<T, kOneHot><<<grid, kThreads, 0, st>>>(v, nseq, ld, static_cast<int>(padlen), p.lut, p.sp, p.ex, ncols, dc,
+                                                                regime, o);
+    }
     count_launch();
     BSQ_CUDA_TRY(cudaGetLastError());
     return BSQ_OK;

@@ -136,15 +136,40 @@ __device__ __forceinline__ void fetch16(const RowSrc &rs, int c0, uint32_t out[4
     }
 }
 
-// Codes of columns c0 .. c0+15 (c0 may be negative or run past padlen; such bytes are
-// don't-care) of a row with `len` residues.  Column layout (src/tokenize.h:460-478):
+// Per-CTA shared-memory tables for the chunk that holds the end of a row: for k = 0..16 leading
+// bytes that are still BOS/residues, m[k] keeps those bytes and f[k] supplies the rest (EOS at
+// byte k when the tokenizer has one, the pad code after it).  Two LDS.128 + four LOP3 replace
+// ~70 mask-building instructions per tail chunk.
+struct TailTab {
+    uint4 m[17];
+    uint4 f[17];
+};
+__device__ __forceinline__ void init_tailtab(TailTab &tab, const Specials &sp) {
+    const int k = static_cast<int>(threadIdx.x) - 64;  // threads 64..80 (0..63 load the LUT)
+    if (k >= 0 && k <= 16) {
+        uint32_t m[4], f[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            m[w] = lt_mask(k, w);
+            const uint32_t m_eos = lt_mask(clamp16(k + sp.eos), w);
+            f[w] = (sp.eos_w & m_eos & ~m[w]) | (sp.pad_w & ~m_eos);
+        }
+        tab.m[k] = make_uint4(m[0], m[1], m[2], m[3]);
+        tab.f[k] = make_uint4(f[0], f[1], f[2], f[3]);
+    }
+}
+
+// Codes of columns c0 .. c0+15 of a row with `len` residues, for c0 < bos + len + eos (the
+// caller emits the constant pad vector beyond that).  Column layout (src/tokenize.h:460-478):
 //   [0, bos)            BOS
 //   [bos, bos+len)      lut[residue]
 //   bos+len             EOS (if eos)
 //   beyond              pad code
-// `ms` is the row's mask source (one-hot only) or nullptr.
+// With MAYBE_NEG, c0 may be negative (rows that do not start 16-byte aligned in the output);
+// bytes left of column 0 are don't-care.  `ms` is the row's mask source (one-hot only) or nullptr.
+template <bool MAYBE_NEG>
 __device__ __forceinline__ uint4 tokens16(const RowSrc &rs, const RowSrc *ms, int len, int c0,
-                                          const Specials &sp, const uint8_t *lut) {
+                                          const Specials &sp, const uint8_t *lut, const TailTab &tab) {
     const int r0 = c0 - sp.bos;  // residue index of the chunk's first column
     uint32_t t[4] = {0u, 0u, 0u, 0u};
     if (min(r0 + 16, len) > max(r0, 0)) {
@@ -160,8 +185,7 @@ __device__ __forceinline__ uint4 tokens16(const RowSrc &rs, const RowSrc *ms, in
         }
     }
     const int n = sp.bos + len;  // column of EOS
-    if (c0 + 16 > n || c0 < 0) {
-        // chunk holds the end of the row (EOS / pad) or starts before column 0 (unaligned rows)
+    if (MAYBE_NEG && c0 < 0) {
         const int kr0 = clamp16(sp.bos - c0), kr1 = clamp16(n - c0), kr2 = clamp16(n + sp.eos - c0);
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
@@ -170,8 +194,13 @@ __device__ __forceinline__ uint4 tokens16(const RowSrc &rs, const RowSrc *ms, in
             const uint32_t m_eos = lt_mask(kr2, w);
             t[w] = (sp.bos_w & m_bos) | (t[w] & m_res & ~m_bos) | (sp.eos_w & m_eos & ~m_res) | (sp.pad_w & ~m_eos);
         }
-    } else if (c0 < sp.bos) {
-        t[0] = __byte_perm(t[0], sp.bos_w, 0x3214);  // c0 == 0: column 0 is BOS, the rest are residues
+    } else {
+        if (c0 < sp.bos) t[0] = __byte_perm(t[0], sp.bos_w, 0x3214);  // c0 == 0: column 0 is BOS
+        if (c0 + 16 > n) {                                           // the row ends inside this chunk
+            const uint4 m = tab.m[n - c0], f = tab.f[n - c0];
+            t[0] = (t[0] & m.x) | f.x; t[1] = (t[1] & m.y) | f.y;
+            t[2] = (t[2] & m.z) | f.z; t[3] = (t[3] & m.w) | f.w;
+        }
     }
     return make_uint4(t[0], t[1], t[2], t[3]);
 }
