@@ -62,38 +62,64 @@ __device__ __forceinline__ uint4 expand_vec(const uint8_t *codes, const Expand &
 //          uniform datapath.  Otherwise 32 >> lanes_log2 rows share a warp.
 // ALIGNED: padlen % 16 == 0, i.e. every row starts 16-byte aligned in the output and has no
 //          partial chunk (always true for the wide element types handled here).
+struct RowInfo {  // what a warp needs to know about its row, published through shared memory
+    const uint8_t *al;
+    int off, len;
+};
+
 template <typename T, bool ROWWARP, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads)
 tokenize_rows_kernel(SeqView v, int64_t nseq, int padlen, int lanes_log2, LutParam lutp, Specials sp, Expand ex,
                      T *__restrict__ out) {
     constexpr int S = sizeof(T);
+    constexpr int WARPS = kThreads / 32;
     __shared__ __align__(16) uint8_t lut[256];
     __shared__ TailTab tab;
-    __shared__ __align__(16) uint8_t stage[S == 1 ? 16 : (kThreads / 32) * 512];
-    load_lut(lut, lutp);
-    init_tailtab(tab, sp);
+    __shared__ __align__(16) RowInfo rinfo[WARPS];
+    __shared__ __align__(16) uint8_t stage[S == 1 ? 16 : WARPS * 512];
+    load_lut(lut, lutp);    // threads 0..63
+    init_tailtab(tab, sp);  // threads 64..80
+    if (ROWWARP && threadIdx.x >= 96 && threadIdx.x < 96 + WARPS) {
+        // one thread per row of this CTA resolves the row's offsets and source alignment, so the
+        // 8 warps do not each repeat that (dependent-load + 64-bit) arithmetic in all 32 lanes
+        const int w = threadIdx.x - 96;
+        const int64_t row = static_cast<int64_t>(blockIdx.x) * WARPS + w;
+        if (row < nseq) {
+            const int64_t start = __ldg(v.offs + row);
+            const int len = static_cast<int>(__ldg(v.offs + row + 1) - start);
+            const RowSrc r0 = make_rowsrc(v.bytes, start, sp.bos, len);
+            rinfo[w].al = r0.al;
+            rinfo[w].off = r0.off;
+            rinfo[w].len = len;
+        }
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);  // tell the compiler it is uniform
     if (ROWWARP) lanes_log2 = 5;
     const int L = 1 << lanes_log2;
-    const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * (kThreads / 32) + warp) * (32 >> lanes_log2);
+    const int64_t row0 = (static_cast<int64_t>(blockIdx.x) * WARPS + warp) * (32 >> lanes_log2);
     const int64_t row = ROWWARP ? row0 : row0 + (lane >> lanes_log2);
     const int sub = lane & (L - 1);
     const bool row_ok = row < nseq;
-    int64_t start = 0;
+    RowSrc rs;
     int len = 0;
     if (ROWWARP) {
         if (!row_ok) return;  // whole warp
-        int64_t o = 0;
-        if (lane < 2) o = __ldg(v.offs + row + lane);
-        start = __shfl_sync(0xffffffffu, o, 0);
-        len = static_cast<int>(__shfl_sync(0xffffffffu, o, 1) - start);
-    } else if (row_ok) {
-        start = __ldg(v.offs + row);
-        len = static_cast<int>(__ldg(v.offs + row + 1) - start);
+        const RowInfo ri = rinfo[warp];
+        len = ri.len;
+        rs.al = ri.al;
+        rs.off = ri.off;
+        rs.fw = (ri.off + sp.bos) & ~15;
+        rs.lw = (ri.off + sp.bos + len - 1) & ~15;
+    } else {
+        int64_t start = 0;
+        if (row_ok) {
+            start = __ldg(v.offs + row);
+            len = static_cast<int>(__ldg(v.offs + row + 1) - start);
+        }
+        rs = make_rowsrc(v.bytes, start, sp.bos, len);
     }
-    const RowSrc rs = make_rowsrc(v.bytes, start, sp.bos, len);
     const int npos = sp.bos + len + sp.eos;
     const int64_t rowbase = row * padlen;  // flat element index of column 0
     const uint4 padv = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
@@ -102,8 +128,7 @@ tokenize_rows_kernel(SeqView v, int64_t nseq, int padlen, int lanes_log2, LutPar
         const int r = ALIGNED ? 0 : static_cast<int>(rowbase & 15);  // misalignment of the row in the flat output
         if (!row_ok) return;
         uint8_t *orow = reinterpret_cast<uint8_t *>(out) + rowbase;
-        for (int c0 = 16 * sub - r; c0 < padlen; c0 += 16 * L) {
-            const uint4 codes = c0 >= npos ? padv : tokens16<!ALIGNED>(rs, nullptr, len, c0, sp, lut, tab);
+        auto store = [&](int c0, const uint4 &codes) {
             if (ALIGNED || (c0 >= 0 && c0 + 16 <= padlen)) {
                 __stcs(reinterpret_cast<uint4 *>(orow + c0), codes);
             } else {  // partial chunk at either end of an unaligned row
@@ -112,6 +137,18 @@ tokenize_rows_kernel(SeqView v, int64_t nseq, int padlen, int lanes_log2, LutPar
                 for (int j = 0; j < 16; ++j)
                     if (c0 + j >= 0 && c0 + j < padlen) orow[c0 + j] = static_cast<uint8_t>(w[j >> 2] >> (8 * (j & 3)));
             }
+        };
+        // two chunks (16*L columns apart) per iteration: both chunks' loads are in flight before
+        // either is translated
+        for (int c0 = 16 * sub - r; c0 < padlen; c0 += 32 * L) {
+            const int c1 = c0 + 16 * L;
+            const bool ld0 = c0 < npos && has_residues(c0, sp.bos, len);
+            const bool ld1 = c1 < padlen && c1 < npos && has_residues(c1, sp.bos, len);
+            Fetched f0, f1;
+            if (ld0) f0 = fetch_issue(rs, c0);
+            if (ld1) f1 = fetch_issue(rs, c1);
+            store(c0, c0 >= npos ? padv : tokens16_from<!ALIGNED>(f0, ld0, rs, len, c0, sp, lut, tab));
+            if (c1 < padlen) store(c1, c1 >= npos ? padv : tokens16_from<!ALIGNED>(f1, ld1, rs, len, c1, sp, lut, tab));
         }
     } else {
         // rows are 16-byte aligned here (the host checked padlen * sizeof(T) % 16 == 0)

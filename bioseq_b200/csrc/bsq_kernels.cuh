@@ -105,17 +105,30 @@ __device__ __forceinline__ RowSrc make_rowsrc(const uint8_t *base, int64_t start
     return r;
 }
 
-// The 16 bytes of columns c0 .. c0+15 as four little-endian words: two aligned 16-byte
-// ld.global.nc loads + a funnel-shift realignment.  The byte shift (off + c0) & 15 is the same
-// for every chunk of a row, so when a warp works on one row the switch is warp-uniform.
-__device__ __forceinline__ void fetch16(const RowSrc &rs, int c0, uint32_t out[4]) {
+// The 16 bytes of columns c0 .. c0+15, in two steps so that callers can issue the loads of
+// several chunks before consuming any of them:
+//   fetch_issue   two aligned 16-byte ld.global.nc loads (the second only when the chunk is not
+//                 16-byte aligned in the source),
+//   fetch_align   funnel-shift realignment into four little-endian words.
+// The byte shift (off + c0) & 15 is the same for every chunk of a row, so when a warp works on
+// one row the switch is warp-uniform.
+struct Fetched {
+    uint4 v0, v1;
+};
+__device__ __forceinline__ Fetched fetch_issue(const RowSrc &rs, int c0) {
     const int a = rs.off + c0;
     const int a0 = a & ~15;
-    const uint32_t s = static_cast<uint32_t>(a) & 15u;
-    const uint4 v0 = ldg16(reinterpret_cast<uintptr_t>(rs.al + min(max(a0, rs.fw), rs.lw)));
-    uint4 v1 = make_uint4(0u, 0u, 0u, 0u);
-    if (s != 0u) v1 = ldg16(reinterpret_cast<uintptr_t>(rs.al + min(max(a0 + 16, rs.fw), rs.lw)));
+    Fetched f;
+    f.v0 = ldg16(reinterpret_cast<uintptr_t>(rs.al) + static_cast<uint32_t>(min(max(a0, rs.fw), rs.lw)));
+    f.v1 = make_uint4(0u, 0u, 0u, 0u);
+    if ((a & 15) != 0)
+        f.v1 = ldg16(reinterpret_cast<uintptr_t>(rs.al) + static_cast<uint32_t>(min(max(a0 + 16, rs.fw), rs.lw)));
+    return f;
+}
+__device__ __forceinline__ void fetch_align(const Fetched &f, const RowSrc &rs, int c0, uint32_t out[4]) {
+    const uint32_t s = static_cast<uint32_t>(rs.off + c0) & 15u;
     const uint32_t sh = (s & 3u) * 8u;
+    const uint4 &v0 = f.v0, &v1 = f.v1;
     switch (s >> 2) {
         case 0:
             out[0] = __funnelshift_r(v0.x, v0.y, sh); out[1] = __funnelshift_r(v0.y, v0.z, sh);
@@ -134,6 +147,15 @@ __device__ __forceinline__ void fetch16(const RowSrc &rs, int c0, uint32_t out[4
             out[2] = __funnelshift_r(v1.y, v1.z, sh); out[3] = __funnelshift_r(v1.z, v1.w, sh);
             break;
     }
+}
+__device__ __forceinline__ void fetch16(const RowSrc &rs, int c0, uint32_t out[4]) {
+    const Fetched f = fetch_issue(rs, c0);
+    fetch_align(f, rs, c0, out);
+}
+// does the chunk starting at column c0 hold at least one residue?
+__device__ __forceinline__ bool has_residues(int c0, int bos, int len) {
+    const int r0 = c0 - bos;
+    return min(r0 + 16, len) > max(r0, 0);
 }
 
 // Per-CTA shared-memory tables for the chunk that holds the end of a row: for k = 0..16 leading
@@ -168,22 +190,7 @@ __device__ __forceinline__ void init_tailtab(TailTab &tab, const Specials &sp) {
 // With MAYBE_NEG, c0 may be negative (rows that do not start 16-byte aligned in the output);
 // bytes left of column 0 are don't-care.  `ms` is the row's mask source (one-hot only) or nullptr.
 template <bool MAYBE_NEG>
-__device__ __forceinline__ uint4 tokens16(const RowSrc &rs, const RowSrc *ms, int len, int c0,
-                                          const Specials &sp, const uint8_t *lut, const TailTab &tab) {
-    const int r0 = c0 - sp.bos;  // residue index of the chunk's first column
-    uint32_t t[4] = {0u, 0u, 0u, 0u};
-    if (min(r0 + 16, len) > max(r0, 0)) {
-        uint32_t raw[4];
-        fetch16(rs, c0, raw);
-#pragma unroll
-        for (int w = 0; w < 4; ++w) t[w] = translate4(raw[w], lut);
-        if (ms != nullptr) {  // masked-out residues become kCodeInvalid (0xFF)
-            uint32_t m[4];
-            fetch16(*ms, c0, m);
-#pragma unroll
-            for (int w = 0; w < 4; ++w) t[w] |= __vcmpeq4(m[w], 0u);
-        }
-    }
+__device__ __forceinline__ uint4 tokens16_finish(uint32_t t[4], int len, int c0, const Specials &sp, const TailTab &tab) {
     const int n = sp.bos + len;  // column of EOS
     if (MAYBE_NEG && c0 < 0) {
         const int kr0 = clamp16(sp.bos - c0), kr1 = clamp16(n - c0), kr2 = clamp16(n + sp.eos - c0);
@@ -203,6 +210,39 @@ __device__ __forceinline__ uint4 tokens16(const RowSrc &rs, const RowSrc *ms, in
         }
     }
     return make_uint4(t[0], t[1], t[2], t[3]);
+}
+
+template <bool MAYBE_NEG>
+__device__ __forceinline__ uint4 tokens16(const RowSrc &rs, const RowSrc *ms, int len, int c0,
+                                          const Specials &sp, const uint8_t *lut, const TailTab &tab) {
+    uint32_t t[4] = {0u, 0u, 0u, 0u};
+    if (has_residues(c0, sp.bos, len)) {
+        uint32_t raw[4];
+        fetch16(rs, c0, raw);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) t[w] = translate4(raw[w], lut);
+        if (ms != nullptr) {  // masked-out residues become kCodeInvalid (0xFF)
+            uint32_t m[4];
+            fetch16(*ms, c0, m);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) t[w] |= __vcmpeq4(m[w], 0u);
+        }
+    }
+    return tokens16_finish<MAYBE_NEG>(t, len, c0, sp, tab);
+}
+
+// Same result as tokens16 (no mask) from loads issued earlier with fetch_issue.
+template <bool MAYBE_NEG>
+__device__ __forceinline__ uint4 tokens16_from(const Fetched &f, bool loaded, const RowSrc &rs, int len, int c0,
+                                               const Specials &sp, const uint8_t *lut, const TailTab &tab) {
+    uint32_t t[4] = {0u, 0u, 0u, 0u};
+    if (loaded) {
+        uint32_t raw[4];
+        fetch_align(f, rs, c0, raw);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) t[w] = translate4(raw[w], lut);
+    }
+    return tokens16_finish<MAYBE_NEG>(t, len, c0, sp, tab);
 }
 
 // One code, any column: the scalar twin of tokens16.
