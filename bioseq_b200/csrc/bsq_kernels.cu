@@ -16,6 +16,8 @@
 // Reference semantics: src/tokenize.h:381-485 (K1/K2), :283-371 (K3), :131-179 (K4).
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -170,6 +172,139 @@ tokenize_rows_kernel(SeqView v, int64_t nseq, int padlen, int lanes_log2, LutPar
                     __stcs(reinterpret_cast<uint4 *>(out + srow * padlen + scol), expand_vec<T>(wstage + e, ex));
             }
             __syncwarp();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1t: the same batch-first one-byte tokeniser as a persistent, TMA-fed kernel.
+//
+// Every warp owns a ring of NB shared-memory row buffers.  One elected lane issues a 1-D bulk
+// asynchronous copy (cp.async.bulk global -> shared, completion counted on an mbarrier) of the
+// 16-byte-aligned window that holds a row's residues, NB-1 rows ahead of the row being
+// translated, so the HBM latency of a row is overlapped with the LUT work of the previous rows
+// instead of being exposed once per row per warp.  Rows are dealt round-robin to the warps of
+// the whole grid (consecutive warps work on consecutive rows: the packed residues are read as
+// one contiguous stream).  Offsets of up to 32 upcoming rows are loaded one row per lane and
+// handed around through a small per-warp shared-memory table.
+// Requires padlen % 16 == 0 (rows 16-byte aligned in the output).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kThreads)
+tokenize_rows_tma_kernel(SeqView v, int64_t nseq, int padlen, int bufsz, LutParam lutp, Specials sp, uint8_t *__restrict__ out) {
+    constexpr int WARPS = kThreads / 32;
+    extern __shared__ __align__(128) uint8_t ring[];  // WARPS * NB * bufsz
+    __shared__ __align__(16) uint8_t lut[256];
+    __shared__ TailTab tab;
+    __shared__ __align__(8) uint64_t bars[WARPS * NB];
+    __shared__ __align__(16) RowInfo rinfo[WARPS][32];
+    load_lut(lut, lutp);
+    init_tailtab(tab, sp);
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+    uint64_t *mybar = bars + warp * NB;
+    uint8_t *mybuf = ring + static_cast<size_t>(warp) * NB * bufsz;
+    if (lane < NB) mbar_init(mybar + lane, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
+    const int64_t GW = static_cast<int64_t>(gridDim.x) * WARPS;
+    const uint4 padv = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
+    uint32_t issued = 0, consumed = 0;  // rows with residues only; buffer = n % NB, parity = (n / NB) & 1
+
+    for (int64_t batch0 = gw; batch0 < nseq; batch0 += 32 * GW) {
+        // lane j resolves row batch0 + j*GW of this warp's next 32 rows
+        {
+            const int64_t myrow = batch0 + lane * GW;
+            RowInfo ri;
+            ri.al = nullptr; ri.off = 0; ri.len = 0;
+            if (myrow < nseq) {
+                const int64_t start = __ldg(v.offs + myrow);
+                ri.len = static_cast<int>(__ldg(v.offs + myrow + 1) - start);
+                const uint8_t *src = v.bytes + start - sp.bos;
+                ri.off = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
+                ri.al = src - ri.off;
+            }
+            __syncwarp();
+            rinfo[warp][lane] = ri;
+            __syncwarp();
+        }
+        const int nrows = static_cast<int>(min(static_cast<int64_t>(32), (nseq - batch0 + GW - 1) / GW));
+        auto issue = [&](int j) {  // warp-uniform j
+            const RowInfo ri = rinfo[warp][j];
+            if (ri.len > 0) {
+                if (lane == 0) {
+                    const int fw = (ri.off + sp.bos) & ~15, lw = (ri.off + sp.bos + ri.len - 1) & ~15;
+                    const uint32_t bytes = static_cast<uint32_t>(lw - fw + 16);
+                    const uint32_t b = issued % NB;
+                    mbar_expect_tx(mybar + b, bytes);
+                    bulk_g2s(mybuf + b * bufsz, ri.al + fw, bytes, mybar + b);
+                }
+                ++issued;
+            }
+        };
+        for (int j = 0; j < min(NB - 1, nrows); ++j) issue(j);
+        for (int j = 0; j < nrows; ++j) {
+            if (j + NB - 1 < nrows) issue(j + NB - 1);
+            const RowInfo ri = rinfo[warp][j];
+            const int len = ri.len;
+            const int npos = sp.bos + len + sp.eos;
+            const int fw = (ri.off + sp.bos) & ~15;
+            const uint8_t *buf = mybuf + (consumed % NB) * bufsz;
+            if (len > 0) {
+                mbar_wait(mybar + consumed % NB, (consumed / NB) & 1u);
+                ++consumed;
+            }
+            RowSrc rs;  // only .off is used by fetch_align
+            rs.al = nullptr; rs.off = ri.off; rs.fw = 0; rs.lw = 0;
+            uint8_t *orow = out + (batch0 + static_cast<int64_t>(j) * GW) * padlen;
+            for (int c0 = 16 * lane; c0 < padlen; c0 += 512) {
+                uint4 codes = padv;
+                if (c0 < npos) {
+                    uint32_t t[4] = {0u, 0u, 0u, 0u};
+                    if (has_residues(c0, sp.bos, len)) {
+                        const int a = ri.off + c0;
+                        const int w0 = (a & ~15) - fw;  // window offset of the aligned word holding byte a (>= -16)
+                        Fetched f;
+                        f.v0 = *reinterpret_cast<const uint4 *>(buf + max(w0, 0));
+                        f.v1 = *reinterpret_cast<const uint4 *>(buf + w0 + 16);
+                        uint32_t raw[4];
+                        fetch_align(f, rs, c0, raw);
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) t[w] = translate4(raw[w], lut);
+                    }
+                    codes = tokens16_finish<false>(t, len, c0, sp, tab);
+                }
+                __stcs(reinterpret_cast<uint4 *>(orow + c0), codes);
+            }
+            __syncwarp();  // every lane is done with this buffer before it is refilled
         }
     }
 }
@@ -605,6 +740,16 @@ namespace {
 
 inline uint32_t rep4(uint32_t b) { return (b & 0xffu) * 0x01010101u; }
 
+// BSQ_TMA=0 selects the plain warp-per-row kernel; BSQ_TMA_CTAS caps the persistent grid (CTAs per SM).
+bool tma_enabled() {
+    static const bool on = [] { const char *e = std::getenv("BSQ_TMA"); return e == nullptr || e[0] != '0'; }();
+    return on;
+}
+int tma_ctas_per_sm() {
+    static const int n = [] { const char *e = std::getenv("BSQ_TMA_CTAS"); return e ? std::max(1, std::atoi(e)) : 6; }();
+    return n;
+}
+
 struct Prepared {
     LutParam lut;
     Specials sp;
@@ -665,6 +810,30 @@ int launch_bf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t /*ld*/, i
     // one-byte tokens: the codes are the output bytes (ids wrap to 8 bits like the reference's
     // int -> int8 store); wider types expand codes through Expand.
     const Prepared p = prepare(tok, sizeof(T) == 1 ? 0 : 1);
+    if (sizeof(T) == 1 && padlen % 16 == 0 && padlen > 256 && tma_enabled()) {
+        constexpr int NB = 3, WARPS = kThreads / 32;
+        const int bufsz = static_cast<int>((padlen + 48 + 15) / 16 * 16);
+        const size_t smem = static_cast<size_t>(WARPS) * NB * bufsz;
+        if (smem <= 100 * 1024) {
+            int dev = 0, sms = 0;
+            BSQ_CUDA_TRY(cudaGetDevice(&dev));
+            BSQ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+            const int fit = static_cast<int>((220 * 1024) / (smem + 4096));
+            const int per_sm = std::max(1, std::min(std::min(8, fit), tma_ctas_per_sm()));
+            const int64_t want = (nseq + WARPS - 1) / WARPS;
+            const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(want, static_cast<int64_t>(sms) * per_sm));
+            static bool attr_set = false;
+            if (!attr_set) {
+                BSQ_CUDA_TRY(cudaFuncSetAttribute(tokenize_rows_tma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+                attr_set = true;
+            }
+            tokenize_rows_tma_kernel<NB><<<blocks, kThreads, smem, st>>>(v, nseq, static_cast<int>(padlen), bufsz, p.lut, p.sp,
+                                                                          static_cast<uint8_t *>(d_out));
+            count_launch();
+            BSQ_CUDA_TRY(cudaGetLastError());
+            return BSQ_OK;
+        }
+    }
     if (sizeof(T) == 1 || (padlen * sizeof(T)) % 16 == 0) {
         int lanes_log2 = 0;  // lanes per row: smallest power of two covering the row, at most a warp
         while (lanes_log2 < 5 && (16ll << lanes_log2) < padlen + (sizeof(T) == 1 ? 15 : 0)) ++lanes_log2;
