@@ -223,7 +223,7 @@ tokenize_rows_tma_kernel(SeqView v, int64_t nseq, int padlen, int bufsz, LutPara
     __shared__ __align__(16) uint8_t lut[256];
     __shared__ TailTab tab;
     __shared__ __align__(8) uint64_t bars[WARPS * NB];
-    __shared__ __align__(16) RowInfo rinfo[WARPS][32];
+    __shared__ __align__(16) int4 rinfo[WARPS][32];  // per row: len, source byte shift, window origin, ring slot | parity
     load_lut(lut, lutp);
     init_tailtab(tab, sp);
     const int lane = threadIdx.x & 31;
@@ -237,61 +237,63 @@ tokenize_rows_tma_kernel(SeqView v, int64_t nseq, int padlen, int bufsz, LutPara
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
     const int64_t GW = static_cast<int64_t>(gridDim.x) * WARPS;
     const uint4 padv = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
-    uint32_t issued = 0, consumed = 0;  // rows with residues only; buffer = n % NB, parity = (n / NB) & 1
+    const int64_t row_pitch = GW * padlen;  // output distance between two consecutive rows of this warp
+    uint32_t seq_base = 0;                  // rows with residues handled so far (ring position)
 
     for (int64_t batch0 = gw; batch0 < nseq; batch0 += 32 * GW) {
-        // lane j resolves row batch0 + j*GW of this warp's next 32 rows
-        {
-            const int64_t myrow = batch0 + lane * GW;
-            RowInfo ri;
-            ri.al = nullptr; ri.off = 0; ri.len = 0;
-            if (myrow < nseq) {
-                const int64_t start = __ldg(v.offs + myrow);
-                ri.len = static_cast<int>(__ldg(v.offs + myrow + 1) - start);
-                const uint8_t *src = v.bytes + start - sp.bos;
-                ri.off = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
-                ri.al = src - ri.off;
+        // lane j resolves row batch0 + j*GW of this warp's next 32 rows: where its residues live,
+        // which aligned window has to be copied, and which ring slot the copy will use
+        const int64_t myrow = batch0 + lane * GW;
+        int mylen = 0, myoff = 0, myfw = 0;
+        uint32_t mybytes = 0;
+        const uint8_t *mysrc = nullptr;
+        if (myrow < nseq) {
+            const int64_t start = __ldg(v.offs + myrow);
+            mylen = static_cast<int>(__ldg(v.offs + myrow + 1) - start);
+            const uint8_t *src = v.bytes + start - sp.bos;
+            myoff = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
+            myfw = (myoff + sp.bos) & ~15;
+            if (mylen > 0) {
+                mybytes = static_cast<uint32_t>(((myoff + sp.bos + mylen - 1) & ~15) - myfw + 16);
+                mysrc = src - myoff + myfw;
             }
-            __syncwarp();
-            rinfo[warp][lane] = ri;
-            __syncwarp();
         }
+        const uint32_t has = __ballot_sync(0xffffffffu, mybytes != 0u);
+        const uint32_t myseq = seq_base + __popc(has & ((1u << lane) - 1u));
+        const uint32_t myslot = myseq % NB;
+        const uint32_t my_dst = smem_u32(mybuf + myslot * bufsz), my_bar = smem_u32(mybar + myslot);
+        __syncwarp();
+        rinfo[warp][lane] = make_int4(mylen, myoff, myfw, static_cast<int>(myslot | (((myseq / NB) & 1u) << 8) | (mybytes ? 0x10000u : 0u)));
+        __syncwarp();
+        seq_base += __popc(has);
         const int nrows = static_cast<int>(min(static_cast<int64_t>(32), (nseq - batch0 + GW - 1) / GW));
-        auto issue = [&](int j) {  // warp-uniform j
-            const RowInfo ri = rinfo[warp][j];
-            if (ri.len > 0) {
-                if (lane == 0) {
-                    const int fw = (ri.off + sp.bos) & ~15, lw = (ri.off + sp.bos + ri.len - 1) & ~15;
-                    const uint32_t bytes = static_cast<uint32_t>(lw - fw + 16);
-                    const uint32_t b = issued % NB;
-                    mbar_expect_tx(mybar + b, bytes);
-                    bulk_g2s(mybuf + b * bufsz, ri.al + fw, bytes, mybar + b);
-                }
-                ++issued;
+        // the lane that resolved a row also issues its copy (everything it needs is in its registers)
+        auto issue = [&](int j) {
+            if (lane == j && mybytes != 0u) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(my_bar), "r"(mybytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(my_dst),
+                             "l"(mysrc), "r"(mybytes), "r"(my_bar)
+                             : "memory");
             }
         };
         for (int j = 0; j < min(NB - 1, nrows); ++j) issue(j);
-        for (int j = 0; j < nrows; ++j) {
+        uint8_t *orow = out + batch0 * padlen;
+        for (int j = 0; j < nrows; ++j, orow += row_pitch) {
             if (j + NB - 1 < nrows) issue(j + NB - 1);
-            const RowInfo ri = rinfo[warp][j];
-            const int len = ri.len;
+            const int4 ri = rinfo[warp][j];
+            const int len = ri.x, off = ri.y, fw = ri.z;
             const int npos = sp.bos + len + sp.eos;
-            const int fw = (ri.off + sp.bos) & ~15;
-            const uint8_t *buf = mybuf + (consumed % NB) * bufsz;
-            if (len > 0) {
-                mbar_wait(mybar + consumed % NB, (consumed / NB) & 1u);
-                ++consumed;
-            }
+            const uint32_t slot = static_cast<uint32_t>(ri.w) & 0xffu;
+            const uint8_t *buf = mybuf + slot * bufsz;
+            if (ri.w & 0x10000) mbar_wait(mybar + slot, (static_cast<uint32_t>(ri.w) >> 8) & 1u);
             RowSrc rs;  // only .off is used by fetch_align
-            rs.al = nullptr; rs.off = ri.off; rs.fw = 0; rs.lw = 0;
-            uint8_t *orow = out + (batch0 + static_cast<int64_t>(j) * GW) * padlen;
+            rs.al = nullptr; rs.off = off; rs.fw = 0; rs.lw = 0;
             for (int c0 = 16 * lane; c0 < padlen; c0 += 512) {
                 uint4 codes = padv;
                 if (c0 < npos) {
                     uint32_t t[4] = {0u, 0u, 0u, 0u};
                     if (has_residues(c0, sp.bos, len)) {
-                        const int a = ri.off + c0;
-                        const int w0 = (a & ~15) - fw;  // window offset of the aligned word holding byte a (>= -16)
+                        const int w0 = ((off + c0) & ~15) - fw;  // window offset of the aligned word holding the chunk's first byte (>= -16)
                         Fetched f;
                         f.v0 = *reinterpret_cast<const uint4 *>(buf + max(w0, 0));
                         f.v1 = *reinterpret_cast<const uint4 *>(buf + w0 + 16);
@@ -746,7 +748,7 @@ bool tma_enabled() {
     return on;
 }
 int tma_ctas_per_sm() {
-    static const int n = [] { const char *e = std::getenv("BSQ_TMA_CTAS"); return e ? std::max(1, std::atoi(e)) : 6; }();
+    static const int n = [] { const char *e = std::getenv("BSQ_TMA_CTAS"); return e ? std::max(1, std::atoi(e)) : 4; }();
     return n;
 }
 

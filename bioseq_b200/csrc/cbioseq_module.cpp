@@ -513,8 +513,9 @@ private:
             else
                 rc = bsq_tokenize_host(ctx.stager, st, static_cast<const uint8_t *>(b.ptr), ho, n, padlen, &tok_, batch_first, kind,
                                        optr);
-            // the caller's arrays are only borrowed for the duration of the call
-            if (rc == BSQ_OK) rc = bsq_stager_sync_copies(ctx.stager);
+            // pageable arrays have been fully consumed (bounced through the pinned ring) on return;
+            // pinned arrays are read asynchronously like any cudaMemcpyAsync source: the caller must
+            // not overwrite them before the stream reaches this point.
         }
         check(rc, onehot);
         return out;

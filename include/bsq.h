@@ -159,8 +159,11 @@ int bsq_decode_chars(int device, void *stream, const void *d_tokens, int itemsiz
  * stream and launch its kernel on `stream` as soon as it lands, so the transfer of
  * range k+1 overlaps the compute of range k.  Inputs may be pinned (copied directly) or
  * pageable (bounced through the ring).  Lengths are checked first (bsq_check_lengths_host).
- * The calls return once all work is enqueued; the staging buffers stay owned by the
- * stager and are reused by the next call on it (which waits for the previous one). */
+ * The calls return once all work is enqueued.  Pageable sources have been fully read when
+ * the call returns; pinned sources are read asynchronously (cudaMemcpyAsync semantics: do
+ * not overwrite them until `stream` reaches this point, or call bsq_stager_sync_copies).
+ * The staging buffers stay owned by the stager and are reused by the next call on it
+ * (which waits for the previous one on the device, not on the host). */
 typedef struct bsq_stager bsq_stager;
 int bsq_stager_create(bsq_stager **out, int device);
 void bsq_stager_destroy(bsq_stager *s);

@@ -198,6 +198,27 @@ def test_unaligned_device_buffers_and_offset_base():
         assert_same_bits(want_o, out.cpu().numpy())
 
 
+@pytest.mark.parametrize("flags", [dict(), dict(bos=True, eos=True, padchar=True), dict(eos=True), dict(bos=True)])
+def test_tma_row_kernel_shapes(flags):
+    # one-byte batch-first output with padlen % 16 == 0 and > 256 goes through the persistent
+    # TMA-fed kernel: empty rows, rows that fill padlen exactly, every source alignment, more rows
+    # than one 32-row batch per warp of the persistent grid, and an unaligned residue buffer
+    tok, orc = capi.tokenizer("PROTEIN", **flags), OracleTokenizer("PROTEIN", **flags)
+    extra = int(flags.get("bos", False)) + int(flags.get("eos", False))
+    for n, padlen, hi in ((1, 272, 270), (3000, 272, 270 - extra + extra), (777, 1024, 1024), (65, 4096, 4096), (200_000, 272, 40)):
+        hi = min(hi, padlen) - extra
+        buf, offs = gen(1234 + n, n, 0, hi, MIX)
+        lens = np.diff(offs)
+        lens[:: max(1, n // 7)] = hi          # some rows exactly fill padlen
+        offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        buf = np.resize(buf, int(offs[-1]))
+        want = orc.batch_tokenize((buf, offs), padlen=padlen, batch_first=True)
+        assert_same_bits(want, abi_tokenize(tok, buf, offs, padlen, True, "B").cpu().numpy())
+        big = torch.zeros(buf.size + 64, dtype=torch.uint8, device="cuda")
+        big[5:5 + buf.size] = to_dev(buf)
+        assert_same_bits(want, abi_tokenize(tok, buf, offs, padlen, True, "B", d_bytes=big[5:]).cpu().numpy())
+
+
 def test_staged_pipeline_multi_chunk_and_reuse():
     # > 4 MiB of residues so the host-staged path runs several pipeline stages; odd batch size so the
     # last range is not a whole tile; pageable and pinned sources; back-to-back reuse of one stager.
@@ -422,3 +443,18 @@ def test_python_decode_many_rows():
     want = orc.decode_tokens(orc.batch_tokenize((buf, offs), padlen=304, batch_first=True))
     assert t.decode_tokens(toks) == want
     assert t.decode_tokens(toks.to(torch.int32)) == want
+
+
+def test_sharded_equals_single_device():
+    # shards are independent; concatenating them reproduces the unsharded output.
+    from bioseq_b200.shard import tokenize_sharded
+    t = bioseq_b200.pbeos_tokenizers["PROTEIN"]
+    buf, offs = gen(88, 30_001, 0, 600, b"ACDEFGHIKLMNPQRSTVWYX")
+    full_bf = t.batch_tokenize_packed(buf, offs, padlen=608, batch_first=True)
+    full_sf = t.batch_tokenize_packed(buf, offs, padlen=608, batch_first=False)
+    for world in (2, 3, 8):
+        parts = [tokenize_sharded(t, buf, offs, 608, world, r, batch_first=True) for r in range(world)]
+        assert [p[1][0] for p in parts][0] == 0 and parts[-1][1][1] == 30_001
+        assert torch.equal(torch.cat([p[0] for p in parts], dim=0), full_bf)
+        parts = [tokenize_sharded(t, buf, offs, 608, world, r, batch_first=False)[0] for r in range(world)]
+        assert torch.equal(torch.cat(parts, dim=1), full_sf)
