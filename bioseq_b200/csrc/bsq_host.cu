@@ -299,7 +299,7 @@ int staged_run(bsq_stager *s, cudaStream_t st, const uint8_t *h_bytes, const int
         } else {
             const size_t off = batch_first ? static_cast<size_t>(i0) * padlen * esize : static_cast<size_t>(i0) * esize;
             rc = bsq::launch_tokenize(st, d_bytes_shifted, s->d_offs + i0, i1 - i0, nseq, padlen, *tok, batch_first, kind,
-                                      static_cast<uint8_t *>(d_out) + off);
+                                      static_cast<uint8_t *>(d_out) + off, /*first_off=*/h_offs[i0]);
         }
         if (rc) return rc;
         i0 = i1;

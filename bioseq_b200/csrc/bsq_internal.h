@@ -16,9 +16,11 @@ void count_launch(int n = 1);
 #ifdef __CUDACC__
 // Launchers shared by the device entry points and the host-staged pipeline.  `nseq`
 // sequences starting at d_offs[0] are processed; `ld` is the batch extent of the whole
-// output array and d_out points at this range's first row (batch-first) / column.
+// output array and d_out points at this range's first row (batch-first) / column.  first_off is
+// d_offs[0] when the host knows it (-1 otherwise): it lets the TMA-fed kernel anchor its tensor map
+// at the range's first residue so that coordinates stay small for sub-ranges of huge buffers.
 int launch_tokenize(cudaStream_t st, const uint8_t *d_bytes, const int64_t *d_offs, int64_t nseq, int64_t ld,
-                    int64_t padlen, const bsq_tokenizer &tok, int batch_first, int kind, void *d_out);
+                    int64_t padlen, const bsq_tokenizer &tok, int batch_first, int kind, void *d_out, int64_t first_off);
 int launch_onehot(cudaStream_t st, const uint8_t *d_bytes, const int64_t *d_offs, const uint8_t *d_mask, int64_t nseq,
                   int64_t ld, int64_t padlen, const bsq_tokenizer &tok, int kind, void *d_out);
 int check_launch_args(int device, int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int kind, const void *d_out);

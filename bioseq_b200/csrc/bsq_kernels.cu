@@ -176,19 +176,7 @@ tokenize_rows_kernel(SeqView v, int64_t nseq, int padlen, int lanes_log2, LutPar
     }
 }
 
-// ------------------------------------------------------------------------------------------
-// K1t: the same batch-first one-byte tokeniser as a persistent, TMA-fed kernel.
-//
-// Every warp owns a ring of NB shared-memory row buffers.  One elected lane issues a 1-D bulk
-// asynchronous copy (cp.async.bulk global -> shared, completion counted on an mbarrier) of the
-// 16-byte-aligned window that holds a row's residues, NB-1 rows ahead of the row being
-// translated, so the HBM latency of a row is overlapped with the LUT work of the previous rows
-// instead of being exposed once per row per warp.  Rows are dealt round-robin to the warps of
-// the whole grid (consecutive warps work on consecutive rows: the packed residues are read as
-// one contiguous stream).  Offsets of up to 32 upcoming rows are loaded one row per lane and
-// handed around through a small per-warp shared-memory table.
-// Requires padlen % 16 == 0 (rows 16-byte aligned in the output).
-// ------------------------------------------------------------------------------------------
+// ---- PTX helpers: mbarrier + 1-D bulk asynchronous copy (TMA unit, SASS UBLKCP) ----
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -201,69 +189,165 @@ __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, u
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+
+// ------------------------------------------------------------------------------------------
+// K1r: batch-first one-byte tokens, persistent, bulk-copy fed, realignment specialised per row.
+//
+// Every warp owns a ring of NB shared-memory row buffers with one mbarrier each.  The lane that
+// resolved a row issues a 1-D bulk asynchronous copy (cp.async.bulk global -> shared, completion
+// counted on the mbarrier) of the 16-byte-aligned window that holds the row's residues, NB-1 rows
+// ahead of the row being translated, so a row's HBM latency is hidden behind the LUT work of the
+// previous rows.  Rows are dealt round-robin to the warps of the persistent grid (consecutive
+// warps read consecutive rows: the packed residues are consumed as one contiguous stream).
+// Per 16-byte output vector the work is the 16 LUT look-ups plus a handful of instructions:
+//   * the row's shared-memory window is addressed so that the two LDS.128 of a vector need no
+//     clamping (32 bytes of slack in front, 16 behind; whatever lies there is masked out by the
+//     BOS / tail fix-ups),
+//   * the byte shift between the packed source and the 16-byte aligned output vectors is constant
+//     along a row and uniform across the warp, so the row loop is instantiated four times (word
+//     shift Q = 0..3) and entered through one uniform branch per row: realignment is four funnel
+//     shifts with compile-time word selection instead of a data-dependent select tree,
+//   * rows whose padlen is not a multiple of 16 use the same code: vectors are aligned in the
+//     *flat* output (index i = r + column, r = misalignment of the row's first byte), the shift
+//     absorbs r, and only the (at most two) vectors a row shares with its neighbours are stored
+//     piecewise.
+// (A tensor-map TMA copy cannot do the realignment: cp.async.bulk.tensor needs the box start to be
+// 16-byte aligned in global memory -- tools/probes/tma1d_probe.cu -- exactly like the 1-D bulk copy.)
+// ------------------------------------------------------------------------------------------
+constexpr int kSlack = 32;
+
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar_smem, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
+        "BSQ_WAIT_%=:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
+        "@!p bra BSQ_WAIT_%=;\n"
+        "}\n" ::"r"(bar_smem),
         "r"(parity)
         : "memory");
 }
 
-template <int NB>
+// Store bytes [lo, hi) of a 16-byte vector (staged in this lane's 16 bytes of shared memory) with
+// at most four naturally aligned stores per side.  dst is 16-byte aligned.
+__device__ __forceinline__ void store_partial16(uint8_t *dst, const uint8_t *stg, int lo, int hi) {
+    int p = lo;
+    if (hi - p >= 1 && (p & 1)) { dst[p] = stg[p]; p += 1; }
+    if (hi - p >= 2 && (p & 2)) { *reinterpret_cast<uint16_t *>(dst + p) = *reinterpret_cast<const uint16_t *>(stg + p); p += 2; }
+    if (hi - p >= 4 && (p & 4)) { *reinterpret_cast<uint32_t *>(dst + p) = *reinterpret_cast<const uint32_t *>(stg + p); p += 4; }
+    if (hi - p >= 8 && (p & 8)) { *reinterpret_cast<uint2 *>(dst + p) = *reinterpret_cast<const uint2 *>(stg + p); p += 8; }
+    if (hi - p >= 8) { *reinterpret_cast<uint2 *>(dst + p) = *reinterpret_cast<const uint2 *>(stg + p); p += 8; }
+    if (hi - p >= 4) { *reinterpret_cast<uint32_t *>(dst + p) = *reinterpret_cast<const uint32_t *>(stg + p); p += 4; }
+    if (hi - p >= 2) { *reinterpret_cast<uint16_t *>(dst + p) = *reinterpret_cast<const uint16_t *>(stg + p); p += 2; }
+    if (hi - p >= 1) { dst[p] = stg[p]; }
+}
+
+// All vectors of one row.  Index space: i = r + column (i0 a multiple of 16 <=> the vector is 16-byte
+// aligned in the flat output at oal + i0).  rowbase + i is the shared-memory address of the aligned
+// 16-byte source word that holds the byte of index i0's first column; Q/sh = word/bit part of the
+// source-to-output byte shift.
+template <int Q, bool ALIGNED>
+__device__ __forceinline__ void row_vectors(const uint8_t *rowbase, uint32_t sh, int r, int first, int n, int npos, int total,
+                                            uint8_t *oal, int lane, const Specials &sp, const uint8_t *lut, const TailTab &tab,
+                                            uint8_t *pstage) {
+    const uint4 padv = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
+    for (int i0 = 16 * lane; i0 < total; i0 += 512) {
+        uint4 codes = padv;
+        if (i0 < npos) {
+            uint32_t t[4] = {0u, 0u, 0u, 0u};
+            if (i0 < n && (ALIGNED || i0 + 16 > first)) {
+                const uint4 v0 = *reinterpret_cast<const uint4 *>(rowbase + i0);
+                const uint4 v1 = *reinterpret_cast<const uint4 *>(rowbase + i0 + 16);
+                const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) t[k] = translate4(__funnelshift_r(w[Q + k], w[Q + k + 1], sh), lut);
+            }
+            if (ALIGNED) {
+                if (sp.bos && i0 == 0) t[0] = __byte_perm(t[0], sp.bos_w, 0x3214);
+            } else if (sp.bos && i0 <= r && r < i0 + 16) {  // byte r - i0 of this vector is BOS
+                const uint4 ma = tab.m[r - i0], mb = tab.m[r - i0 + 1];
+                t[0] = (t[0] & ~(mb.x & ~ma.x)) | (sp.bos_w & mb.x & ~ma.x);
+                t[1] = (t[1] & ~(mb.y & ~ma.y)) | (sp.bos_w & mb.y & ~ma.y);
+                t[2] = (t[2] & ~(mb.z & ~ma.z)) | (sp.bos_w & mb.z & ~ma.z);
+                t[3] = (t[3] & ~(mb.w & ~ma.w)) | (sp.bos_w & mb.w & ~ma.w);
+            }
+            if (i0 + 16 > n) {  // the row ends inside this vector: keep n - i0 bytes, then EOS / pad
+                const uint4 m = tab.m[n - i0], f = tab.f[n - i0];
+                t[0] = (t[0] & m.x) | f.x; t[1] = (t[1] & m.y) | f.y;
+                t[2] = (t[2] & m.z) | f.z; t[3] = (t[3] & m.w) | f.w;
+            }
+            codes = make_uint4(t[0], t[1], t[2], t[3]);
+        }
+        if (ALIGNED || (i0 >= r && i0 + 16 <= total)) {
+            __stcs(reinterpret_cast<uint4 *>(oal + i0), codes);
+        } else {  // the (at most two) vectors shared with the neighbouring rows
+            uint8_t *stg = pstage + 16 * lane;
+            *reinterpret_cast<uint4 *>(stg) = codes;
+            store_partial16(oal + i0, stg, max(r - i0, 0), min(total - i0, 16));
+        }
+    }
+}
+
+template <int NB, bool ALIGNED>
 __global__ void __launch_bounds__(kThreads)
-tokenize_rows_tma_kernel(SeqView v, int64_t nseq, int padlen, int bufsz, LutParam lutp, Specials sp, uint8_t *__restrict__ out) {
+tokenize_rows_ring_kernel(SeqView v, int64_t nseq, int padlen, int bufsz, LutParam lutp, Specials sp, uint8_t *__restrict__ out) {
     constexpr int WARPS = kThreads / 32;
     extern __shared__ __align__(128) uint8_t ring[];  // WARPS * NB * bufsz
     __shared__ __align__(16) uint8_t lut[256];
     __shared__ TailTab tab;
     __shared__ __align__(8) uint64_t bars[WARPS * NB];
-    __shared__ __align__(16) int4 rinfo[WARPS][32];  // per row: len, source byte shift, window origin, ring slot | parity
+    __shared__ __align__(16) int4 rinfo[WARPS][32];  // per row: len, rowbase offset in the slot, shift | slot | parity | copy flag, r
+    __shared__ __align__(16) uint8_t pstage[ALIGNED ? 16 : WARPS * 512];
+    // Programmatic dependent launch: let the next kernel of the stream start its own prologue now,
+    // and do ours (LUT, tail tables, barriers: no global memory) before waiting for the previous
+    // kernel of the stream to finish.  Both are no-ops for launches without the PDL attribute.
+    asm volatile("griddepcontrol.launch_dependents;");
     load_lut(lut, lutp);
     init_tailtab(tab, sp);
     const int lane = threadIdx.x & 31;
     const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
     uint64_t *mybar = bars + warp * NB;
+    const uint32_t bar0 = smem_u32(mybar);
     uint8_t *mybuf = ring + static_cast<size_t>(warp) * NB * bufsz;
     if (lane < NB) mbar_init(mybar + lane, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * WARPS + warp;
     const int64_t GW = static_cast<int64_t>(gridDim.x) * WARPS;
-    const uint4 padv = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
     const int64_t row_pitch = GW * padlen;  // output distance between two consecutive rows of this warp
     uint32_t seq_base = 0;                  // rows with residues handled so far (ring position)
 
     for (int64_t batch0 = gw; batch0 < nseq; batch0 += 32 * GW) {
-        // lane j resolves row batch0 + j*GW of this warp's next 32 rows: where its residues live,
-        // which aligned window has to be copied, and which ring slot the copy will use
+        // lane j resolves row batch0 + j*GW of this warp's next 32 rows: the aligned window that has
+        // to be copied, the ring slot it will use, and the row's source-to-output byte shift
         const int64_t myrow = batch0 + lane * GW;
-        int mylen = 0, myoff = 0, myfw = 0;
+        int mylen = 0, myr = 0, myrb = 0, myshift = 0;
         uint32_t mybytes = 0;
         const uint8_t *mysrc = nullptr;
         if (myrow < nseq) {
             const int64_t start = __ldg(v.offs + myrow);
             mylen = static_cast<int>(__ldg(v.offs + myrow + 1) - start);
-            const uint8_t *src = v.bytes + start - sp.bos;
-            myoff = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
-            myfw = (myoff + sp.bos) & ~15;
+            const uint8_t *src = v.bytes + start - sp.bos;  // source of column 0
+            const int off = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
+            const int fw = (off + sp.bos) & ~15;            // first aligned word that holds a residue (0 or 16)
+            myr = ALIGNED ? 0 : static_cast<int>((myrow * padlen) & 15);
+            const int d = off - myr;                        // source position (relative to src - off) of index 0
+            myshift = d & 15;
+            myrb = kSlack + (d < 0 ? -16 : 0) - fw;         // slot offset of the aligned word holding index 0
             if (mylen > 0) {
-                mybytes = static_cast<uint32_t>(((myoff + sp.bos + mylen - 1) & ~15) - myfw + 16);
-                mysrc = src - myoff + myfw;
+                mybytes = static_cast<uint32_t>(((off + sp.bos + mylen - 1) & ~15) - fw + 16);
+                mysrc = src - off + fw;
             }
         }
         const uint32_t has = __ballot_sync(0xffffffffu, mybytes != 0u);
         const uint32_t myseq = seq_base + __popc(has & ((1u << lane) - 1u));
         const uint32_t myslot = myseq % NB;
-        const uint32_t my_dst = smem_u32(mybuf + myslot * bufsz), my_bar = smem_u32(mybar + myslot);
+        const uint32_t my_dst = smem_u32(mybuf + myslot * bufsz + kSlack), my_bar = bar0 + 8u * myslot;
         __syncwarp();
-        rinfo[warp][lane] = make_int4(mylen, myoff, myfw, static_cast<int>(myslot | (((myseq / NB) & 1u) << 8) | (mybytes ? 0x10000u : 0u)));
+        rinfo[warp][lane] = make_int4(mylen, myrb + static_cast<int>(myslot) * bufsz,
+                                      myshift | static_cast<int>(myslot << 8) | static_cast<int>(((myseq / NB) & 1u) << 12) | (mybytes ? 0x10000 : 0), myr);
         __syncwarp();
         seq_base += __popc(has);
         const int nrows = static_cast<int>(min(static_cast<int64_t>(32), (nseq - batch0 + GW - 1) / GW));
@@ -280,31 +364,19 @@ tokenize_rows_tma_kernel(SeqView v, int64_t nseq, int padlen, int bufsz, LutPara
         uint8_t *orow = out + batch0 * padlen;
         for (int j = 0; j < nrows; ++j, orow += row_pitch) {
             if (j + NB - 1 < nrows) issue(j + NB - 1);
-            const int4 ri = rinfo[warp][j];
-            const int len = ri.x, off = ri.y, fw = ri.z;
-            const int npos = sp.bos + len + sp.eos;
-            const uint32_t slot = static_cast<uint32_t>(ri.w) & 0xffu;
-            const uint8_t *buf = mybuf + slot * bufsz;
-            if (ri.w & 0x10000) mbar_wait(mybar + slot, (static_cast<uint32_t>(ri.w) >> 8) & 1u);
-            RowSrc rs;  // only .off is used by fetch_align
-            rs.al = nullptr; rs.off = off; rs.fw = 0; rs.lw = 0;
-            for (int c0 = 16 * lane; c0 < padlen; c0 += 512) {
-                uint4 codes = padv;
-                if (c0 < npos) {
-                    uint32_t t[4] = {0u, 0u, 0u, 0u};
-                    if (has_residues(c0, sp.bos, len)) {
-                        const int w0 = ((off + c0) & ~15) - fw;  // window offset of the aligned word holding the chunk's first byte (>= -16)
-                        Fetched f;
-                        f.v0 = *reinterpret_cast<const uint4 *>(buf + max(w0, 0));
-                        f.v1 = *reinterpret_cast<const uint4 *>(buf + w0 + 16);
-                        uint32_t raw[4];
-                        fetch_align(f, rs, c0, raw);
-#pragma unroll
-                        for (int w = 0; w < 4; ++w) t[w] = translate4(raw[w], lut);
-                    }
-                    codes = tokens16_finish<false>(t, len, c0, sp, tab);
-                }
-                __stcs(reinterpret_cast<uint4 *>(orow + c0), codes);
+            const int4 q = rinfo[warp][j];
+            const int len = q.x, r = ALIGNED ? 0 : q.w;
+            const int first = r + sp.bos, n = first + len, npos = n + sp.eos, total = r + padlen;
+            const uint8_t *rowbase = mybuf + q.y;
+            const uint32_t sh = (static_cast<uint32_t>(q.z) & 3u) * 8u;
+            if (q.z & 0x10000) mbar_wait_u32(bar0 + 8u * ((static_cast<uint32_t>(q.z) >> 8) & 0xfu), (static_cast<uint32_t>(q.z) >> 12) & 1u);
+            uint8_t *oal = orow - r;
+            uint8_t *ps = pstage + (ALIGNED ? 0 : warp * 512);
+            switch ((q.z >> 2) & 3) {  // warp-uniform
+                case 0: row_vectors<0, ALIGNED>(rowbase, sh, r, first, n, npos, total, oal, lane, sp, lut, tab, ps); break;
+                case 1: row_vectors<1, ALIGNED>(rowbase, sh, r, first, n, npos, total, oal, lane, sp, lut, tab, ps); break;
+                case 2: row_vectors<2, ALIGNED>(rowbase, sh, r, first, n, npos, total, oal, lane, sp, lut, tab, ps); break;
+                default: row_vectors<3, ALIGNED>(rowbase, sh, r, first, n, npos, total, oal, lane, sp, lut, tab, ps); break;
             }
             __syncwarp();  // every lane is done with this buffer before it is refilled
         }
@@ -742,13 +814,22 @@ namespace {
 
 inline uint32_t rep4(uint32_t b) { return (b & 0xffu) * 0x01010101u; }
 
-// BSQ_TMA=0 selects the plain warp-per-row kernel; BSQ_TMA_CTAS caps the persistent grid (CTAs per SM).
-bool tma_enabled() {
-    static const bool on = [] { const char *e = std::getenv("BSQ_TMA"); return e == nullptr || e[0] != '0'; }();
+// Debug / A-B knobs: BSQ_RING=0 falls back to the plain warp-per-row kernel (K1), BSQ_RING_CTAS caps the
+// persistent grid (CTAs per SM, default 4), BSQ_PDL=0 disables programmatic dependent launch.
+int env_int(const char *name, int dflt) {
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+bool ring_enabled() {
+    static const bool on = env_int("BSQ_RING", 1) != 0;
     return on;
 }
-int tma_ctas_per_sm() {
-    static const int n = [] { const char *e = std::getenv("BSQ_TMA_CTAS"); return e ? std::max(1, std::atoi(e)) : 4; }();
+bool pdl_enabled() {
+    static const bool on = env_int("BSQ_PDL", 1) != 0;
+    return on;
+}
+int ring_ctas_per_sm() {
+    static const int n = std::max(1, env_int("BSQ_RING_CTAS", 4));
     return n;
 }
 
@@ -808,31 +889,47 @@ int check_common(int device, int64_t nseq, int64_t padlen, const bsq_tokenizer *
 }
 
 template <typename T>
-int launch_bf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t /*ld*/, int64_t padlen, const bsq_tokenizer &tok, void *d_out) {
+int launch_bf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t /*ld*/, int64_t padlen, const bsq_tokenizer &tok, void *d_out,
+              int64_t first_off) {
     // one-byte tokens: the codes are the output bytes (ids wrap to 8 bits like the reference's
     // int -> int8 store); wider types expand codes through Expand.
     const Prepared p = prepare(tok, sizeof(T) == 1 ? 0 : 1);
-    if (sizeof(T) == 1 && padlen % 16 == 0 && padlen > 256 && tma_enabled()) {
-        constexpr int NB = 3, WARPS = kThreads / 32;
-        const int bufsz = static_cast<int>((padlen + 48 + 15) / 16 * 16);
+    if (sizeof(T) == 1 && padlen > 256 && ring_enabled()) {
+        // K1r: persistent, bulk-copy fed, per-row specialised realignment; any padlen that fits the ring
+        constexpr int WARPS = kThreads / 32, NB = 2;
+        const bool aligned = padlen % 16 == 0;
+        const int bufsz = static_cast<int>((padlen + 80 + 15) / 16 * 16);
         const size_t smem = static_cast<size_t>(WARPS) * NB * bufsz;
-        if (smem <= 100 * 1024) {
+        if (smem <= 200 * 1024) {
             int dev = 0, sms = 0;
             BSQ_CUDA_TRY(cudaGetDevice(&dev));
             BSQ_CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-            const int fit = static_cast<int>((220 * 1024) / (smem + 4096));
-            const int per_sm = std::max(1, std::min(std::min(8, fit), tma_ctas_per_sm()));
+            const size_t per_cta = smem + 8192;  // + static shared memory and allocation granularity
+            const int fit = static_cast<int>((220 * 1024) / per_cta);
+            const int per_sm = std::max(1, std::min(std::min(8, fit), ring_ctas_per_sm()));
             const int64_t want = (nseq + WARPS - 1) / WARPS;
             const unsigned blocks = static_cast<unsigned>(std::min<int64_t>(want, static_cast<int64_t>(sms) * per_sm));
-            static bool attr_set = false;
-            if (!attr_set) {
-                BSQ_CUDA_TRY(cudaFuncSetAttribute(tokenize_rows_tma_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                attr_set = true;
-            }
-            tokenize_rows_tma_kernel<NB><<<blocks, kThreads, smem, st>>>(v, nseq, static_cast<int>(padlen), bufsz, p.lut, p.sp,
-                                                                          static_cast<uint8_t *>(d_out));
+            // Programmatic dependent launch hides this launch's ramp behind the previous kernel's tail.  The
+            // early CTAs sit next to the previous kernel's, so it is only used when two whole persistent grids
+            // fit on the SMs at once -- otherwise the late CTAs pile up on the first SMs to drain and the
+            // static row partition becomes unbalanced (measured: 2x slower).
+            const bool pdl = pdl_enabled() && 2 * per_sm * per_cta <= 220 * 1024 && 2 * per_sm * kThreads <= 2048;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(blocks);
+            cfg.blockDim = dim3(kThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = pdl ? 1 : 0;
+            const int pl = static_cast<int>(padlen);
+            uint8_t *o = static_cast<uint8_t *>(d_out);
+            auto kern = aligned ? tokenize_rows_ring_kernel<NB, true> : tokenize_rows_ring_kernel<NB, false>;
+            BSQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            BSQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, v, nseq, pl, bufsz, p.lut, p.sp, o));
             count_launch();
-            BSQ_CUDA_TRY(cudaGetLastError());
             return BSQ_OK;
         }
     }
@@ -870,7 +967,8 @@ int launch_bf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t /*ld*/, i
 }
 
 template <typename T, bool ONEHOT>
-int launch_sf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t ld, int64_t padlen, const bsq_tokenizer &tok, void *d_out) {
+int launch_sf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t ld, int64_t padlen, const bsq_tokenizer &tok, void *d_out,
+              int64_t /*first_off*/) {
     const Prepared p = prepare(tok, ONEHOT ? 2 : 1);
     const int64_t gx = (nseq + kTileSeqs - 1) / kTileSeqs, gy = (padlen + kTilePos - 1) / kTilePos;
     if (gx > 0x7fffffffll || gy > 65535) return fail(BSQ_ERR_ARG, "batch too large for one launch");
@@ -920,18 +1018,18 @@ InvParam make_inv(const bsq_tokenizer &tok) {
 
 #define BSQ_DISPATCH(FN, ...)                                                               \
     switch (kind) {                                                                         \
-        case BSQ_I8: return FN<int8_t __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out);    \
-        case BSQ_I16: return FN<int16_t __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out);  \
-        case BSQ_I32: return FN<int32_t __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out);  \
-        case BSQ_I64: return FN<int64_t __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out);  \
-        case BSQ_F32: return FN<float __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out);    \
-        default: return FN<double __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out);        \
+        case BSQ_I8: return FN<int8_t __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out, first_off);    \
+        case BSQ_I16: return FN<int16_t __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out, first_off);  \
+        case BSQ_I32: return FN<int32_t __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out, first_off);  \
+        case BSQ_I64: return FN<int64_t __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out, first_off);  \
+        case BSQ_F32: return FN<float __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out, first_off);    \
+        default: return FN<double __VA_ARGS__>(st, v, nseq, ld, padlen, tok, d_out, first_off);        \
     }
 #define BSQ_COMMA_FALSE , false
 #define BSQ_COMMA_TRUE , true
 
 int launch_tokenize(cudaStream_t st, const uint8_t *d_bytes, const int64_t *d_offs, int64_t nseq, int64_t ld,
-                    int64_t padlen, const bsq_tokenizer &tok, int batch_first, int kind, void *d_out) {
+                    int64_t padlen, const bsq_tokenizer &tok, int batch_first, int kind, void *d_out, int64_t first_off) {
     if (nseq <= 0) return BSQ_OK;
     const SeqView v{d_bytes, d_offs, nullptr};
     if (batch_first) {
@@ -946,6 +1044,7 @@ int launch_onehot(cudaStream_t st, const uint8_t *d_bytes, const int64_t *d_offs
     if (nseq <= 0) return BSQ_OK;
     if (static_cast<int64_t>(kTileSeqs) * tok.alphabet_size > 0x7fffffffll) return fail(BSQ_ERR_ARG, "alphabet too large");
     const SeqView v{d_bytes, d_offs, d_mask};
+    const int64_t first_off = -1;
     BSQ_DISPATCH(launch_sf, BSQ_COMMA_TRUE)
 }
 
@@ -965,7 +1064,7 @@ int bsq_tokenize(int device, void *stream, const uint8_t *d_bytes, const int64_t
     if (nseq == 0) return BSQ_OK;
     if (d_offsets == nullptr) return fail(BSQ_ERR_ARG, "null offsets");
     return launch_tokenize(static_cast<cudaStream_t>(stream), d_bytes, d_offsets, nseq, nseq, padlen, *tok, batch_first,
-                           kind, d_out);
+                           kind, d_out, /*first_off=*/-1);
 }
 
 int bsq_onehot(int device, void *stream, const uint8_t *d_bytes, const int64_t *d_offsets, const uint8_t *d_mask,
