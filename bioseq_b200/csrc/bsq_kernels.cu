@@ -246,16 +246,20 @@ __device__ __forceinline__ void store_partial16(uint8_t *dst, const uint8_t *stg
 // aligned in the flat output at oal + i0).  rowbase + i is the shared-memory address of the aligned
 // 16-byte source word that holds the byte of index i0's first column; Q/sh = word/bit part of the
 // source-to-output byte shift.
+// ptail: (unaligned rows only) the codes of the previous row's last r columns, i.e. bytes [0, r) of
+// this row's first vector -- a row owns every aligned vector that ENDS inside it, so all stores are
+// whole vectors; `lim` is where this row's ownership ends (total rounded down to 16, except for the
+// last row of the launch, which also stores its final partial vector).
 template <int Q, bool ALIGNED>
-__device__ __forceinline__ void row_vectors(const uint8_t *rowbase, uint32_t sh, int r, int first, int n, int npos, int total,
+__device__ __forceinline__ void row_vectors(const uint8_t *rowbase, uint32_t sh, int r, int n, int npos, int lim, int total,
                                             uint8_t *oal, int lane, const Specials &sp, const uint8_t *lut, const TailTab &tab,
-                                            uint8_t *pstage) {
+                                            const uint4 &ptail, uint8_t *pstage) {
     const uint4 padv = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
-    for (int i0 = 16 * lane; i0 < total; i0 += 512) {
+    for (int i0 = 16 * lane; i0 < lim; i0 += 512) {
         uint4 codes = padv;
         if (i0 < npos) {
             uint32_t t[4] = {0u, 0u, 0u, 0u};
-            if (i0 < n && (ALIGNED || i0 + 16 > first)) {
+            if (i0 < n) {
                 const uint4 v0 = *reinterpret_cast<const uint4 *>(rowbase + i0);
                 const uint4 v1 = *reinterpret_cast<const uint4 *>(rowbase + i0 + 16);
                 const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -264,12 +268,12 @@ __device__ __forceinline__ void row_vectors(const uint8_t *rowbase, uint32_t sh,
             }
             if (ALIGNED) {
                 if (sp.bos && i0 == 0) t[0] = __byte_perm(t[0], sp.bos_w, 0x3214);
-            } else if (sp.bos && i0 <= r && r < i0 + 16) {  // byte r - i0 of this vector is BOS
-                const uint4 ma = tab.m[r - i0], mb = tab.m[r - i0 + 1];
-                t[0] = (t[0] & ~(mb.x & ~ma.x)) | (sp.bos_w & mb.x & ~ma.x);
-                t[1] = (t[1] & ~(mb.y & ~ma.y)) | (sp.bos_w & mb.y & ~ma.y);
-                t[2] = (t[2] & ~(mb.z & ~ma.z)) | (sp.bos_w & mb.z & ~ma.z);
-                t[3] = (t[3] & ~(mb.w & ~ma.w)) | (sp.bos_w & mb.w & ~ma.w);
+            } else if (i0 == 0) {  // bytes [0, r): the previous row's tail; byte r: BOS
+                const uint4 ma = tab.m[r], mb = tab.m[r + sp.bos];
+                t[0] = (t[0] & ~mb.x) | (sp.bos_w & mb.x & ~ma.x) | (ptail.x & ma.x);
+                t[1] = (t[1] & ~mb.y) | (sp.bos_w & mb.y & ~ma.y) | (ptail.y & ma.y);
+                t[2] = (t[2] & ~mb.z) | (sp.bos_w & mb.z & ~ma.z) | (ptail.z & ma.z);
+                t[3] = (t[3] & ~mb.w) | (sp.bos_w & mb.w & ~ma.w) | (ptail.w & ma.w);
             }
             if (i0 + 16 > n) {  // the row ends inside this vector: keep n - i0 bytes, then EOS / pad
                 const uint4 m = tab.m[n - i0], f = tab.f[n - i0];
@@ -278,12 +282,12 @@ __device__ __forceinline__ void row_vectors(const uint8_t *rowbase, uint32_t sh,
             }
             codes = make_uint4(t[0], t[1], t[2], t[3]);
         }
-        if (ALIGNED || (i0 >= r && i0 + 16 <= total)) {
+        if (ALIGNED || i0 + 16 <= total) {
             __stcs(reinterpret_cast<uint4 *>(oal + i0), codes);
-        } else {  // the (at most two) vectors shared with the neighbouring rows
+        } else {  // final partial vector of the launch's last row
             uint8_t *stg = pstage + 16 * lane;
             *reinterpret_cast<uint4 *>(stg) = codes;
-            store_partial16(oal + i0, stg, max(r - i0, 0), min(total - i0, 16));
+            store_partial16(oal + i0, stg, 0, total - i0);
         }
     }
 }
@@ -296,8 +300,10 @@ tokenize_rows_ring_kernel(SeqView v, int64_t nseq, int padlen, int bufsz, LutPar
     __shared__ __align__(16) uint8_t lut[256];
     __shared__ TailTab tab;
     __shared__ __align__(8) uint64_t bars[WARPS * NB];
-    __shared__ __align__(16) int4 rinfo[WARPS][32];  // per row: len, rowbase offset in the slot, shift | slot | parity | copy flag, r
+    __shared__ __align__(16) int4 rinfo[WARPS][32];  // per row: len, rowbase offset in the slot, shift | slot | parity | copy flag, r | flags
     __shared__ __align__(16) uint8_t pstage[ALIGNED ? 16 : WARPS * 512];
+    __shared__ int64_t rstart[ALIGNED ? 1 : WARPS][32];  // unaligned rows: first residue and the previous row's length,
+    __shared__ int rprev[ALIGNED ? 1 : WARPS][32];       // read only when that row reaches into this row's first vector
     // Programmatic dependent launch: let the next kernel of the stream start its own prologue now,
     // and do ours (LUT, tail tables, barriers: no global memory) before waiting for the previous
     // kernel of the stream to finish.  Both are no-ops for launches without the PDL attribute.
@@ -329,11 +335,20 @@ tokenize_rows_ring_kernel(SeqView v, int64_t nseq, int padlen, int bufsz, LutPar
         if (myrow < nseq) {
             const int64_t start = __ldg(v.offs + myrow);
             mylen = static_cast<int>(__ldg(v.offs + myrow + 1) - start);
+            if (!ALIGNED) {
+                myr = static_cast<int>((myrow * padlen) & 15);
+                if (myrow == nseq - 1) myr |= 0x200;  // last row of the launch: also stores its final partial vector
+                if ((myr & 15) != 0) {                // (row 0 starts a vector, so there is a previous row)
+                    const int plen = static_cast<int>(start - __ldg(v.offs + myrow - 1));
+                    if (sp.bos + plen + sp.eos > padlen - (myr & 15)) myr |= 0x100;  // its EOS / residues reach into our first vector
+                    rstart[warp][lane] = start;
+                    rprev[warp][lane] = plen;
+                }
+            }
             const uint8_t *src = v.bytes + start - sp.bos;  // source of column 0
             const int off = static_cast<int>(reinterpret_cast<uintptr_t>(src) & 15u);
             const int fw = (off + sp.bos) & ~15;            // first aligned word that holds a residue (0 or 16)
-            myr = ALIGNED ? 0 : static_cast<int>((myrow * padlen) & 15);
-            const int d = off - myr;                        // source position (relative to src - off) of index 0
+            const int d = off - (myr & 15);                 // source position (relative to src - off) of index 0
             myshift = d & 15;
             myrb = kSlack + (d < 0 ? -16 : 0) - fw;         // slot offset of the aligned word holding index 0
             if (mylen > 0) {
@@ -365,18 +380,35 @@ tokenize_rows_ring_kernel(SeqView v, int64_t nseq, int padlen, int bufsz, LutPar
         for (int j = 0; j < nrows; ++j, orow += row_pitch) {
             if (j + NB - 1 < nrows) issue(j + NB - 1);
             const int4 q = rinfo[warp][j];
-            const int len = q.x, r = ALIGNED ? 0 : q.w;
-            const int first = r + sp.bos, n = first + len, npos = n + sp.eos, total = r + padlen;
+            const int len = q.x, r = ALIGNED ? 0 : (q.w & 15);
+            const int n = r + sp.bos + len, npos = n + sp.eos, total = r + padlen;
+            const int lim = (ALIGNED || (q.w & 0x200)) ? total : (total & ~15);
             const uint8_t *rowbase = mybuf + q.y;
             const uint32_t sh = (static_cast<uint32_t>(q.z) & 3u) * 8u;
+            uint8_t *ps = pstage + (ALIGNED ? 0 : warp * 512);
+            uint4 ptail = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
+            if (!ALIGNED && (q.w & 0x100)) {
+                // rare: the previous row is so long that its residues / EOS reach into this row's first vector;
+                // rebuild those (at most 15) codes one by one from global memory (src/tokenize.h:464-478)
+                if (lane < r) {
+                    const int plen = rprev[warp][j];
+                    const int jres = padlen - r + lane - sp.bos;  // residue index of that column in the previous row
+                    uint32_t code = sp.pad_w & 0xffu;
+                    if (jres < plen) code = lut[__ldg(v.bytes + rstart[warp][j] - plen + jres)];
+                    else if (jres == plen && sp.eos) code = sp.eos_w & 0xffu;
+                    ps[lane] = static_cast<uint8_t>(code);
+                }
+                __syncwarp();
+                ptail = *reinterpret_cast<const uint4 *>(ps);
+                __syncwarp();
+            }
             if (q.z & 0x10000) mbar_wait_u32(bar0 + 8u * ((static_cast<uint32_t>(q.z) >> 8) & 0xfu), (static_cast<uint32_t>(q.z) >> 12) & 1u);
             uint8_t *oal = orow - r;
-            uint8_t *ps = pstage + (ALIGNED ? 0 : warp * 512);
             switch ((q.z >> 2) & 3) {  // warp-uniform
-                case 0: row_vectors<0, ALIGNED>(rowbase, sh, r, first, n, npos, total, oal, lane, sp, lut, tab, ps); break;
-                case 1: row_vectors<1, ALIGNED>(rowbase, sh, r, first, n, npos, total, oal, lane, sp, lut, tab, ps); break;
-                case 2: row_vectors<2, ALIGNED>(rowbase, sh, r, first, n, npos, total, oal, lane, sp, lut, tab, ps); break;
-                default: row_vectors<3, ALIGNED>(rowbase, sh, r, first, n, npos, total, oal, lane, sp, lut, tab, ps); break;
+                case 0: row_vectors<0, ALIGNED>(rowbase, sh, r, n, npos, lim, total, oal, lane, sp, lut, tab, ptail, ps); break;
+                case 1: row_vectors<1, ALIGNED>(rowbase, sh, r, n, npos, lim, total, oal, lane, sp, lut, tab, ptail, ps); break;
+                case 2: row_vectors<2, ALIGNED>(rowbase, sh, r, n, npos, lim, total, oal, lane, sp, lut, tab, ptail, ps); break;
+                default: row_vectors<3, ALIGNED>(rowbase, sh, r, n, npos, lim, total, oal, lane, sp, lut, tab, ptail, ps); break;
             }
             __syncwarp();  // every lane is done with this buffer before it is refilled
         }

@@ -205,11 +205,16 @@ def test_tma_row_kernel_shapes(flags):
     # than one 32-row batch per warp of the persistent grid, and an unaligned residue buffer
     tok, orc = capi.tokenizer("PROTEIN", **flags), OracleTokenizer("PROTEIN", **flags)
     extra = int(flags.get("bos", False)) + int(flags.get("eos", False))
-    for n, padlen, hi in ((1, 272, 270), (3000, 272, 270 - extra + extra), (777, 1024, 1024), (65, 4096, 4096), (200_000, 272, 40)):
+    # ... and padlens that are not a multiple of 16 (rows own the aligned vectors that END inside them; a
+    # nearly full previous row reaches into the next row's first vector)
+    for n, padlen, hi in ((1, 272, 270), (3000, 272, 270 - extra + extra), (777, 1024, 1024), (65, 4096, 4096), (200_000, 272, 40),
+                          (1, 1026, 1000), (2, 257, 257), (3001, 273, 273), (777, 1026, 1026), (513, 1001, 1001), (100_000, 259, 30)):
         hi = min(hi, padlen) - extra
         buf, offs = gen(1234 + n, n, 0, hi, MIX)
         lens = np.diff(offs)
         lens[:: max(1, n // 7)] = hi          # some rows exactly fill padlen
+        if n > 100 and hi >= 40:
+            lens[5:40] = np.arange(hi - 34, hi + 1)   # a run of nearly full rows, every tail length
         offs = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
         buf = np.resize(buf, int(offs[-1]))
         want = orc.batch_tokenize((buf, offs), padlen=padlen, batch_first=True)
