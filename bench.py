@@ -309,7 +309,7 @@ def run_ours(args):
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("tokenize_bf_kernel")
+                traffic = json.load(open(tp)).get("tokenize_rows_ring_kernel")
             except Exception:
                 traffic = None
         line = {
@@ -325,7 +325,7 @@ def run_ours(args):
                     "matches_device_resident": e2e_ok, "list_of_bytes_api": e2e_list},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "tokenize_bf_kernel<int8>",
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "tokenize_rows_ring_kernel<2,true> (K1r)",
                          "algorithmic_bytes_per_launch": int(alg_bytes / max(launches, 1)),
                          "launch_us": per_launch_ms * 1e3},
             "cpu_baseline": cpu, "parity_vs_cpu_reference": parity, "clocks": clocks, "extra": extra,
