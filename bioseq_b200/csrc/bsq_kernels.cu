@@ -512,28 +512,33 @@ __device__ __forceinline__ void transpose4x4(const uint32_t x[4], uint32_t y[4])
     y[3] = __byte_perm(t2, t3, 0x7632);
 }
 
-// MODE: how phase 2 leaves the tile.
+// MODE: how phase 2 leaves the tile (a template parameter, so every variant gets its own register budget).
 constexpr int kTokFast = 0;     // one-byte tokens, batch extent a multiple of 16: register 4x4 transposes + st.v4
 constexpr int kTokGeneric = 1;  // any element type / alignment: one element per lane, coalesced along the batch
-constexpr int kOneHot = 2;      // one-hot expansion (regime picked at run time, see below)
-// one-hot regimes
-constexpr int kOhRow = 0;      // C*sizeof(T) is 4, 8 or 16: one store writes the whole one-hot row of a (pos, seq)
-constexpr int kOhScatter = 1;  // 16-byte zero fill of the run, barrier, then one scalar store per (pos, seq)
-constexpr int kOhScalar = 2;   // unaligned runs: one element per lane
+constexpr int kOhRow = 2;       // one-hot, C*sizeof(T) is 4, 8 or 16: one store writes the whole one-hot row of a (pos, seq)
+constexpr int kOhVec = 3;       // one-hot, aligned runs, any C*sizeof(T): 16-byte vectors assembled in registers (zeros included)
+constexpr int kOhScalar = 4;    // one-hot, unaligned runs: one element per lane
 
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreads)
 seqfirst_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, LutParam lutp, Specials sp, Expand ex, int ncols,
-                FastDiv div_ncols, int regime, T *__restrict__ out) {
+                FastDiv div_ncols, FastDiv div_rowbytes, T *__restrict__ out) {
     // nseq sequences are processed; ld (>= nseq) is the batch extent of the output array, so a
     // sub-range of a larger batch can be written in place (out already points at its first column).
-    constexpr bool ONEHOT = MODE == kOneHot;
+    constexpr bool ONEHOT = MODE >= kOhRow;
     constexpr int PITCH = MODE == kTokFast ? kTilePos : kTilePitch;
     __shared__ __align__(16) uint8_t lut[256];
     __shared__ __align__(16) uint8_t tile[kTileSeqs * PITCH];
     __shared__ TailTab tab;
+    __shared__ uint4 ohtab[MODE == kOhVec ? 17 : 1];  // [b] = 16-byte vector with T(1) at byte b (b % sizeof(T) == 0); [16] = zero
     load_lut(lut, lutp);
     init_tailtab(tab, sp);
+    if (MODE == kOhVec && threadIdx.x >= 96 && threadIdx.x < 96 + 17) {
+        const int b = threadIdx.x - 96;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (b < 16 && b % static_cast<int>(sizeof(T)) == 0) set_one<T>(w, b / static_cast<int>(sizeof(T)));
+        ohtab[b] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
     __syncthreads();
     const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kTileSeqs;
     const int p0 = blockIdx.y * kTilePos;
@@ -615,7 +620,7 @@ seqfirst_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, LutParam lutp, 
                 }
             }
         }
-    } else if (regime == kOhRow) {
+    } else if (MODE == kOhRow) {
         const int row_bytes = ncols * static_cast<int>(sizeof(T));
         for (int pp = warp; pp < npos_tile; pp += kThreads / 32) {
             uint8_t *orow = reinterpret_cast<uint8_t *>(out + (static_cast<int64_t>(p0 + pp) * ld + i0) * ncols);
@@ -633,23 +638,36 @@ seqfirst_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, LutParam lutp, 
                 }
             }
         }
-    } else if (regime == kOhScatter) {
-        constexpr int EPV = 16 / sizeof(T);
-        const int nvec = nseq_tile * ncols / EPV;  // exact: the host checked divisibility
+    } else if (MODE == kOhVec) {
+        // Any C * sizeof(T) (codes are direct column ids here; 0xFF = all-zero row): every 16-byte vector of
+        // the (pos, seq-run, C) output is assembled in registers from the `nover` sequences whose one-hot
+        // rows can overlap it -- a table look-up (the vector with T(1) at byte b) and four ORs each -- and
+        // stored once, zeros included: no fill pass, no partial-sector traffic, only st.global.v4.
+        constexpr int S = static_cast<int>(sizeof(T));
+        const int row_bytes = ncols * S;
+        const int nvec = (nseq_tile * row_bytes) >> 4;
+        const int nover = (16 + row_bytes - 1) / row_bytes + ((16 % row_bytes) != 0);  // warp-uniform trip count
         for (int pp = warp; pp < npos_tile; pp += kThreads / 32) {
-            uint4 *orow = reinterpret_cast<uint4 *>(out + (static_cast<int64_t>(p0 + pp) * ld + i0) * ncols);
-            for (int vec = lane; vec < nvec; vec += 32) orow[vec] = make_uint4(0u, 0u, 0u, 0u);
-        }
-        __syncthreads();  // orders the zero fill before the ones (same addresses, different threads)
-        for (int pp = warp; pp < npos_tile; pp += kThreads / 32) {
-            T *orow = out + (static_cast<int64_t>(p0 + pp) * ld + i0) * ncols;
-#pragma unroll
-            for (int m = 0; m < kTileSeqs / 32; ++m) {
-                const int il = lane + 32 * m;
-                if (il < nseq_tile) {
-                    const int col = expand_code(tile[il * PITCH + pp], ex);
-                    if (col >= 0) orow[il * ncols + col] = cast_id<T>(1);
+            uint8_t *orow = reinterpret_cast<uint8_t *>(out + (static_cast<int64_t>(p0 + pp) * ld + i0) * ncols);
+            const uint8_t *tcol = tile + pp;
+            for (int vec = lane; vec < nvec; vec += 32) {
+                const int b0 = 16 * vec;
+                int il = static_cast<int>(fd_div(static_cast<uint32_t>(b0), div_rowbytes));
+                int rel = il * row_bytes - b0;  // byte offset of sequence il's row inside this vector (<= 0)
+                uint4 w = make_uint4(0u, 0u, 0u, 0u);
+                for (int k = 0; k < nover; ++k, ++il, rel += row_bytes) {
+                    const uint32_t code = il < nseq_tile ? tcol[il * PITCH] : 0xffu;
+                    const uint32_t b = min(static_cast<uint32_t>(rel + static_cast<int>(code) * S), 16u);  // 16 = not in this vector
+                    const uint4 o = ohtab[b];
+                    w.x |= o.x; w.y |= o.y; w.z |= o.z; w.w |= o.w;
                 }
+                __stcs(reinterpret_cast<uint4 *>(orow + b0), w);
+            }
+            // elements after the last whole vector (partial last tile only)
+            T *erow = reinterpret_cast<T *>(orow);
+            for (int e = (nvec << 4) / S + lane; e < nseq_tile * ncols; e += 32) {
+                const int il = static_cast<int>(fd_div(static_cast<uint32_t>(e), div_ncols));
+                erow[e] = static_cast<int>(tcol[il * PITCH]) == e - il * ncols ? cast_id<T>(1) : cast_id<T>(0);
             }
         }
     } else {
@@ -1013,19 +1031,24 @@ int launch_sf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t ld, int64
         // the register-transpose path needs one-byte elements whose rows start 16-byte aligned and
         // codes that are the output bytes (every alphabet but BYTES, whose special ids exceed 8 bits)
         if (sizeof(T) == 1 && aligned && ld % 16 == 0 && tok.pad_id < 0x80)
-            seqfirst_kernel<T, kTokFast><<<grid, kThreads, 0, st>>>(v, nseq, ld, static_cast<int>(padlen), p.lut, p.sp, p.ex, 1, dc, 0, o);
+            seqfirst_kernel<T, kTokFast><<<grid, kThreads, 0, st>>>(v, nseq, ld, static_cast<int>(padlen), p.lut, p.sp, p.ex, 1, dc, dc, o);
         else
-            seqfirst_kernel<T, kTokGeneric><<<grid, kThreads, 0, st>>>(v, nseq, ld, static_cast<int>(padlen), p.lut, p.sp, p.ex, 1, dc, 0, o);
+            seqfirst_kernel<T, kTokGeneric><<<grid, kThreads, 0, st>>>(v, nseq, ld, static_cast<int>(padlen), p.lut, p.sp, p.ex, 1, dc, dc, o);
     } else {
         const int64_t row_bytes = static_cast<int64_t>(ncols) * sizeof(T);
         // 16-byte stores need every row of the (padlen, ld, ncols) array and this launch's first
-        // column to start on a 16-byte boundary, and whole vectors per tile run
-        const bool vec_ok = aligned && (ld * row_bytes) % 16 == 0 && (nseq * row_bytes) % 16 == 0;
-        int regime = kOhScalar;
-        if (aligned && (row_bytes == 4 || row_bytes == 8 || row_bytes == 16)) regime = kOhRow;
-        else if (vec_ok) regime = kOhScatter;
-        seqfirst_kernel<T, kOneHot><<<grid, kThreads, 0, st>>>(v, nseq, ld, static_cast<int>(padlen), p.lut, p.sp, p.ex, ncols, dc,
-                                                                regime, o);
+        // column to start on a 16-byte boundary (tiles are 128 sequences wide, so then every run does)
+        const bool vec_ok = aligned && (ld * row_bytes) % 16 == 0;  // every tile's run starts on a 16-byte boundary
+        const FastDiv drb = make_fastdiv(static_cast<uint32_t>(row_bytes));
+        const int pl = static_cast<int>(padlen);
+        if (aligned && row_bytes == 16)
+            seqfirst_kernel<T, kOhRow><<<grid, kThreads, 0, st>>>(v, nseq, ld, pl, p.lut, p.sp, p.ex, ncols, dc, drb, o);
+        else if (vec_ok && tok.pad_id < 0x80)  // (BYTES alphabet: ids need the Expand table)
+            seqfirst_kernel<T, kOhVec><<<grid, kThreads, 0, st>>>(v, nseq, ld, pl, p.lut, p.sp, p.ex, ncols, dc, drb, o);
+        else if (aligned && (row_bytes == 4 || row_bytes == 8))
+            seqfirst_kernel<T, kOhRow><<<grid, kThreads, 0, st>>>(v, nseq, ld, pl, p.lut, p.sp, p.ex, ncols, dc, drb, o);
+        else
+            seqfirst_kernel<T, kOhScalar><<<grid, kThreads, 0, st>>>(v, nseq, ld, pl, p.lut, p.sp, p.ex, ncols, dc, drb, o);
     }
     count_launch();
     BSQ_CUDA_TRY(cudaGetLastError());
