@@ -719,35 +719,58 @@ __device__ __forceinline__ uint32_t inv_lookup(const uint16_t *inv, int32_t key)
     return (key >= -128 && key < 384) ? inv[key + 128] : kInvNone;
 }
 
-// pass 1: one CTA per row.  row_len[r] = decoded length; first_bad = min flat index of a
-// token without an entry.
-__global__ void __launch_bounds__(128)
-decode_len_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t cols, int64_t row_stride,
-                  int64_t col_stride, InvParam invp, int64_t *__restrict__ row_len,
+// pass 1: one warp per row, persistent grid (rows dealt round-robin to the warps).  row_len[r] =
+// decoded length; first_bad = min flat index of a token without an entry.  FAST: one-byte tokens,
+// contiguous along the row, every row 4-byte aligned -> four tokens per 32-bit load.
+constexpr int kDecWarps = 8;
+
+__device__ __forceinline__ void decode_fetch4(const uint8_t *rp, int itemsize, int64_t col_stride, int64_t c, int64_t cols,
+                                              const uint16_t *inv, bool fast, uint32_t e[4]) {
+    // entries of tokens c .. c+3 of a row (kInvNone beyond the row end is reported as 0xFFFE = "absent")
+    if (fast) {
+        const uint32_t x = c < cols ? *reinterpret_cast<const uint32_t *>(rp + c) : 0u;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e[k] = c + k < cols ? inv[((x >> (8 * k)) & 0xffu) + 128] : 0xFFFEu;
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e[k] = c + k < cols ? inv_lookup(inv, load_key(rp + (c + k) * col_stride, itemsize)) : 0xFFFEu;
+    }
+}
+
+__global__ void __launch_bounds__(kDecWarps * 32)
+decode_len_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t rows, int64_t cols, int64_t row_stride,
+                  int64_t col_stride, int fast, InvParam invp, int64_t *__restrict__ row_len,
                   unsigned long long *first_bad) {
     __shared__ uint16_t inv[512];
-    __shared__ int s_cnt[4];
-    for (int i = threadIdx.x; i < 512; i += 128) inv[i] = invp.e[i];
+    for (int i = threadIdx.x; i < 512; i += kDecWarps * 32) inv[i] = invp.e[i];
     __syncthreads();
-    const int64_t r = blockIdx.x;
-    const uint8_t *rp = tokens + r * row_stride;
-    int specials = 0;
-    unsigned long long bad = ~0ull;
-    for (int64_t c = threadIdx.x; c < cols; c += 128) {
-        const uint32_t e = inv_lookup(inv, load_key(rp + c * col_stride, itemsize));
-        if (e == kInvNone) bad = min(bad, static_cast<unsigned long long>(r * cols + c));
-        else specials += (e >> 8) & 1;
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kDecWarps + (threadIdx.x >> 5);
+    const int64_t GW = static_cast<int64_t>(gridDim.x) * kDecWarps;
+    for (int64_t r = gw; r < rows; r += GW) {
+        const uint8_t *rp = tokens + r * row_stride;
+        int specials = 0;
+        unsigned long long bad = ~0ull;
+        for (int64_t c0 = 0; c0 < cols; c0 += 128) {
+            const int64_t c = c0 + 4 * lane;
+            uint32_t e[4];
+            decode_fetch4(rp, itemsize, col_stride, c, cols, inv, fast != 0, e);
+#pragma unroll
+            for (int k = 3; k >= 0; --k) {
+                if (e[k] == kInvNone) bad = static_cast<unsigned long long>(r * cols + c + k);  // lowest k wins
+                else if (e[k] != 0xFFFEu) specials += (e[k] >> 8) & 1;
+            }
+            if (bad != ~0ull) break;  // this lane's first bad token is its lowest; later chunks cannot beat it
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            specials += __shfl_xor_sync(0xffffffffu, specials, o);
+            bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, o));
+        }
+        if (lane == 0) {
+            row_len[r] = cols + 4ll * specials;
+            if (bad != ~0ull) atomicMin(first_bad, bad);
+        }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-        specials += __shfl_xor_sync(0xffffffffu, specials, o);
-        bad = min(bad, __shfl_xor_sync(0xffffffffu, bad, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        s_cnt[threadIdx.x >> 5] = specials;
-        if (bad != ~0ull) atomicMin(first_bad, bad);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) row_len[r] = cols + 4ll * (s_cnt[0] + s_cnt[1] + s_cnt[2] + s_cnt[3]);
 }
 
 // exclusive scan of row_len (three small kernels; rows can be millions)
@@ -810,50 +833,82 @@ scan_add_kernel(int64_t *__restrict__ data, int64_t n, const int64_t *__restrict
     if (i == 0) data[n] = *grand_total;
 }
 
-// pass 2: one CTA per row; threads take 8 consecutive tokens, a CTA-wide scan of the
-// decoded lengths gives every thread its write position.
-constexpr int kDecTok = 8;
-__global__ void __launch_bounds__(128)
-decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t cols, int64_t row_stride,
-                    int64_t col_stride, InvParam invp, const int64_t *__restrict__ row_offs,
+// pass 2: one warp per row, persistent grid.  Per step a warp takes 128 tokens (four per lane), a warp
+// scan of the decoded lengths gives every lane its position, and the characters are first laid out in
+// a per-warp shared-memory stage that carries the same 16-byte misalignment as the row's place in
+// the output buffer: whole 16-byte vectors then leave with st.global.v4, only the row's first and
+// last partial vectors (shared with the neighbouring rows) are written byte-wise.
+constexpr int kDecStage = 16 + 128 * 5 + 16;
+
+__global__ void __launch_bounds__(kDecWarps * 32)
+decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t rows, int64_t cols, int64_t row_stride,
+                    int64_t col_stride, int fast, InvParam invp, const int64_t *__restrict__ row_offs,
                     uint8_t *__restrict__ chars) {
     __shared__ uint16_t inv[512];
-    __shared__ int64_t s_warp[32];
-    __shared__ int64_t s_total;
-    for (int i = threadIdx.x; i < 512; i += 128) inv[i] = invp.e[i];
-    if (threadIdx.x < 32) s_warp[threadIdx.x] = 0;
+    __shared__ __align__(16) uint8_t stage_all[kDecWarps][kDecStage];
+    for (int i = threadIdx.x; i < 512; i += kDecWarps * 32) inv[i] = invp.e[i];
     __syncthreads();
-    const int64_t r = blockIdx.x;
-    const uint8_t *rp = tokens + r * row_stride;
-    uint8_t *dst = chars + row_offs[r];
-    for (int64_t seg = 0; seg < cols; seg += 128 * kDecTok) {
-        uint32_t e[kDecTok];
-        int mylen = 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *stage = stage_all[warp];
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kDecWarps + warp;
+    const int64_t GW = static_cast<int64_t>(gridDim.x) * kDecWarps;
+    for (int64_t r = gw; r < rows; r += GW) {
+        const uint8_t *rp = tokens + r * row_stride;
+        uint8_t *dst = chars + row_offs[r];
+        int fill = static_cast<int>(reinterpret_cast<uintptr_t>(dst) & 15u);  // bytes of the stage in front of the data
+        uint8_t *gal = dst - fill;                                             // aligned address of stage[0]
+        int head = fill;                                                       // > 0: stage[0 .. head) is not ours
+        for (int64_t c0 = 0; c0 < cols; c0 += 128) {
+            uint32_t e[4];
+            decode_fetch4(rp, itemsize, col_stride, c0 + 4 * lane, cols, inv, fast != 0, e);
+            int mylen = 0;
 #pragma unroll
-        for (int j = 0; j < kDecTok; ++j) {
-            const int64_t c = seg + static_cast<int64_t>(threadIdx.x) * kDecTok + j;
-            e[j] = c < cols ? inv_lookup(inv, load_key(rp + c * col_stride, itemsize)) : kInvNone;
-            mylen += e[j] == kInvNone ? 0 : ((e[j] & 0x100u) ? 5 : 1);
-        }
-        // 128 threads = 4 warps; block_exclusive_scan is written for any warp count <= 32
-        int64_t pos = block_exclusive_scan(mylen, s_warp, &s_total);
-#pragma unroll
-        for (int j = 0; j < kDecTok; ++j) {
-            if (e[j] == kInvNone) continue;
-            if (e[j] & 0x100u) {
-                const uint32_t k = e[j] & 3u;  // <BOS> <EOS> <PAD>
-                dst[pos] = '<';
-                dst[pos + 1] = k == 0 ? 'B' : (k == 1 ? 'E' : 'P');
-                dst[pos + 2] = k == 2 ? 'A' : 'O';
-                dst[pos + 3] = k == 2 ? 'D' : 'S';
-                dst[pos + 4] = '>';
-                pos += 5;
-            } else {
-                dst[pos++] = static_cast<uint8_t>(e[j]);
+            for (int k = 0; k < 4; ++k) mylen += e[k] >= 0xFFFEu ? 0 : ((e[k] & 0x100u) ? 5 : 1);
+            int incl = mylen;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
             }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            uint8_t *w = stage + fill + incl - mylen;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (e[k] >= 0xFFFEu) continue;
+                if (e[k] & 0x100u) {
+                    const uint32_t sp = e[k] & 3u;  // <BOS> <EOS> <PAD>
+                    w[0] = '<';
+                    w[1] = sp == 0 ? 'B' : (sp == 1 ? 'E' : 'P');
+                    w[2] = sp == 2 ? 'A' : 'O';
+                    w[3] = sp == 2 ? 'D' : 'S';
+                    w[4] = '>';
+                    w += 5;
+                } else {
+                    *w++ = static_cast<uint8_t>(e[k]);
+                }
+            }
+            __syncwarp();
+            fill += total;
+            const int nfull = fill >> 4;
+            for (int vv = lane; vv < nfull; vv += 32) {
+                if (vv == 0 && head > 0) {  // first vector of the row: bytes [0, head) belong to the previous row
+                    for (int i = head; i < 16; ++i) gal[i] = stage[i];
+                } else {
+                    *reinterpret_cast<uint4 *>(gal + 16 * vv) = *reinterpret_cast<const uint4 *>(stage + 16 * vv);
+                }
+            }
+            if (nfull > 0) head = 0;
+            const int rest = fill & 15;
+            uint8_t keep = 0;
+            if (lane < rest) keep = stage[16 * nfull + lane];
+            __syncwarp();
+            if (nfull > 0 && lane < rest) stage[lane] = keep;
+            __syncwarp();
+            gal += 16 * nfull;
+            fill = rest;
         }
-        dst += s_total;
-        __syncthreads();
+        // the row's last partial vector
+        for (int i = head + lane; i < fill; i += 32) gal[i] = stage[i];
+        __syncwarp();
     }
 }
 
@@ -1055,6 +1110,14 @@ int launch_sf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t ld, int64
     return BSQ_OK;
 }
 
+// one-byte tokens, contiguous along the row, every row 4-byte aligned: four tokens per 32-bit load
+int decode_fast_path(const void *d_tokens, int itemsize, int64_t row_stride, int64_t col_stride) {
+    return itemsize == 1 && col_stride == 1 && row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(d_tokens) & 3u) == 0;
+}
+unsigned decode_grid(int64_t rows) {  // persistent: one warp per row, rows dealt round-robin
+    return static_cast<unsigned>(std::min<int64_t>((rows + kDecWarps - 1) / kDecWarps, 148 * 8));
+}
+
 InvParam make_inv(const bsq_tokenizer &tok) {
     InvParam inv;
     for (int i = 0; i < 512; ++i) inv.e[i] = kInvNone;
@@ -1174,8 +1237,9 @@ int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int items
     BSQ_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_work), sizeof(int64_t) * (2 + nblocks), st));
     BSQ_CUDA_TRY(cudaMemsetAsync(d_work, 0xff, sizeof(int64_t), st));
     const InvParam inv = make_inv(*tok);
-    decode_len_kernel<<<static_cast<unsigned>(rows), 128, 0, st>>>(
-        static_cast<const uint8_t *>(d_tokens), itemsize, cols, row_stride, col_stride, inv, d_row_offsets,
+    const int fast = decode_fast_path(d_tokens, itemsize, row_stride, col_stride);
+    decode_len_kernel<<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
+        static_cast<const uint8_t *>(d_tokens), itemsize, rows, cols, row_stride, col_stride, fast, inv, d_row_offsets,
         reinterpret_cast<unsigned long long *>(d_work));
     scan_local_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2);
     scan_totals_kernel<<<1, kScanBlock, 0, st>>>(d_work + 2, nblocks, d_work + 1);
@@ -1208,8 +1272,9 @@ int bsq_decode_chars(int device, void *stream, const void *d_tokens, int itemsiz
     BSQ_CUDA_TRY(cudaSetDevice(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const InvParam inv = make_inv(*tok);
-    decode_chars_kernel<<<static_cast<unsigned>(rows), 128, 0, st>>>(
-        static_cast<const uint8_t *>(d_tokens), itemsize, cols, row_stride, col_stride, inv, d_row_offsets, d_chars);
+    decode_chars_kernel<<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
+        static_cast<const uint8_t *>(d_tokens), itemsize, rows, cols, row_stride, col_stride,
+        decode_fast_path(d_tokens, itemsize, row_stride, col_stride), inv, d_row_offsets, d_chars);
     count_launch();
     BSQ_CUDA_TRY(cudaGetLastError());
     return BSQ_OK;
