@@ -519,6 +519,24 @@ constexpr int kOhRow = 2;       // one-hot, C*sizeof(T) is 4, 8 or 16: one store
 constexpr int kOhVec = 3;       // one-hot, aligned runs, any C*sizeof(T): 16-byte vectors assembled in registers (zeros included)
 constexpr int kOhScalar = 4;    // one-hot, unaligned runs: one element per lane
 
+// Phase 0 stages, for each of the tile's 128 sequences, the 16-byte aligned window of packed residues
+// that holds the tile's 128 columns: one 1-D bulk asynchronous copy (TMA unit) per sequence, issued by
+// the thread that resolved the sequence's offsets, completion counted on one mbarrier.  The window of
+// sequence il lands at stage + il * kStagePitch so that column p0 + j sits at byte (A & 15) + j, A being
+// the global address of column p0 (at most 15 + 127 < 144).  Phase 1 then needs no clamping and no
+// data-dependent select tree: five 4-byte aligned LDS.32 at the lane's own word offset and four funnel
+// shifts realign any source alignment, whatever mix of sequences a warp holds.  Bytes of the pitch that
+// no copy wrote are stale; they only ever reach columns that the BOS / tail fix-ups overwrite.
+constexpr int kStagePitch = kTilePos + 16;
+
+__device__ __forceinline__ void staged16(const uint8_t *srow, uint32_t o, uint32_t out[4]) {
+    const uint32_t *wp = reinterpret_cast<const uint32_t *>(srow + (o & ~3u));
+    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+    const uint32_t sh = (o & 3u) * 8u;
+    out[0] = __funnelshift_r(w0, w1, sh); out[1] = __funnelshift_r(w1, w2, sh);
+    out[2] = __funnelshift_r(w2, w3, sh); out[3] = __funnelshift_r(w3, w4, sh);
+}
+
 template <typename T, int MODE>
 __global__ void __launch_bounds__(kThreads)
 seqfirst_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, LutParam lutp, Specials sp, Expand ex, int ncols,
@@ -527,10 +545,13 @@ seqfirst_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, LutParam lutp, 
     // sub-range of a larger batch can be written in place (out already points at its first column).
     constexpr bool ONEHOT = MODE >= kOhRow;
     constexpr int PITCH = MODE == kTokFast ? kTilePos : kTilePitch;
+    extern __shared__ __align__(128) uint8_t stage[];  // kTileSeqs * kStagePitch residues (+ as much again for a mask)
     __shared__ __align__(16) uint8_t lut[256];
     __shared__ __align__(16) uint8_t tile[kTileSeqs * PITCH];
     __shared__ TailTab tab;
     __shared__ uint4 ohtab[MODE == kOhVec ? 17 : 1];  // [b] = 16-byte vector with T(1) at byte b (b % sizeof(T) == 0); [16] = zero
+    __shared__ __align__(16) int4 rinfo[kTileSeqs];   // per sequence: len, (A & 15) of the residues, of the mask
+    __shared__ __align__(8) uint64_t bar;
     load_lut(lut, lutp);
     init_tailtab(tab, sp);
     if (MODE == kOhVec && threadIdx.x >= 96 && threadIdx.x < 96 + 17) {
@@ -539,32 +560,78 @@ seqfirst_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, LutParam lutp, 
         if (b < 16 && b % static_cast<int>(sizeof(T)) == 0) set_one<T>(w, b / static_cast<int>(sizeof(T)));
         ohtab[b] = make_uint4(w[0], w[1], w[2], w[3]);
     }
+    if (threadIdx.x == 128) {
+        mbar_init(&bar, kTileSeqs);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     const int64_t i0 = static_cast<int64_t>(blockIdx.x) * kTileSeqs;
     const int p0 = blockIdx.y * kTilePos;
     const int nseq_tile = static_cast<int>(min(static_cast<int64_t>(kTileSeqs), nseq - i0));
     const int npos_tile = min(kTilePos, padlen - p0);
+    const bool masked = ONEHOT && v.mask != nullptr;
+    uint8_t *mstage = stage + kTileSeqs * kStagePitch;
+
+    // ---- phase 0: one thread per sequence resolves it and issues its bulk copy ----
+    if (threadIdx.x < kTileSeqs) {
+        const int il = threadIdx.x;
+        int len = 0;
+        uint32_t shb = 0, shm = 0, nb = 0;
+        if (il < nseq_tile) {
+            const int64_t start = __ldg(v.offs + i0 + il);
+            len = static_cast<int>(__ldg(v.offs + i0 + il + 1) - start);
+            const int r0 = max(p0 - sp.bos, 0), r1 = min(p0 + kTilePos - sp.bos, len);  // residues under this tile
+            const int64_t col0 = start - sp.bos + p0;                                     // packed index of column p0
+            shb = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(v.bytes + col0) & 15u);
+            if (masked) shm = static_cast<uint32_t>(reinterpret_cast<uintptr_t>(v.mask + col0) & 15u);
+            if (r1 > r0) {
+                const uintptr_t a = reinterpret_cast<uintptr_t>(v.bytes + col0) & ~static_cast<uintptr_t>(15);
+                const uintptr_t w0 = reinterpret_cast<uintptr_t>(v.bytes + start + r0) & ~static_cast<uintptr_t>(15);
+                const uintptr_t w1 = (reinterpret_cast<uintptr_t>(v.bytes + start + r1 - 1) & ~static_cast<uintptr_t>(15)) + 16;
+                nb = static_cast<uint32_t>(w1 - w0);
+                uint32_t nm = 0;
+                uintptr_t m0 = 0, ma = 0;
+                if (masked) {
+                    ma = reinterpret_cast<uintptr_t>(v.mask + col0) & ~static_cast<uintptr_t>(15);
+                    m0 = reinterpret_cast<uintptr_t>(v.mask + start + r0) & ~static_cast<uintptr_t>(15);
+                    nm = static_cast<uint32_t>((reinterpret_cast<uintptr_t>(v.mask + start + r1 - 1) & ~static_cast<uintptr_t>(15)) + 16 - m0);
+                }
+                mbar_expect_tx(&bar, nb + nm);
+                bulk_g2s(stage + il * kStagePitch + (w0 - a), reinterpret_cast<const void *>(w0), nb, &bar);
+                if (masked) bulk_g2s(mstage + il * kStagePitch + (m0 - ma), reinterpret_cast<const void *>(m0), nm, &bar);
+            }
+        }
+        if (nb == 0u) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&bar)) : "memory");
+        rinfo[il] = make_int4(len, static_cast<int>(shb), static_cast<int>(shm), 0);
+    }
+    __syncthreads();  // rinfo
+    mbar_wait_u32(smem_u32(&bar), 0u);
 
     // ---- phase 1: tile[seq][pos] <- codes; lanes run along the positions of a sequence ----
+    const uint4 padv = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
 #pragma unroll
     for (int u = 0; u < (kTileSeqs * kTilePos / 16) / kThreads; ++u) {
         const int ch = threadIdx.x + u * kThreads;
         const int q = ch & 7, il = ch >> 3;
         const int c0 = p0 + 16 * q;
         if (il < nseq_tile && c0 < padlen) {
-            const int64_t start = __ldg(v.offs + i0 + il);
-            const int len = static_cast<int>(__ldg(v.offs + i0 + il + 1) - start);
-            uint4 codes;
-            if (c0 >= sp.bos + len + sp.eos) {
-                codes = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
-            } else {
-                const RowSrc rs = make_rowsrc(v.bytes, start, sp.bos, len);
-                if (ONEHOT && v.mask != nullptr) {
-                    const RowSrc ms = make_rowsrc(v.mask, start, sp.bos, len);
-                    codes = tokens16<false>(rs, &ms, len, c0, sp, lut, tab);
-                } else {
-                    codes = tokens16<false>(rs, nullptr, len, c0, sp, lut, tab);
+            const int4 ri = rinfo[il];
+            const int len = ri.x;
+            uint4 codes = padv;
+            if (c0 < sp.bos + len + sp.eos) {
+                uint32_t t[4] = {0u, 0u, 0u, 0u};
+                if (has_residues(c0, sp.bos, len)) {
+                    uint32_t raw[4];
+                    staged16(stage + il * kStagePitch, static_cast<uint32_t>(ri.y) + 16u * q, raw);
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) t[w] = translate4(raw[w], lut);
+                    if (masked) {  // masked-out residues become kCodeInvalid (0xFF)
+                        staged16(mstage + il * kStagePitch, static_cast<uint32_t>(ri.z) + 16u * q, raw);
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) t[w] |= __vcmpeq4(raw[w], 0u);
+                    }
                 }
+                codes = tokens16_finish<false>(t, len, c0, sp, tab);
             }
             if (MODE == kTokFast) {
                 // 16-byte chunks XOR-swizzled by the sequence group, so that phase 2's column-of-words
@@ -679,6 +746,140 @@ seqfirst_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, LutParam lutp, 
                 const int col = e - il * ncols;
                 const int hot = expand_code(tile[il * PITCH + pp], ex);
                 orow[e] = hot == col ? cast_id<T>(1) : cast_id<T>(0);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2t: (padlen, nseq) one-byte tokens -- the reference's default layout (batch_first=False) -- as a
+// dedicated, instruction-lean kernel (the tile kernel above was issue-bound: 700 instructions per
+// warp per 16 KB tile, profiles/r01d_seqfirst_*).  Same 128 x 128 tile, but
+//   * the sequences' windows are staged with per-lane 16-byte cp.async (LDGSTS): the eight lanes that
+//     will translate a sequence's eight chunks copy them, so the hand-over needs cp.async.wait_all +
+//     __syncwarp only -- no mbarrier, no block barrier, no per-copy uniform-datapath loop;
+//   * everything a thread needs per chunk is either thread-constant (chunk column, BOS predicate,
+//     shared-memory addresses) or one LDS.128 of per-sequence data resolved once per CTA;
+//   * phase 2 runs unguarded on full tiles (the common case) and keeps its addresses in registers.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads)
+seqfirst_tok8_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, FastDiv div_ptiles, LutParam lutp, Specials sp,
+                     uint8_t *__restrict__ out) {
+    __shared__ __align__(16) uint8_t lut[256];
+    __shared__ TailTab tab;
+    __shared__ __align__(16) int4 rinfo[kTileSeqs];  // n = bos + len, A & 15, A & ~15 (A = global address of column p0)
+    __shared__ __align__(128) uint8_t stage[kTileSeqs * kStagePitch];
+    __shared__ __align__(128) uint8_t tile[kTileSeqs * kTilePos];
+    const int tid = threadIdx.x;
+    // 1-D grid, position tiles fastest: the tiles of one group of sequences run back to back, so the
+    // 32-byte sectors that two neighbouring windows share are still in L2 when the second one asks
+    const uint32_t st = fd_div(blockIdx.x, div_ptiles);
+    const int64_t i0 = static_cast<int64_t>(st) * kTileSeqs;
+    const int p0 = static_cast<int>(blockIdx.x - st * div_ptiles.d) * kTilePos;
+    const int nseq_tile = static_cast<int>(min(static_cast<int64_t>(kTileSeqs), nseq - i0));
+    load_lut(lut, lutp);
+    init_tailtab(tab, sp);
+    if (tid >= 128) {  // warps 4..7 resolve the tile's sequences
+        const int il = tid - 128;
+        int n = 0;
+        uintptr_t a = 0;
+        if (il < nseq_tile) {
+            const int64_t start = __ldg(v.offs + i0 + il);
+            n = sp.bos + static_cast<int>(__ldg(v.offs + i0 + il + 1) - start);
+            a = reinterpret_cast<uintptr_t>(v.bytes + (start - sp.bos + p0));
+        }
+        rinfo[il] = make_int4(n, static_cast<int>(a & 15u), static_cast<int>(static_cast<uint32_t>(a & ~static_cast<uintptr_t>(15))),
+                              static_cast<int>(static_cast<uint32_t>(a >> 32)));
+    }
+    __syncthreads();
+
+    // ---- phase 0: lane (il, q) copies 16-byte word q (and lane q == 0 word 8) of sequence il's window ----
+    const int q = tid & 7;
+    const int c0 = p0 + 16 * q;  // first column of this thread's chunks
+    const uint32_t stage_s = smem_u32(stage) + static_cast<uint32_t>(tid >> 3) * kStagePitch;
+    int nn[4], sh[4];
+    int4 ris[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) ris[u] = rinfo[(tid >> 3) + 32 * u];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int4 ri = ris[u];
+        nn[u] = ri.x;
+        sh[u] = ri.y;
+        // stage offsets [olo, ohi) hold the residues under this tile (columns max(bos, p0) .. min(n, p0 + 128))
+        const int olo = ri.y + max(sp.bos - p0, 0), ohi = ri.y + min(ri.x - p0, kTilePos);
+        const uint8_t *src = reinterpret_cast<const uint8_t *>((static_cast<uint64_t>(static_cast<uint32_t>(ri.w)) << 32) |
+                                                               static_cast<uint32_t>(ri.z));
+        const uint32_t dst = stage_s + static_cast<uint32_t>(32 * u) * kStagePitch + 16u * q;
+        if (16 * q < ohi && 16 * q + 16 > olo) cp_async16(dst, src + 16 * q);
+        if (q == 0 && ohi > kTilePos) cp_async16(dst + kTilePos, src + kTilePos);
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+
+    // ---- phase 1: tile[seq][pos] <- codes ----
+    const uint4 padv = make_uint4(sp.pad_w, sp.pad_w, sp.pad_w, sp.pad_w);
+    const bool bos_here = sp.bos && c0 == 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int il = (tid >> 3) + 32 * u;
+        const int n = nn[u];
+        uint4 codes = padv;
+        if (c0 < n + sp.eos) {
+            uint32_t t[4] = {0u, 0u, 0u, 0u};
+            if (c0 < n) {
+                uint32_t raw[4];
+                staged16(stage + il * kStagePitch, static_cast<uint32_t>(sh[u]) + 16u * q, raw);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) t[w] = translate4(raw[w], lut);
+            }
+            if (bos_here) t[0] = __byte_perm(t[0], sp.bos_w, 0x3214);
+            if (c0 + 16 > n) {  // the row ends inside this chunk
+                const uint4 m = tab.m[n - c0], f = tab.f[n - c0];
+                t[0] = (t[0] & m.x) | f.x; t[1] = (t[1] & m.y) | f.y;
+                t[2] = (t[2] & m.z) | f.z; t[3] = (t[3] & m.w) | f.w;
+            }
+            codes = make_uint4(t[0], t[1], t[2], t[3]);
+        }
+        // 16-byte chunks XOR-swizzled by the sequence group, so that phase 2's column-of-words reads
+        // (16 sequences apart) hit 32 distinct banks
+        *reinterpret_cast<uint4 *>(tile + il * kTilePos + 16 * (q ^ ((il >> 4) & 7))) = codes;
+    }
+    __syncthreads();
+
+    // ---- phase 2: thread = 16 sequences (group A) x 4 positions (word pw): 16 LDS.32, four 4x4 byte
+    // transposes, one 16-byte store per position; lanes A = 0..7 make 128 contiguous bytes per row ----
+    const int warp = tid >> 5, lane = tid & 31;
+    const int A = lane & 7, pw = 4 * warp + (lane >> 3);
+    const uint32_t *t32 = reinterpret_cast<const uint32_t *>(tile) + 16 * A * (kTilePos / 4) + (pw ^ (4 * A));
+    uint32_t y[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        uint32_t x[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) x[k] = t32[(4 * a + k) * (kTilePos / 4)];
+        transpose4x4(x, y[a]);
+    }
+    const int pos = p0 + 4 * pw;
+    uint8_t *o = out + (static_cast<int64_t>(pos) * ld + i0 + 16 * A);
+    if (nseq_tile == kTileSeqs && p0 + kTilePos <= padlen) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j, o += ld) __stcs(reinterpret_cast<uint4 *>(o), make_uint4(y[0][j], y[1][j], y[2][j], y[3][j]));
+    } else {
+        const int nvalid = nseq_tile - 16 * A;  // sequences of this group that exist
+#pragma unroll
+        for (int j = 0; j < 4; ++j, o += ld) {
+            if (pos + j >= padlen || nvalid <= 0) continue;
+            if (nvalid >= 16) {
+                __stcs(reinterpret_cast<uint4 *>(o), make_uint4(y[0][j], y[1][j], y[2][j], y[3][j]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < 16; ++k)
+                    if (k < nvalid) o[k] = static_cast<uint8_t>(y[k >> 2][j] >> (8 * (k & 3)));
             }
         }
     }
@@ -1082,29 +1283,38 @@ int launch_sf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t ld, int64
     const FastDiv dc = make_fastdiv(static_cast<uint32_t>(ncols));
     const bool aligned = (reinterpret_cast<uintptr_t>(d_out) & 15u) == 0;
     T *o = static_cast<T *>(d_out);
+    const int pl = static_cast<int>(padlen);
+    const size_t smem = static_cast<size_t>(kTileSeqs) * kStagePitch * (v.mask != nullptr ? 2 : 1);  // staged residues (+ mask)
+    const int64_t row_bytes = static_cast<int64_t>(ncols) * sizeof(T);
+    const FastDiv drb = make_fastdiv(static_cast<uint32_t>(row_bytes));
+    // (with a mask the two staging areas + the static tile exceed the 48 KB a kernel gets without opting in)
+#define BSQ_SF(MODE)                                                                                                        \
+    do {                                                                                                                    \
+        if (v.mask != nullptr)                                                                                              \
+            BSQ_CUDA_TRY(cudaFuncSetAttribute(seqfirst_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                              static_cast<int>(smem)));                                                     \
+        seqfirst_kernel<T, MODE><<<grid, kThreads, smem, st>>>(v, nseq, ld, pl, p.lut, p.sp, p.ex, ncols, dc, drb, o);      \
+    } while (0)
     if (!ONEHOT) {
         // the register-transpose path needs one-byte elements whose rows start 16-byte aligned and
         // codes that are the output bytes (every alphabet but BYTES, whose special ids exceed 8 bits)
-        if (sizeof(T) == 1 && aligned && ld % 16 == 0 && tok.pad_id < 0x80)
-            seqfirst_kernel<T, kTokFast><<<grid, kThreads, 0, st>>>(v, nseq, ld, static_cast<int>(padlen), p.lut, p.sp, p.ex, 1, dc, dc, o);
-        else
-            seqfirst_kernel<T, kTokGeneric><<<grid, kThreads, 0, st>>>(v, nseq, ld, static_cast<int>(padlen), p.lut, p.sp, p.ex, 1, dc, dc, o);
+        if (sizeof(T) == 1 && aligned && ld % 16 == 0 && tok.pad_id < 0x80) {
+            if (env_int("BSQ_SF_OLD", 0)) BSQ_SF(kTokFast);
+            else if (gx * gy > 0x7fffffffll) return fail(BSQ_ERR_ARG, "batch too large for one launch");
+            else seqfirst_tok8_kernel<<<static_cast<unsigned>(gx * gy), kThreads, 0, st>>>(
+                    v, nseq, ld, pl, make_fastdiv(static_cast<uint32_t>(gy)), p.lut, p.sp, reinterpret_cast<uint8_t *>(o));
+        }
+        else BSQ_SF(kTokGeneric);
     } else {
-        const int64_t row_bytes = static_cast<int64_t>(ncols) * sizeof(T);
         // 16-byte stores need every row of the (padlen, ld, ncols) array and this launch's first
         // column to start on a 16-byte boundary (tiles are 128 sequences wide, so then every run does)
         const bool vec_ok = aligned && (ld * row_bytes) % 16 == 0;  // every tile's run starts on a 16-byte boundary
-        const FastDiv drb = make_fastdiv(static_cast<uint32_t>(row_bytes));
-        const int pl = static_cast<int>(padlen);
-        if (aligned && row_bytes == 16)
-            seqfirst_kernel<T, kOhRow><<<grid, kThreads, 0, st>>>(v, nseq, ld, pl, p.lut, p.sp, p.ex, ncols, dc, drb, o);
-        else if (vec_ok && tok.pad_id < 0x80)  // (BYTES alphabet: ids need the Expand table)
-            seqfirst_kernel<T, kOhVec><<<grid, kThreads, 0, st>>>(v, nseq, ld, pl, p.lut, p.sp, p.ex, ncols, dc, drb, o);
-        else if (aligned && (row_bytes == 4 || row_bytes == 8))
-            seqfirst_kernel<T, kOhRow><<<grid, kThreads, 0, st>>>(v, nseq, ld, pl, p.lut, p.sp, p.ex, ncols, dc, drb, o);
-        else
-            seqfirst_kernel<T, kOhScalar><<<grid, kThreads, 0, st>>>(v, nseq, ld, pl, p.lut, p.sp, p.ex, ncols, dc, drb, o);
+        if (aligned && row_bytes == 16) BSQ_SF(kOhRow);
+        else if (vec_ok && tok.pad_id < 0x80) BSQ_SF(kOhVec);  // (BYTES alphabet: ids need the Expand table)
+        else if (aligned && (row_bytes == 4 || row_bytes == 8)) BSQ_SF(kOhRow);
+        else BSQ_SF(kOhScalar);
     }
+#undef BSQ_SF
     count_launch();
     BSQ_CUDA_TRY(cudaGetLastError());
     return BSQ_OK;
