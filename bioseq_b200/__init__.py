@@ -21,6 +21,7 @@ except ImportError as _e:  # pragma: no cover - exercised only on a broken check
         "`python -m bioseq_b200.build`; there is no pure-Python or CPU fallback." % (_e,)) from _e
 
 from .cbioseq import Tokenizer, Threading, set_num_threads, get_num_threads  # noqa: F401
+from .cbioseq import FlatFile, FlatFileIterator, getstats  # noqa: F401
 
 LIBBSQ_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "libbsq.so")
 
@@ -112,9 +113,13 @@ def torchify(arr):
     return arr if isinstance(arr, torch.Tensor) else torch.from_numpy(arr)
 
 
+from . import loaders  # noqa: E402
+from .loaders import PyViewFF  # noqa: E402
+
 __all__ = ["onehot_encode", "cbioseq", "f_encode", "Tokenizer", "make_embedding",
            "bos_tokenizers", "eos_tokenizers", "beos_tokenizers", "pbeos_tokenizers", "peos_tokenizers",
            "pbos_tokenizers", "pos_tokenizers", "default_tokenizers", "total_tokenizer_dict", "get_tokenizer_dict",
            "DNATokenizer", "AmineTokenizer", "Reduced6Tokenizer", "Reduced8Tokenizer", "Reduced10Tokenizer",
            "Reduced14Tokenizer", "DayhoffTokenizer", "LIATokenizer", "LIBTokenizer", "torchify",
-           "set_num_threads", "get_num_threads", "Threading", "keys", "bkeys"]
+           "set_num_threads", "get_num_threads", "Threading", "keys", "bkeys", "FlatFile", "FlatFileIterator", "getstats",
+           "PyViewFF", "loaders"]

@@ -15,10 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 
-LIB_SOURCES = ["bsq_kernels.cu", "bsq_host.cu", "bsq_alphabet.cpp"]
-LIB_DEPS = LIB_SOURCES + ["bsq_kernels.cuh", "bsq_internal.h", os.path.join(ROOT, "include", "bsq.h")]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC,-Wall", "-shared"]
+LIB_SOURCES = ["bsq_kernels.cu", "bsq_host.cu", "bsq_flatfile.cu", "bsq_alphabet.cpp"]
+NVCC_COMPILE = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+                "-Xcompiler", "-fPIC,-Wall"]
 
 
 def lib_path():
@@ -44,8 +43,20 @@ def _run(cmd, verbose):
 
 def build(force=False, verbose=False):
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    if force or _stale(lib_path(), LIB_DEPS):
-        _run([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", lib_path()] + LIB_SOURCES, verbose)
+    hdrs = ["bsq_kernels.cuh", "bsq_internal.h", os.path.join(ROOT, "include", "bsq.h")]
+    # one object per source (kept under bioseq_b200/build/, git-ignored) so that touching the
+    # host code does not recompile the kernels
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    objs, relink = [], force or not os.path.exists(lib_path())
+    for src in LIB_SOURCES:
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        objs.append(obj)
+        if force or _stale(obj, [src] + hdrs):
+            _run([nvcc] + NVCC_COMPILE + (["-Xptxas", "-v"] if verbose else []) + ["-c", src, "-o", obj], verbose)
+            relink = True
+    if relink or _stale(lib_path(), objs):
+        _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", lib_path()] + objs + ["-lz"], verbose)
     if force or _stale(module_path(), ["cbioseq_module.cpp", os.path.join(ROOT, "include", "bsq.h"), lib_path()]):
         import pybind11
         _run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-Wall",

@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libbsq.so")
 
-OK, ERR_ARG, ERR_TOO_LONG, ERR_BAD_TOKEN, ERR_KEY, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4, -5, -6
+OK, ERR_ARG, ERR_TOO_LONG, ERR_BAD_TOKEN, ERR_KEY, ERR_CUDA, ERR_NOMEM, ERR_IO, ERR_RANGE = 0, -1, -2, -3, -4, -5, -6, -7, -8
 I8, I16, I32, I64, F32, F64 = range(6)
 
 
@@ -64,6 +64,17 @@ def lib():
         "bsq_stager_sync_copies": (i32, [vp]),
         "bsq_tokenize_host": (i32, [vp, vp, vp, vp, i64, i64, tokp, i32, i32, vp]),
         "bsq_onehot_host": (i32, [vp, vp, vp, vp, vp, i64, i64, tokp, i32, vp]),
+        "bsq_flatfile_make": (i32, [C.c_char_p, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]),
+        "bsq_flatfile_open": (i32, [C.POINTER(vp), C.c_char_p, i64, i32]),
+        "bsq_flatfile_close": (None, [vp]),
+        "bsq_flatfile_nseqs": (i64, [vp]),
+        "bsq_flatfile_seq_offset": (i64, [vp]),
+        "bsq_flatfile_max_seq_len": (i64, [vp]),
+        "bsq_flatfile_offsets": (vp, [vp]),
+        "bsq_flatfile_bytes": (vp, [vp]),
+        "bsq_flatfile_is_pinned": (i32, [vp]),
+        "bsq_fastx_lengths": (i32, [C.c_char_p, C.POINTER(C.POINTER(i64)), C.POINTER(i64)]),
+        "bsq_free": (None, [vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -76,7 +87,10 @@ EXPORTS = ("bsq_abi_version bsq_last_error bsq_launch_count bsq_launch_count_res
            "bsq_alphabet_count bsq_alphabet_key bsq_tokenizer_init bsq_tokenizer_lookup bsq_pack_create bsq_pack_destroy "
            "bsq_pack_gather bsq_pack_bytes bsq_pack_offsets bsq_pack_nseq bsq_pack_nbytes bsq_pack_maxlen "
            "bsq_check_lengths_host bsq_check_lengths_device bsq_tokenize bsq_onehot bsq_decode_lengths bsq_decode_chars "
-           "bsq_stager_create bsq_stager_destroy bsq_stager_sync_copies bsq_tokenize_host bsq_onehot_host").split()
+           "bsq_stager_create bsq_stager_destroy bsq_stager_sync_copies bsq_tokenize_host bsq_onehot_host "
+           "bsq_flatfile_make bsq_flatfile_open bsq_flatfile_close bsq_flatfile_nseqs bsq_flatfile_seq_offset "
+           "bsq_flatfile_max_seq_len bsq_flatfile_offsets bsq_flatfile_bytes bsq_flatfile_is_pinned bsq_fastx_lengths "
+           "bsq_free").split()
 
 
 def last_error():
@@ -89,6 +103,8 @@ def check(rc, onehot=False):
     msg = last_error()
     if rc == ERR_ARG or (rc == ERR_TOO_LONG and onehot):
         raise ValueError(msg)
+    if rc == ERR_RANGE:
+        raise IndexError(msg)
     raise RuntimeError(msg)
 
 
@@ -204,4 +220,32 @@ class Pack:
     def close(self):
         if self.h:
             lib().bsq_pack_destroy(self.h)
+            self.h = C.c_void_p()
+
+
+class FlatFile:
+    """bsq_flatfile through the C ABI: what a non-Python host binds (the Python class lives in cbioseq)."""
+
+    def __init__(self, path, maxseqlen=-1, pinned=False):
+        self.h = C.c_void_p()
+        check(lib().bsq_flatfile_open(C.byref(self.h), os.fsencode(path), maxseqlen, int(pinned)))
+
+    @staticmethod
+    def make(inpath, outpath=""):
+        n, m = C.c_int64(), C.c_int64()
+        check(lib().bsq_flatfile_make(os.fsencode(inpath), os.fsencode(outpath), C.byref(n), C.byref(m)))
+        return n.value, m.value
+
+    @property
+    def nseqs(self): return lib().bsq_flatfile_nseqs(self.h)
+    @property
+    def maxseqlen(self): return lib().bsq_flatfile_max_seq_len(self.h)
+    @property
+    def bytes_ptr(self): return lib().bsq_flatfile_bytes(self.h)
+    @property
+    def offsets_ptr(self): return lib().bsq_flatfile_offsets(self.h)
+
+    def close(self):
+        if self.h:
+            lib().bsq_flatfile_close(self.h)
             self.h = C.c_void_p()

@@ -35,6 +35,7 @@ namespace bsqpy {
     const std::string msg = bsq_last_error();
     switch (rc) {
         case BSQ_ERR_ARG: throw py::value_error(msg);
+        case BSQ_ERR_RANGE: throw py::index_error(msg);
         case BSQ_ERR_TOO_LONG:  // tokens: runtime_error (tokenize.h:458); one-hot: invalid_argument (:361)
             if (onehot) throw py::value_error(msg);
             throw std::runtime_error(msg);
@@ -208,6 +209,116 @@ ArrayArg array_arg(const py::object &obj, const char *what, int itemsize, const 
     return a;
 }
 
+// ------------------------------------------------------------------ FlatFile (src/fxstats.cpp:24-200)
+// Same constructor overloads, methods and properties as the reference's class.  Sequences come
+// back as bytearray like there.  Additive: `pinned=` (hold the file in page-locked memory so
+// batches DMA straight from it), `packed()` (zero-copy numpy views of residues + offsets) and
+// being accepted directly by Tokenizer.batch_tokenize / batch_onehot_encode (no Python objects
+// per sequence).
+class FlatFile {
+public:
+    FlatFile(const std::string &path, py::ssize_t maxseqlen, bool pinned) : path_(path) {
+        check(bsq_flatfile_open(&f_, path.c_str(), maxseqlen, pinned ? BSQ_FF_PINNED : BSQ_FF_MMAP));
+    }
+    FlatFile(const std::string &inpath, const std::string &outpath, bool pinned)
+        : path_(outpath.empty() ? inpath + ".ff" : outpath) {
+        int64_t n = 0, longest = 0;
+        check(bsq_flatfile_make(inpath.c_str(), outpath.c_str(), &n, &longest));
+        check(bsq_flatfile_open(&f_, path_.c_str(), longest, pinned ? BSQ_FF_PINNED : BSQ_FF_MMAP));
+    }
+    FlatFile(const FlatFile &) = delete;
+    FlatFile &operator=(const FlatFile &) = delete;
+    ~FlatFile() { bsq_flatfile_close(f_); }
+
+    const bsq_flatfile *handle() const { return f_; }
+    const std::string &path() const { return path_; }
+    int64_t nseqs() const { return bsq_flatfile_nseqs(f_); }
+    int64_t seq_offset() const { return bsq_flatfile_seq_offset(f_); }
+    int64_t max_seq_len() const { return bsq_flatfile_max_seq_len(f_); }
+    bool is_pinned() const { return bsq_flatfile_is_pinned(f_) != 0; }
+
+    py::bytearray access(int64_t i) const {
+        if (i < 0 || i >= nseqs()) throw py::index_error("Accessing sequence out of range");  // src/fxstats.cpp:129
+        const int64_t *o = bsq_flatfile_offsets(f_);
+        return py::bytearray(reinterpret_cast<const char *>(bsq_flatfile_bytes(f_) + o[i]), static_cast<size_t>(o[i + 1] - o[i]));
+    }
+    py::list range_access(py::ssize_t i, py::ssize_t j, py::ssize_t step) const {  // src/fxstats.cpp:121-126
+        if (step == 0) throw py::value_error("step must be nonzero");
+        py::list ret;
+        for (py::ssize_t idx = i; step > 0 ? idx < j : idx > j; idx += step) ret.append(access(idx));
+        return ret;
+    }
+    py::list slice_access(const py::slice &slc) const {  // src/fxstats.cpp:106-114
+        size_t start = 0, stop = 0, step = 0, len = 0;
+        if (!slc.compute(static_cast<size_t>(nseqs()), &start, &stop, &step, &len)) throw py::error_already_set();
+        return range_access(static_cast<py::ssize_t>(start), static_cast<py::ssize_t>(stop), static_cast<py::ssize_t>(step));
+    }
+    // The reference indexes its index array twice (`access(ptr[ptr[i]])`, src/fxstats.cpp:95-105);
+    // here entry i selects sequence idx[i].
+    py::list array_access(const py::array &idx) const {
+        py::array_t<uint64_t, py::array::forcecast> ids(idx);
+        py::list ret;
+        const uint64_t *p = ids.data();
+        for (py::ssize_t i = 0; i < ids.size(); ++i) ret.append(access(static_cast<int64_t>(p[i])));
+        return ret;
+    }
+    py::object getitem(py::ssize_t idx) const {  // src/fxstats.cpp:176-187
+        if (idx < 0) {
+            if (idx < -static_cast<py::ssize_t>(nseqs())) throw py::index_error("For a negative index, idx must be >= -len(x)");
+            idx += nseqs();
+        }
+        return access(idx);
+    }
+    py::array indptr() const {  // a copy, like src/fxstats.cpp:115-120
+        py::array_t<uint64_t> ret(static_cast<py::ssize_t>(nseqs() + 1));
+        std::memcpy(ret.mutable_data(), bsq_flatfile_offsets(f_), sizeof(uint64_t) * static_cast<size_t>(nseqs() + 1));
+        return ret;
+    }
+    // zero-copy (residues uint8, offsets[start..stop] int64) views; they keep `self` alive
+    py::tuple packed(py::ssize_t start, const py::object &stop_o, const py::object &self) const {
+        const int64_t n = nseqs();
+        int64_t stop = stop_o.is_none() ? n : stop_o.cast<int64_t>();
+        if (start < 0 || stop < start || stop > n) throw py::index_error("Accessing sequence out of range");
+        const int64_t *o = bsq_flatfile_offsets(f_);
+        py::array_t<uint8_t> bytes({static_cast<py::ssize_t>(o[n])}, {1}, bsq_flatfile_bytes(f_), self);
+        py::array_t<int64_t> offs({static_cast<py::ssize_t>(stop - start + 1)}, {8}, o + start, self);
+        py::detail::array_proxy(bytes.ptr())->flags &= ~py::detail::npy_api::NPY_ARRAY_WRITEABLE_;
+        py::detail::array_proxy(offs.ptr())->flags &= ~py::detail::npy_api::NPY_ARRAY_WRITEABLE_;
+        return py::make_tuple(bytes, offs);
+    }
+
+private:
+    std::string path_;
+    bsq_flatfile *f_ = nullptr;
+};
+
+// src/fxstats.cpp:136-151.  The reference's __next__ advances *before* the first item is
+// read and yields the iterator itself, so `for it in ff` visits sequences 1..n-1 through
+// `it.seq` / `it.sequence`; mirrored as is.  (`ff[i]`, `ff.access(...)`, `ff.packed()` see all.)
+struct FlatFileIterator {
+    const FlatFile *ff;
+    int64_t start, stop;
+    FlatFileIterator &next() {
+        if (++start == stop) throw py::stop_iteration("End of iterator");
+        return *this;
+    }
+    py::bytearray sequence() const { return ff->access(start); }
+};
+
+py::list getstats(const py::sequence &items) {  // src/fxstats.cpp:202-219
+    py::list out;
+    for (const auto &item : items) {
+        const std::string path = item.cast<std::string>();
+        int64_t *lens = nullptr, n = 0;
+        check(bsq_fastx_lengths(path.c_str(), &lens, &n));
+        py::array_t<uint64_t> arr(static_cast<py::ssize_t>(n));
+        for (int64_t i = 0; i < n; ++i) arr.mutable_data()[i] = static_cast<uint64_t>(lens[i]);
+        bsq_free(lens);
+        out.append(arr);
+    }
+    return out;
+}
+
 // ------------------------------------------------------------------ the Tokenizer class
 class Tokenizer {
 public:
@@ -268,6 +379,8 @@ public:
         const char dc = destchar.empty() ? '\0' : destchar[0];
         const int kind = bsq_kind_of_destchar(dc);
         if (kind < 0) raise_status(kind);
+        if (py::isinstance<FlatFile>(batch))  // additive: a whole FlatFile, no per-sequence objects
+            return run_flatfile(batch.cast<const FlatFile &>(), 0, py::none(), py::none(), padlen, dc, kind, false, batch_first, device);
         if (padlen <= 0) throw py::value_error("batch tokenize requires padlen is provded.");
         Unpacked u;
         unpack_items(batch, u);
@@ -281,6 +394,8 @@ public:
         const char dc = destchar.empty() ? '\0' : destchar[0];
         const int kind = bsq_kind_of_destchar(dc);
         if (kind < 0) raise_status(kind);
+        if (py::isinstance<FlatFile>(batch))
+            return run_flatfile(batch.cast<const FlatFile &>(), 0, py::none(), mask, padlen, dc, kind, true, false, device);
         if (padlen <= 0) throw py::value_error("batch tokenize requires padlen is provded.");
         Unpacked u;
         unpack_items(batch, u);
@@ -318,6 +433,23 @@ public:
     py::object onehot_packed(const py::object &bytes, const py::object &offsets, py::ssize_t padlen, const std::string &destchar,
                              const py::object &mask, const py::object &device, bool check_len) const {
         return run_packed(bytes, offsets, mask, padlen, destchar, true, false, device, check_len);
+    }
+
+    // ---- additive: sequences [start, stop) of a FlatFile; padlen <= 0 means the file's longest
+    // sequence + bos + eos (what FlatFileDataset uses, bioseq/loaders.py:44)
+    py::object tokenize_flatfile(const FlatFile &ff, py::ssize_t start, const py::object &stop, py::ssize_t padlen,
+                                 const std::string &destchar, bool batch_first, const py::object &device) const {
+        const char dc = destchar.empty() ? '\0' : destchar[0];
+        const int kind = bsq_kind_of_destchar(dc);
+        if (kind < 0) raise_status(kind);
+        return run_flatfile(ff, start, stop, py::none(), padlen, dc, kind, false, batch_first, device);
+    }
+    py::object onehot_flatfile(const FlatFile &ff, py::ssize_t start, const py::object &stop, py::ssize_t padlen,
+                               const std::string &destchar, const py::object &mask, const py::object &device) const {
+        const char dc = destchar.empty() ? '\0' : destchar[0];
+        const int kind = bsq_kind_of_destchar(dc);
+        if (kind < 0) raise_status(kind);
+        return run_flatfile(ff, start, stop, mask, padlen, dc, kind, true, false, device);
     }
 
     // ---- single-sequence onehot_encode (src/tokenize.cpp:8-48, src/tokenize.h:188-216)
@@ -464,6 +596,51 @@ private:
         return out;
     }
 
+    // FlatFile range -> device.  The file's offset table and residues are the packed form already.
+    // mask (one-hot only): a uint8 array covering the whole file's residues, indexed like them.
+    py::object run_flatfile(const FlatFile &ff, py::ssize_t start, const py::object &stop_o, const py::object &mask,
+                            py::ssize_t padlen, char dc, int kind, bool onehot, bool batch_first, const py::object &device) const {
+        Torch &t = Torch::get();
+        const int64_t total = ff.nseqs();
+        const int64_t stop = stop_o.is_none() ? total : stop_o.cast<int64_t>();
+        if (start < 0 || stop < start || stop > total) throw py::index_error("Accessing sequence out of range");
+        if (padlen <= 0) padlen = ff.max_seq_len() + bos_ + eos_;
+        if (padlen <= 0) throw py::value_error("batch tokenize requires padlen is provded.");
+        const int64_t n = stop - start;
+        const int64_t *ho = bsq_flatfile_offsets(ff.handle()) + start;
+        const uint8_t *hb = bsq_flatfile_bytes(ff.handle());
+        ArrayArg m;
+        if (!mask.is_none()) {
+            m = array_arg(mask, "mask", 1, "uint8", t.uint8);
+            if (m.on_device) throw py::value_error("mask must be a host array for a FlatFile batch");
+            if (m.count < bsq_flatfile_offsets(ff.handle())[total]) throw py::value_error("mask shorter than the file's residues");
+        }
+        check(bsq_check_lengths_host(ho, n, padlen, &tok_), onehot);
+        const int dev = resolve_device(device);
+        std::vector<int64_t> shape;
+        if (onehot) shape = {padlen, n, tok_.alphabet_size};
+        else if (batch_first) shape = {n, padlen};
+        else shape = {padlen, n};
+        py::object out = new_tensor(shape, t.dtype_of(dc, kind), dev);
+        if (n == 0) return out;
+        void *st = current_stream(dev);
+        void *optr = data_ptr(out);
+        DeviceCtx &ctx = device_ctx(dev);
+        int rc;
+        {
+            py::gil_scoped_release nogil;
+            std::lock_guard<std::mutex> g(ctx.mu);
+            if (onehot)
+                rc = bsq_onehot_host(ctx.stager, st, hb, ho, static_cast<const uint8_t *>(m.ptr), n, padlen, &tok_, kind, optr);
+            else
+                rc = bsq_tokenize_host(ctx.stager, st, hb, ho, n, padlen, &tok_, batch_first, kind, optr);
+            // a pinned file (or mask) is read asynchronously; it must outlive the copies
+            if (rc == BSQ_OK && (ff.is_pinned() || m.ptr != nullptr)) rc = bsq_stager_sync_copies(ctx.stager);
+        }
+        check(rc, onehot);
+        return out;
+    }
+
     py::object run_packed(const py::object &bytes, const py::object &offsets, const py::object &mask, py::ssize_t padlen,
                           const std::string &destchar, bool onehot, bool batch_first, const py::object &device,
                           bool check_len) const {
@@ -528,9 +705,44 @@ private:
 }  // namespace bsqpy
 
 PYBIND11_MODULE(cbioseq, m) {
+    using bsqpy::FlatFile;
+    using bsqpy::FlatFileIterator;
     using bsqpy::Tokenizer;
     m.doc() = "B200-native drop-in for bioseq's cbioseq tokenizer module (GPU batch tokenisation)";
     m.attr("__bsq_abi_version__") = bsq_abi_version();
+
+    py::class_<FlatFileIterator>(m, "FlatFileIterator")
+        .def(py::init<FlatFileIterator>())
+        .def("__iter__", [](const FlatFileIterator &x) { return x; })
+        .def("__next__", [](FlatFileIterator &x) { return x.next(); })
+        .def_property_readonly("sequence", &FlatFileIterator::sequence)
+        .def_property_readonly("seq", &FlatFileIterator::sequence);
+
+    py::class_<FlatFile>(m, "FlatFile")
+        .def(py::init<std::string, py::ssize_t, bool>(), py::arg("inputfile"), py::arg("maxseqlen") = -1, py::kw_only(),
+             py::arg("pinned") = false)
+        .def(py::init<std::string, std::string, bool>(), py::arg("inputfile"), py::arg("outputfile"), py::kw_only(),
+             py::arg("pinned") = false)
+        .def_property_readonly("path", &FlatFile::path)
+        .def("access", &FlatFile::access)
+        .def("access", &FlatFile::slice_access)
+        .def("access", &FlatFile::range_access, py::arg("start"), py::arg("stop"), py::arg("step") = 1)
+        .def("__len__", &FlatFile::nseqs)
+        .def("nseqs", &FlatFile::nseqs)
+        .def("size", &FlatFile::nseqs)
+        .def("seq_offset", &FlatFile::seq_offset)
+        .def("indptr", &FlatFile::indptr)
+        .def_property_readonly("maxseqlen", &FlatFile::max_seq_len)
+        .def_property_readonly("max_seq_len", &FlatFile::max_seq_len)
+        .def_property_readonly("pinned", &FlatFile::is_pinned)
+        .def("__iter__", [](const FlatFile &x) { return FlatFileIterator{&x, 0, x.nseqs()}; }, py::keep_alive<0, 1>())
+        .def("__getitem__", &FlatFile::getitem)
+        .def("__getitem__", &FlatFile::slice_access)
+        .def("__getitem__", &FlatFile::array_access)
+        .def("packed", [](py::object self, py::ssize_t start, const py::object &stop) {
+                 return self.cast<const FlatFile &>().packed(start, stop, self);
+             }, py::arg("start") = 0, py::arg("stop") = py::none());
+    m.def("getstats", &bsqpy::getstats);
 
     py::class_<Tokenizer>(m, "Tokenizer")
         .def(py::init<std::string, bool, bool, bool>(), py::arg("key"), py::arg("eos") = false, py::arg("bos") = false,
@@ -552,6 +764,12 @@ PYBIND11_MODULE(cbioseq, m) {
         .def("batch_onehot_encode_packed", &Tokenizer::onehot_packed, py::arg("bytes"), py::arg("offsets"), py::arg("padlen") = -1,
              py::arg("destchar") = "B", py::arg("mask") = py::none(), py::arg("device") = py::none(),
              py::arg("check_lengths") = true)
+        .def("batch_tokenize_flatfile", &Tokenizer::tokenize_flatfile, py::arg("flatfile"), py::arg("start") = 0,
+             py::arg("stop") = py::none(), py::arg("padlen") = -1, py::arg("destchar") = "B", py::arg("batch_first") = false,
+             py::arg("device") = py::none())
+        .def("batch_onehot_encode_flatfile", &Tokenizer::onehot_flatfile, py::arg("flatfile"), py::arg("start") = 0,
+             py::arg("stop") = py::none(), py::arg("padlen") = -1, py::arg("destchar") = "B", py::arg("mask") = py::none(),
+             py::arg("device") = py::none())
         .def("alphabet_size", &Tokenizer::alphabet_size)
         .def("bos", &Tokenizer::bos)
         .def("eos", &Tokenizer::eos)

@@ -1,0 +1,118 @@
+"""FlatFile callers of the tokenizer, GPU-fed (reference: bioseq/loaders.py:11-115, bioseq/__init__.py:198-219).
+
+The reference's loaders pull one Python ``bytearray`` per sequence out of the FlatFile, tokenise
+on the CPU and move the numpy result to the device.  Here a range of the file goes to the GPU as
+packed bytes + offsets (``Tokenizer.batch_tokenize_flatfile``), so no per-sequence host work is
+left.  BLOSUM62 augmentation (``augment=``; bioseq/blosum.py) is not part of this path and is
+rejected rather than silently ignored.
+"""
+import numpy as np
+
+from . import cbioseq
+
+
+def FF2NP(x, tokenizer, destfile, *, batch_size=8192, device=None):
+    """Tokenise a whole FlatFile into an ``np.memmap`` of shape (nseqs, maxseqlen + bos + eos), uint8
+    (bioseq/loaders.py:11-26).  Rows are produced on the GPU ``batch_size`` sequences at a time.
+
+    The reference passes ``padlen=maxseqlen`` while sizing rows ``maxseqlen + bos + eos``, which only
+    works without BOS/EOS; the row width is used as padlen here."""
+    assert isinstance(x, cbioseq.FlatFile)
+    assert isinstance(tokenizer, cbioseq.Tokenizer)
+    total_msl = x.maxseqlen + tokenizer.includes_bos() + tokenizer.includes_eos()
+    nseqs = x.nseqs()
+    retmat = np.memmap(destfile, mode='w+', dtype=np.uint8, shape=(nseqs, total_msl))
+    for start in range(0, nseqs, batch_size):
+        stop = min(start + batch_size, nseqs)
+        toks = tokenizer.batch_tokenize_flatfile(x, start, stop, padlen=total_msl, batch_first=True, destchar='B',
+                                                 device=device)
+        retmat[start:stop] = toks.cpu().numpy()
+    return (retmat, destfile)
+
+
+def FF2Tensor(x, tokenizer, *, batch_first=True, destchar='B', device=None):
+    """The whole FlatFile as one token tensor resident on the GPU (one staged pass over the file)."""
+    return tokenizer.batch_tokenize_flatfile(x, 0, None, batch_first=batch_first, destchar=destchar, device=device)
+
+
+class FlatFileDataset:
+    """Map-style dataset over a FlatFile and a Tokenizer (bioseq/loaders.py:29-115).
+
+    ``ds[i]`` -> 1-D ``long`` token tensor of length ``max_seq_len``; ``ds[a:b]`` -> ``(b-a, max_seq_len)``.
+    With ``cnn=True`` items are one-hot ``float`` tensors laid out ``(batch, emb, length)`` for a slice
+    and ``(length, emb)`` for a single index, like the reference.  Tensors live on ``device``.
+    """
+
+    def __init__(self, ff, tokenizer, *, augment=0, augment_frac=0.5, cnn=False, device=None, maskfrac=0.15):
+        assert isinstance(ff, cbioseq.FlatFile)
+        assert isinstance(tokenizer, cbioseq.Tokenizer)
+        if augment:
+            raise NotImplementedError("BLOSUM62 augmentation (bioseq/blosum.py) is outside the GPU tokenisation path")
+        self.ff, self.tokenizer = ff, tokenizer
+        self.maskfrac, self.augment, self.augment_frac, self.cnn, self.device = maskfrac, augment, augment_frac, cnn, device
+        self.max_seq_len = ff.maxseqlen + tokenizer.includes_bos() + tokenizer.includes_eos()
+        self.maxseqlen = self.max_seq_len
+
+    def _range(self, index):
+        n = len(self)
+        if isinstance(index, slice):
+            start, stop, step = index.indices(n)
+            if step != 1:
+                raise IndexError("FlatFileDataset: only contiguous slices go to the GPU as one range")
+            return start, max(start, stop), True
+        if index < 0:
+            index += n
+        if not 0 <= index < n:
+            raise IndexError("Accessing sequence out of range")
+        return index, index + 1, False
+
+    def __getitem__(self, index):
+        import torch
+        start, stop, many = self._range(index)
+        if self.cnn:
+            oh = self.tokenizer.batch_onehot_encode_flatfile(self.ff, start, stop, padlen=self.max_seq_len, destchar='f',
+                                                             device=self.device)
+            return oh.permute(1, 2, 0) if many else oh[:, 0, :]
+        toks = self.tokenizer.batch_tokenize_flatfile(self.ff, start, stop, padlen=self.max_seq_len, batch_first=True,
+                                                      destchar='B', device=self.device).to(torch.long)
+        return toks if many else toks[0]
+
+    def access(self, slc, stop=None, step=None):
+        if isinstance(slc, int):
+            slc = slice(slc, stop, step)
+        return self[slc]
+
+    def batches(self, batch_size):
+        """Consecutive ``(batch, max_seq_len)`` token batches covering the file."""
+        for start in range(0, len(self), batch_size):
+            yield self[start:start + batch_size]
+
+    def __len__(self):
+        return self.ff.nseqs()
+
+    def cleanup(self):
+        pass
+
+
+class PyViewFF:
+    """Pure-numpy view of a FlatFile (bioseq/__init__.py:198-219)."""
+
+    def __init__(self, path):
+        fp = np.memmap(path, mode='r', dtype=np.uint8)
+        self.nseqs = int(fp[:8].view(np.uint64)[0])
+        self.offsets = fp[8:8 * (2 + self.nseqs)].view(np.uint64)
+        self.seqs = fp[8 * (2 + self.nseqs):]
+        self.fp = fp
+
+    def access(self, idx):
+        return bytes(self.seqs[int(self.offsets[idx]):int(self.offsets[idx + 1])])
+
+    def __getitem__(self, idx):
+        if isinstance(idx, int):
+            return self.access(idx)
+        if isinstance(idx, slice):
+            return [self.access(i) for i in range(*idx.indices(self.nseqs))]
+        raise ValueError("PyViewFF can only support slices and integers.")
+
+    def __len__(self):
+        return self.nseqs

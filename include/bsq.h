@@ -45,6 +45,8 @@ extern "C" {
 #define BSQ_ERR_KEY (-4)       /* "Invalid tokenizer type; select one from..." (tokenize.h:78) -> RuntimeError */
 #define BSQ_ERR_CUDA (-5)      /* CUDA runtime failure / no device -> RuntimeError              */
 #define BSQ_ERR_NOMEM (-6)
+#define BSQ_ERR_IO (-7)        /* file could not be opened / read / written -> RuntimeError     */
+#define BSQ_ERR_RANGE (-8)     /* std::out_of_range in the reference -> IndexError              */
 
 /* ---- element kinds of the output array (src/tokenize.cpp:66-79, :83-96) ------------ */
 typedef enum bsq_kind {
@@ -176,6 +178,41 @@ int bsq_tokenize_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const
 int bsq_onehot_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const int64_t *h_offsets,
                     const uint8_t *h_mask, int64_t nseq, int64_t padlen, const bsq_tokenizer *tok,
                     int kind, void *d_out);
+
+/* ---- FlatFile: the on-disk packed-sequence store that feeds the path -------------------- */
+/* The reference's FlatFile (src/fxstats.cpp:26-134) stores a FASTA/FASTQ collection as
+ *     uint64 nseqs | uint64 offsets[nseqs+1] | residue bytes          (src/fxstats.cpp:50-59)
+ * which is exactly the packed bytes + offsets form the kernels read: a range of sequences
+ * [start, stop) of an open file goes to the GPU as
+ *     bsq_tokenize_host(stager, stream, bsq_flatfile_bytes(f), bsq_flatfile_offsets(f) + start,
+ *                       stop - start, padlen, tok, batch_first, kind, d_out)
+ * with no per-sequence host work (the reference materialises one Python bytearray per
+ * sequence, src/fxstats.cpp:128-133, and walks them again in src/tokenize.h:389-419). */
+typedef struct bsq_flatfile bsq_flatfile;
+
+#define BSQ_FF_MMAP 0   /* map the file read-only (pageable: staged through the pinned ring)        */
+#define BSQ_FF_PINNED 1 /* read the file into cudaHostAlloc'ed memory once (direct DMA afterwards) */
+
+/* FlatFile::make (src/fxstats.cpp:33-64): parse a FASTA/FASTQ file (plain or gzip; kseq.h
+ * record rules) and write the flat file.  outpath NULL or "" -> inpath + ".ff".  Returns the
+ * number of sequences and the longest length through the out-pointers (either may be NULL).
+ * BSQ_ERR_IO "<path> failed to open" / "<path> could not be opened for writing" (:41,:53),
+ * BSQ_ERR_ARG "Cannot handle sequences longer than 2^32 - 1" (:46). */
+int bsq_flatfile_make(const char *inpath, const char *outpath, int64_t *nseqs, int64_t *max_seq_len);
+/* FlatFile(path, maxseqlen) (src/fxstats.cpp:66-75).  maxseqlen < 0: computed by a scan of
+ * the offsets.  Unlike the reference the header is validated against the file size. */
+int bsq_flatfile_open(bsq_flatfile **out, const char *path, int64_t maxseqlen, int mode);
+void bsq_flatfile_close(bsq_flatfile *f);
+int64_t bsq_flatfile_nseqs(const bsq_flatfile *f);
+int64_t bsq_flatfile_seq_offset(const bsq_flatfile *f);  /* (nseqs + 2) * 8, src/fxstats.cpp:67 */
+int64_t bsq_flatfile_max_seq_len(const bsq_flatfile *f);
+const int64_t *bsq_flatfile_offsets(const bsq_flatfile *f); /* nseqs+1 entries, relative to bsq_flatfile_bytes */
+const uint8_t *bsq_flatfile_bytes(const bsq_flatfile *f);   /* sequence i = bytes[offsets[i] .. offsets[i+1]) */
+int bsq_flatfile_is_pinned(const bsq_flatfile *f);
+/* getstats / getlens (src/fxstats.cpp:12-23, :202-219): sequence lengths of a FASTA/FASTQ
+ * file.  *lens is malloc'ed by the callee (free it with bsq_free). */
+int bsq_fastx_lengths(const char *path, int64_t **lens, int64_t *n);
+void bsq_free(void *p);
 
 /* ---- misc -------------------------------------------------------------------------- */
 int bsq_abi_version(void);

@@ -177,3 +177,91 @@ def load_ref(opt="O3"):
         return __import__(name)
     except ImportError:
         return None
+
+
+# ---------------------------------------------------------------------------------------------
+# FlatFile (src/fxstats.cpp:26-134): restatement of the FASTA/FASTQ -> flat file conversion.
+# Pinned against the compiled reference (oracle/_ref) by tests/test_flatfile.py and against
+# tests/golden/flatfile.json (generated from the reference by oracle/make_golden_flatfile.py).
+# ---------------------------------------------------------------------------------------------
+_SPACE = b" \t\n\v\f\r"
+
+
+def parse_fastx(data):
+    """Sequences of a FASTA/FASTQ byte string under the rules of the reference's vendored
+    kseq.h (src/kseq.h:173-216) as driven by FlatFile::make (src/fxstats.cpp:40-49):
+    kseq_read until the first negative return."""
+    n, p = len(data), 0
+    seqs = []
+    last_char = 0
+
+    def line_end(q):
+        e = data.find(b"\n", q)
+        return n if e < 0 else e
+
+    while True:
+        if last_char == 0:                                  # kseq.h:178-182 jump to the next header
+            while p < n and data[p] not in b">@":
+                p += 1
+            if p >= n:
+                break
+            last_char = data[p]
+            p += 1
+        if p >= n:                                          # :184 name read hits EOF
+            break
+        i = p
+        while i < n and data[i] not in _SPACE:
+            i += 1
+        delim = data[i] if i < n else 0
+        p = i + 1 if i < n else n
+        if delim != 0x0A:                                   # :185 comment = rest of the line
+            e = line_end(p)
+            p = e + 1 if e < n else n
+        seq = bytearray()
+        c = -1
+        while True:                                         # :190-194 sequence lines
+            if p >= n:
+                c = -1
+                break
+            c = data[p]
+            p += 1
+            if c in (0x3E, 0x2B, 0x40):
+                break
+            if c == 0x0A:
+                continue
+            seq.append(c)
+            if p < n:
+                e = line_end(p)
+                seq += data[p:e]
+                p = e + 1 if e < n else n
+                if len(seq) > 1 and seq[-1] == 0x0D:        # :138 one trailing CR per line
+                    seq.pop()
+        if c in (0x3E, 0x40):
+            last_char = c
+        if c == 0x2B:                                       # '+': FASTQ quality block :203-214
+            e = data.find(b"\n", p)
+            if e < 0:
+                break                                       # -2: no quality string
+            p = e + 1
+            qual = bytearray()
+            while p < n:
+                e = line_end(p)
+                qual += data[p:e]
+                p = e + 1 if e < n else n
+                if len(qual) > 1 and qual[-1] == 0x0D:
+                    qual.pop()
+                if len(qual) >= len(seq):
+                    break
+            last_char = 0
+            if len(qual) != len(seq):
+                break                                       # -2: quality of a different length
+        seqs.append(bytes(seq))
+    return seqs
+
+
+def flatfile_image(seqs):
+    """Bytes of the flat file for a list of sequences (layout src/fxstats.cpp:50-59)."""
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    if seqs:
+        np.cumsum([len(s) for s in seqs], out=offs[1:])
+    return np.uint64(len(seqs)).tobytes() + offs.tobytes() + b"".join(seqs)
