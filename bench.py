@@ -278,15 +278,26 @@ def run_ours(args):
         del seqs
     e2e_bases = sum(sets[i % ROT]["nbases"] for i in range(e2e_steps))
     h2d = int(np.mean([s["nbases"] + 8 * (NSEQ + 1) for s in sets]))
+    host_link = measure_host_link(torch) if "e2e" in sections else None
+
+    # ---- C5 slice on every rank (configs[4]: sharded tokenize + one-hot with H2D staging) ----------
+    c5 = None
+    if "c5" in sections:
+        barrier()
+        c5 = c5_slice(torch, capi, L, dev, st, rank)
+        barrier()
 
     # ---- reduce over ranks: max time ------------------------------------------------------------
-    t = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(bases_timed), float(e2e_bases), float(alg_bytes), float(launches)], dtype=torch.float64, device="cuda")
+    c5v = [c5["ms_h2d_inclusive"], c5["ms_device_resident"]] if c5 else [0.0, 0.0]
+    c5s = [c5["bases"], c5["h2d_bytes"], c5["alg_bytes_device"], c5["bases_device"]] if c5 else [0.0] * 4
+    t = torch.tensor([ms_total, e2e_s * 1e3] + c5v, dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(bases_timed), float(e2e_bases), float(alg_bytes), float(launches)] + [float(x) for x in c5s],
+                       dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_total_max, e2e_ms_max = t.tolist()
-    bases_all, e2e_bases_all, alg_all, launches_all = tot.tolist()
+    ms_total_max, e2e_ms_max, c5_ms_h2d, c5_ms_dev = t.tolist()
+    bases_all, e2e_bases_all, alg_all, launches_all, c5_bases, c5_h2d_bytes, c5_alg, c5_bases_dev = tot.tolist()
 
     extra = {}
     cpu = None
@@ -294,6 +305,8 @@ def run_ours(args):
     if rank == 0:
         if "extra" in sections:
             extra = secondary_measurements(torch, capi, L, dev, st)
+        if "c4" in sections and world == 1:
+            extra["c4_reduced_alphabets_1M_roundtrip"] = c4_measurements(torch, capi, L, dev, st, with_cpu="cpu" in sections)
         clocks = sampler.stop()
         if world == 1 and "cpu" in sections:
             cpu, ref_out = cpu_arm(sets[0]["buf"], sets[0]["offs"], steps=10, warmup=1, budget_s=20.0)
@@ -322,7 +335,10 @@ def run_ours(args):
                        "parallelism": f"{world} ranks, sequences sharded by index, no collective"},
             "e2e": {"value": e2e_bases_all / (e2e_ms_max * 1e-3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": PADLEN, "steps": e2e_steps, "api": "Tokenizer.batch_tokenize_packed(pinned host)",
-                    "matches_device_resident": e2e_ok, "list_of_bytes_api": e2e_list},
+                    "matches_device_resident": e2e_ok, "list_of_bytes_api": e2e_list,
+                    "host_link": None if host_link is None else dict(
+                        host_link, frac=(h2d * e2e_steps * world / (e2e_ms_max * 1e-3) / 1e9) / (host_link["h2d_gbs"] * world),
+                        note="frac = e2e H2D bytes/s over this rank's measured pinned cudaMemcpyAsync H2D rate (x ranks)")},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "tokenize_rows_ring_kernel<2,true> (K1r)",
@@ -330,10 +346,198 @@ def run_ours(args):
                          "launch_us": per_launch_ms * 1e3},
             "cpu_baseline": cpu, "parity_vs_cpu_reference": parity, "clocks": clocks, "extra": extra,
         }
+        if c5:
+            hl = (host_link or {}).get("h2d_gbs")
+            line["c5_slice"] = {
+                "workload": (f"configs[4] in bounded form, per GPU: {c5['nchunks']} chunks x {c5['chunk']} protein seqs (len 50-650), PROTEIN pbeos, "
+                             f"padlen {c5['padlen']}: pinned H2D (double-buffered) + int8 tokens (B,P) + uint8 one-hot (P,B,23) into a ring of 2 buffers"),
+                "n_gpus": world, "bases": int(c5_bases),
+                "h2d_inclusive": {"Gbases/s": c5_bases / c5_ms_h2d / 1e6, "ms_per_pass": c5_ms_h2d,
+                                  "h2d_GB/s_all_ranks": c5_h2d_bytes / c5_ms_h2d / 1e6,
+                                  "frac_of_host_link": None if not hl else c5_h2d_bytes / c5_ms_h2d / 1e6 / (hl * world)},
+                "device_resident": {"Gbases/s": c5_bases_dev / c5_ms_dev / 1e6, "ms_per_pass": c5_ms_dev, "GB/s_all_ranks": c5_alg / c5_ms_dev / 1e6,
+                                    "frac_of_measured_hbm": c5_alg / c5_ms_dev / 1e6 / (peak * world)},
+            }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+C4_KEYS = ("SEB6", "SEB8", "SEB10", "SEB14", "SEV10", "MURPHY", "LIA10", "LIB10", "DAYHOFF")
+
+
+def c4_measurements(torch, capi, L, dev, st, with_cpu):
+    """BASELINE.json configs[3]: reduced protein alphabets, tokenize + decode_tokens round trip, 1 M ragged
+    sequences (gen(104, 1e6, 50, 1024, AA20); pos tokenizers at padlen 1024, pbeos at 1026)."""
+    import ctypes as C
+    import bioseq_b200
+    from bioseq_b200.synth import gen, AA20
+    peak, _ = measured_peak()
+    n = 1_000_000
+    buf, offs = gen(104, n, 50, 1024, AA20)
+    nbases = int(offs[-1])
+    d_b, d_o = torch.from_numpy(buf).cuda(), torch.from_numpy(offs).cuda()
+    out = torch.empty(n * 1026, dtype=torch.uint8, device="cuda")
+    res = {"nseq": n, "bases": nbases, "tokenize": {}, "decode": {}}
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for flavour, flags, padlen in (("pos", dict(padchar=True), 1024), ("pbeos", dict(bos=True, eos=True, padchar=True), 1026)):
+        for key in C4_KEYS:
+            tk = capi.tokenizer(key, **flags)
+            call = (dev, st, d_b.data_ptr(), d_o.data_ptr(), n, padlen, C.byref(tk), 1, capi.I8, out.data_ptr())
+            for _ in range(2):
+                L.bsq_tokenize(*call)
+            a.record()
+            for _ in range(5):
+                L.bsq_tokenize(*call)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b) / 5
+            nbytes = nbases + 8 * (n + 1) + n * padlen
+            res["tokenize"][f"{key}_{flavour}"] = {"us_per_call": ms * 1e3, "Gbases/s": nbases / ms / 1e6,
+                                                   "frac_of_measured_hbm": nbytes / ms / 1e6 / peak}
+        # decode of the last alphabet's tokens: device part (validate + lengths + scan, then characters)
+        toks = out[:n * padlen].view(n, padlen)
+        d_ro = torch.empty(n + 1, dtype=torch.int64, device="cuda")
+        total = capi.decode_lengths(dev, st, toks, 1, n, padlen, padlen, 1, tk, d_ro)
+        d_ch = torch.empty(total, dtype=torch.uint8, device="cuda")
+        tot = C.c_int64()
+
+        def dec():
+            L.bsq_decode_lengths(dev, st, toks.data_ptr(), 1, n, padlen, padlen, 1, C.byref(tk), d_ro.data_ptr(), C.byref(tot))
+            L.bsq_decode_chars(dev, st, toks.data_ptr(), 1, n, padlen, padlen, 1, C.byref(tk), d_ro.data_ptr(), d_ch.data_ptr())
+        dec()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(3):
+            dec()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 3
+        res["decode"][f"{key}_{flavour}_device"] = {"us_per_call": ms * 1e3, "Gtokens/s": n * padlen / ms / 1e6, "chars": int(total),
+                                                    "GB/s": (2 * n * padlen + total + 8 * (n + 1)) / ms / 1e6}
+        # the public call on a slice of rows: device decode + D2H of the characters + Python str objects
+        ptk = bioseq_b200.Tokenizer(key, **flags)
+        rows = 32768
+        ptk.decode_tokens(toks[:1024])
+        t0 = time.perf_counter()
+        strs = ptk.decode_tokens(toks[:rows])
+        dt = time.perf_counter() - t0
+        res["decode"][f"{key}_{flavour}_api_{rows}_rows"] = {"ms": dt * 1e3, "Gtokens/s": rows * padlen / dt / 1e9,
+                                                             "chars": sum(map(len, strs))}
+        if with_cpu:
+            # checker + CPU baseline of the round trip: the reference's own tokenizer on the same rows
+            from bioseq_b200.synth import as_list
+            from oracle.oracle import load_ref
+            R = load_ref()
+            if R is not None:
+                m = 8192
+                rt = R.Tokenizer(key, **flags)
+                seqs = as_list(buf[:int(offs[m])], offs[:m + 1])
+                t0 = time.perf_counter()
+                rtoks = rt.batch_tokenize(seqs, padlen=padlen, destchar="B", batch_first=True, nthreads=os.cpu_count() or 1)
+                t1 = time.perf_counter()
+                rstrs = rt.decode_tokens(rtoks)
+                t2 = time.perf_counter()
+                ok = bool(np.array_equal(rtoks.view(np.uint8), toks[:m].cpu().numpy())) and rstrs == strs[:m]
+                if not ok:
+                    raise SystemExit(f"bench.py: C4 {key} {flavour}: GPU tokens/decoded strings differ from the CPU reference")
+                res["decode"][f"{key}_{flavour}_cpu_reference_{m}_rows"] = {
+                    "tokenize_ms": (t1 - t0) * 1e3, "decode_ms": (t2 - t1) * 1e3, "decode_Gtokens/s": m * padlen / (t2 - t1) / 1e9,
+                    "parity": ok}
+        del d_ch, d_ro
+    return res
+
+
+def c5_slice(torch, capi, L, dev, st, rank, nchunks=8, chunk=131072):
+    """BASELINE.json configs[4], one GPU's share in bounded form: `nchunks` chunks of `chunk` protein sequences
+    (lengths 50..650, seeds 105+chunk index as in SURVEY.md 8d C5), PROTEIN pbeos, padlen 652.  Each chunk goes
+    pinned host -> device on a copy stream (double-buffered) and is tokenised (int8 (B,652)) and one-hot encoded
+    (uint8 (652,B,23)) into a reused ring of two output buffers, like the full 8 M-sequences-per-GPU pass would."""
+    import ctypes as C
+    from bioseq_b200.synth import gen, AA20
+    P, NC = 652, 23
+    tk = capi.tokenizer(KEY, **FLAGS)
+    host = []
+    for c in range(nchunks):
+        buf, offs = gen(105 + c + 1000 * rank, chunk, 50, 650, AA20)
+        host.append((torch.from_numpy(buf).pin_memory(), torch.from_numpy(offs).pin_memory(), int(offs[-1])))
+    maxb = max(h[2] for h in host)
+    dbuf = [torch.empty(maxb + 64, dtype=torch.uint8, device="cuda") for _ in range(2)]
+    doff = [torch.empty(chunk + 1, dtype=torch.int64, device="cuda") for _ in range(2)]
+    toks = [torch.empty((chunk, P), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    oh = [torch.empty((P, chunk, NC), dtype=torch.uint8, device="cuda") for _ in range(2)]
+    copy_stream = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+
+    def one_pass(h2d):
+        for c in range(nchunks):
+            k = c % 2
+            hb, ho, nb = host[c]
+            if h2d:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(consumed[k])
+                    dbuf[k][:nb].copy_(hb, non_blocking=True)
+                    doff[k].copy_(ho, non_blocking=True)
+                    copied[k].record(copy_stream)
+                main.wait_event(copied[k])
+            L.bsq_tokenize(dev, st, dbuf[k].data_ptr(), doff[k].data_ptr(), chunk, P, C.byref(tk), 1, capi.I8, toks[k].data_ptr())
+            L.bsq_onehot(dev, st, dbuf[k].data_ptr(), doff[k].data_ptr(), None, chunk, P, C.byref(tk), capi.I8, oh[k].data_ptr())
+            consumed[k].record(main)
+
+    for k in range(2):
+        consumed[k].record(main)
+    one_pass(True)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 2
+    t0 = time.perf_counter()
+    a.record()
+    for _ in range(reps):
+        one_pass(True)
+    b.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms_h2d = a.elapsed_time(b) / reps
+    # device-resident share: the last two chunks are still in dbuf; re-run the kernels only
+    a.record()
+    for _ in range(reps):
+        one_pass(False)
+    b.record()
+    torch.cuda.synchronize()
+    ms_dev = a.elapsed_time(b) / reps
+    # what the kernel-only pass actually read: chunks nchunks-2 / nchunks-1 alternate in the two device buffers
+    bases = sum(h[2] for h in host)
+    bases_dev = sum(host[nchunks - 2 + (c % 2)][2] for c in range(nchunks))
+    alg = 2 * bases_dev + nchunks * (2 * 8 * (chunk + 1) + chunk * P + P * chunk * NC)
+    return {"bases": bases, "ms_h2d_inclusive": max(ms_h2d, wall * 1e3 / reps), "ms_device_resident": ms_dev,
+            "h2d_bytes": bases + nchunks * 8 * (chunk + 1), "alg_bytes_device": alg, "bases_device": bases_dev,
+            "nchunks": nchunks, "chunk": chunk, "padlen": P}
+
+
+def measure_host_link(torch, nbytes=256 << 20, reps=5):
+    """Pinned host->device copy rate of this rank's link (the roofline of the e2e number)."""
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    d.copy_(h, non_blocking=True)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(reps):
+        d.copy_(h, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    big = nbytes * reps / (a.elapsed_time(b) * 1e-3) / 1e9
+    hs, ds = h[:4 << 20], d[:4 << 20]
+    a.record()
+    for _ in range(32):
+        ds.copy_(hs, non_blocking=True)
+    b.record()
+    torch.cuda.synchronize()
+    small = (4 << 20) * 32 / (a.elapsed_time(b) * 1e-3) / 1e9
+    return {"h2d_gbs": big, "h2d_gbs_4MiB_copies": small, "bytes": nbytes}
 
 
 def secondary_measurements(torch, capi, L, dev, st):
@@ -440,7 +644,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--sections", default="value,e2e,extra,cpu",
+    ap.add_argument("--sections", default="value,e2e,extra,cpu,c4,c5",
                     help="comma list of measurement sections to run (profiling runs use --sections value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -19,6 +19,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 
 #include "bsq_internal.h"
@@ -1404,6 +1405,35 @@ int bsq_onehot(int device, void *stream, const uint8_t *d_bytes, const int64_t *
                          d_out);
 }
 
+// Scratch for the entry points that need a few words of device workspace (length check, decode
+// scan).  A library-owned memory pool per device with an unbounded release threshold: the default
+// pool hands its memory back to the driver at every synchronisation that finds it empty, which made
+// each of these calls pay a fresh physical allocation (measured: decode 1.07 ms -> 11.6 ms per call).
+namespace {
+int scratch_alloc(int device, void **p, size_t bytes, cudaStream_t st) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    if (device < 0 || device >= 64) return fail(BSQ_ERR_ARG, "bad device index");
+    cudaMemPool_t pool;
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (pools[device] == nullptr) {
+            cudaMemPoolProps props = {};
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = device;
+            BSQ_CUDA_TRY(cudaMemPoolCreate(&pools[device], &props));
+            uint64_t keep = ~0ull;
+            BSQ_CUDA_TRY(cudaMemPoolSetAttribute(pools[device], cudaMemPoolAttrReleaseThreshold, &keep));
+        }
+        pool = pools[device];
+    }
+    BSQ_CUDA_TRY(cudaMallocFromPoolAsync(p, bytes, pool, st));
+    return BSQ_OK;
+}
+}  // namespace
+
 int bsq_check_lengths_device(int device, void *stream, const int64_t *d_offsets, int64_t nseq, int64_t padlen,
                              const bsq_tokenizer *tok) {
     if (tok == nullptr) return fail(BSQ_ERR_ARG, "null tokenizer");
@@ -1412,7 +1442,7 @@ int bsq_check_lengths_device(int device, void *stream, const int64_t *d_offsets,
     BSQ_CUDA_TRY(cudaSetDevice(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned long long *d_max = nullptr;
-    BSQ_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_max), sizeof(*d_max), st));
+    if (int rc = scratch_alloc(device, reinterpret_cast<void **>(&d_max), sizeof(*d_max), st)) return rc;
     BSQ_CUDA_TRY(cudaMemsetAsync(d_max, 0, sizeof(*d_max), st));
     const int blocks = static_cast<int>(std::min<int64_t>((nseq + 255) / 256, 148 * 8));
     maxlen_kernel<<<blocks, 256, 0, st>>>(d_offsets, nseq, d_max);
@@ -1444,7 +1474,7 @@ int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int items
     if (d_tokens == nullptr && cols > 0) return fail(BSQ_ERR_ARG, "Empty array cannot yield a decoded string");  // src/tokenize.h:133
     const int64_t nblocks = (rows + kScanBlock - 1) / kScanBlock;
     int64_t *d_work = nullptr;  // [0] first_bad, [1] grand total, [2..] block totals
-    BSQ_CUDA_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_work), sizeof(int64_t) * (2 + nblocks), st));
+    if (int rc = scratch_alloc(device, reinterpret_cast<void **>(&d_work), sizeof(int64_t) * (2 + nblocks), st)) return rc;
     BSQ_CUDA_TRY(cudaMemsetAsync(d_work, 0xff, sizeof(int64_t), st));
     const InvParam inv = make_inv(*tok);
     const int fast = decode_fast_path(d_tokens, itemsize, row_stride, col_stride);
