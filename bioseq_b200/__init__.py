@@ -113,8 +113,20 @@ def torchify(arr):
     return arr if isinstance(arr, torch.Tensor) else torch.from_numpy(arr)
 
 
+from . import consumers  # noqa: E402
 from . import loaders  # noqa: E402
 from .loaders import PyViewFF  # noqa: E402
+from .consumers import batch_onehot_encode_bcl, batch_embed, augment_packed, batch_tokenize_augmented  # noqa: E402
+
+
+def __getattr__(name):
+    # nn.Module front ends import torch.nn; keep `import bioseq_b200` light
+    if name in ("TokenizerLayer", "EmbeddingTokenizerLayer", "layers"):
+        import importlib
+        layers = importlib.import_module(".layers", __name__)
+        return layers if name == "layers" else getattr(layers, name)
+    raise AttributeError(name)
+
 
 __all__ = ["onehot_encode", "cbioseq", "f_encode", "Tokenizer", "make_embedding",
            "bos_tokenizers", "eos_tokenizers", "beos_tokenizers", "pbeos_tokenizers", "peos_tokenizers",
@@ -122,4 +134,5 @@ __all__ = ["onehot_encode", "cbioseq", "f_encode", "Tokenizer", "make_embedding"
            "DNATokenizer", "AmineTokenizer", "Reduced6Tokenizer", "Reduced8Tokenizer", "Reduced10Tokenizer",
            "Reduced14Tokenizer", "DayhoffTokenizer", "LIATokenizer", "LIBTokenizer", "torchify",
            "set_num_threads", "get_num_threads", "Threading", "keys", "bkeys", "FlatFile", "FlatFileIterator", "getstats",
-           "PyViewFF", "loaders"]
+           "PyViewFF", "loaders", "consumers", "batch_onehot_encode_bcl", "batch_embed", "augment_packed",
+           "batch_tokenize_augmented", "TokenizerLayer", "EmbeddingTokenizerLayer"]

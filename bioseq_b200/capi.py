@@ -64,6 +64,13 @@ def lib():
         "bsq_stager_sync_copies": (i32, [vp]),
         "bsq_tokenize_host": (i32, [vp, vp, vp, vp, i64, i64, tokp, i32, i32, vp]),
         "bsq_onehot_host": (i32, [vp, vp, vp, vp, vp, i64, i64, tokp, i32, vp]),
+        "bsq_stage_host": (i32, [vp, vp, vp, vp, i64, C.POINTER(vp), C.POINTER(vp)]),
+        "bsq_stage_release": (i32, [vp, vp]),
+        "bsq_stager_set_augment": (i32, [vp, i32, C.c_double, C.c_uint64, i64]),
+        "bsq_onehot_bcl": (i32, [i32, vp, vp, vp, vp, i64, i64, tokp, i32, vp]),
+        "bsq_embed": (i32, [i32, vp, vp, vp, i64, i64, tokp, i32, vp, i64, i64, vp]),
+        "bsq_augment_blosum62": (i32, [i32, vp, vp, vp, i64, i32, C.c_double, C.c_uint64, i64]),
+        "bsq_blosum62_thresholds": (i32, [vp, vp, vp]),
         "bsq_flatfile_make": (i32, [C.c_char_p, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]),
         "bsq_flatfile_open": (i32, [C.POINTER(vp), C.c_char_p, i64, i32]),
         "bsq_flatfile_close": (None, [vp]),
@@ -90,7 +97,8 @@ EXPORTS = ("bsq_abi_version bsq_last_error bsq_launch_count bsq_launch_count_res
            "bsq_stager_create bsq_stager_destroy bsq_stager_sync_copies bsq_tokenize_host bsq_onehot_host "
            "bsq_flatfile_make bsq_flatfile_open bsq_flatfile_close bsq_flatfile_nseqs bsq_flatfile_seq_offset "
            "bsq_flatfile_max_seq_len bsq_flatfile_offsets bsq_flatfile_bytes bsq_flatfile_is_pinned bsq_fastx_lengths "
-           "bsq_free").split()
+           "bsq_free bsq_stage_host bsq_stage_release bsq_stager_set_augment bsq_onehot_bcl bsq_embed bsq_augment_blosum62 "
+           "bsq_blosum62_thresholds").split()
 
 
 def last_error():
@@ -141,6 +149,28 @@ def onehot(device, stream, d_bytes, d_offsets, d_mask, nseq, padlen, tok, kind, 
                            kind, _ptr(d_out)), onehot=True)
 
 
+def onehot_bcl(device, stream, d_bytes, d_offsets, d_mask, nseq, padlen, tok, kind, d_out):
+    check(lib().bsq_onehot_bcl(device, stream, _ptr(d_bytes), _ptr(d_offsets), _ptr(d_mask), nseq, padlen, C.byref(tok),
+                               kind, _ptr(d_out)), onehot=True)
+
+
+def embed(device, stream, d_bytes, d_offsets, nseq, padlen, tok, batch_first, d_weight, nrows, row_bytes, d_out):
+    check(lib().bsq_embed(device, stream, _ptr(d_bytes), _ptr(d_offsets), nseq, padlen, C.byref(tok), int(batch_first),
+                          _ptr(d_weight), nrows, row_bytes, _ptr(d_out)))
+
+
+def augment_blosum62(device, stream, d_bytes, d_offsets, nseq, chain_len, augment_frac, seed, seq_index_base=0):
+    check(lib().bsq_augment_blosum62(device, stream, _ptr(d_bytes), _ptr(d_offsets), nseq, chain_len, float(augment_frac),
+                                     seed & 0xFFFFFFFFFFFFFFFF, seq_index_base))
+
+
+def blosum62_thresholds():
+    import numpy as np
+    thr, row_of, aa = np.zeros((21, 19), np.uint32), np.zeros(256, np.uint8), np.zeros(20, np.uint8)
+    check(lib().bsq_blosum62_thresholds(thr.ctypes.data, row_of.ctypes.data, aa.ctypes.data))
+    return thr, row_of, aa
+
+
 def check_lengths_host(h_offsets, nseq, padlen, tok, onehot=False):
     check(lib().bsq_check_lengths_host(_ptr(h_offsets), nseq, padlen, C.byref(tok)), onehot)
 
@@ -178,6 +208,18 @@ class Stager:
 
     def sync_copies(self):
         check(lib().bsq_stager_sync_copies(self.h))
+
+    def stage(self, stream, h_bytes, h_offsets, nseq):
+        """-> (biased device residue pointer, device offsets pointer); see bsq_stage_host."""
+        db, do = C.c_void_p(), C.c_void_p()
+        check(lib().bsq_stage_host(self.h, stream, _ptr(h_bytes), _ptr(h_offsets), nseq, C.byref(db), C.byref(do)))
+        return db.value or 0, do.value or 0
+
+    def release(self, stream):
+        check(lib().bsq_stage_release(self.h, stream))
+
+    def set_augment(self, chain_len, augment_frac=1.0, seed=0, seq_index_base=0):
+        check(lib().bsq_stager_set_augment(self.h, chain_len, float(augment_frac), seed & 0xFFFFFFFFFFFFFFFF, seq_index_base))
 
     def close(self):
         if self.h:

@@ -196,6 +196,11 @@ struct bsq_stager {
     bool ring_used[kRingSlots] = {false, false, false};
     int ring_next = 0;
     std::vector<cudaEvent_t> events;  // one per chunk in flight
+    // BLOSUM62 augmentation applied to every staged range before it is tokenised (chain_len 0 = off)
+    int aug_chain = 0;
+    double aug_frac = 0.0;
+    uint64_t aug_seed = 0;
+    int64_t aug_base = 0;
 };
 
 namespace {
@@ -293,6 +298,11 @@ int staged_run(bsq_stager *s, cudaStream_t st, const uint8_t *h_bytes, const int
         BSQ_CUDA_TRY(cudaStreamWaitEvent(st, s->events[nchunk], 0));
         ++nchunk;
         int rc;
+        if (s->aug_chain > 0) {
+            rc = bsq_augment_blosum62(s->device, st, s->d_bytes - base, s->d_offs + i0, i1 - i0, s->aug_chain, s->aug_frac,
+                                      s->aug_seed, s->aug_base + i0);
+            if (rc) return rc;
+        }
         if (onehot) {
             rc = bsq::launch_onehot(st, d_bytes_shifted, s->d_offs + i0, d_mask_shifted, i1 - i0, nseq, padlen, *tok, kind,
                                     static_cast<uint8_t *>(d_out) + static_cast<size_t>(i0) * ncols * esize);
@@ -348,6 +358,57 @@ void bsq_stager_destroy(bsq_stager *s) {
 int bsq_stager_sync_copies(bsq_stager *s) {
     if (s == nullptr) return fail(BSQ_ERR_ARG, "null stager");
     BSQ_CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+    return BSQ_OK;
+}
+
+int bsq_stager_set_augment(bsq_stager *s, int chain_len, double augment_frac, uint64_t seed, int64_t seq_index_base) {
+    if (s == nullptr) return fail(BSQ_ERR_ARG, "null stager");
+    if (chain_len < 0 || !(augment_frac >= 0.0)) return fail(BSQ_ERR_ARG, "bad augmentation parameters");
+    s->aug_chain = chain_len;
+    s->aug_frac = augment_frac;
+    s->aug_seed = seed;
+    s->aug_base = seq_index_base;
+    return BSQ_OK;
+}
+
+int bsq_stage_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const int64_t *h_offsets, int64_t nseq,
+                   const uint8_t **d_bytes, const int64_t **d_offsets) {
+    if (s == nullptr || d_bytes == nullptr || d_offsets == nullptr) return fail(BSQ_ERR_ARG, "null argument");
+    if (nseq < 0 || h_offsets == nullptr) return fail(BSQ_ERR_ARG, "bad offsets");
+    BSQ_CUDA_TRY(cudaSetDevice(s->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int64_t base = h_offsets[0], nbytes = h_offsets[nseq] - base;
+    if (nbytes < 0) return fail(BSQ_ERR_ARG, "offsets must be non-decreasing");
+    if (nbytes > 0 && h_bytes == nullptr) return fail(BSQ_ERR_ARG, "null residue buffer");
+    if (s->busy) BSQ_CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->done, 0));
+    if (int rc = dev_reserve(reinterpret_cast<void **>(&s->d_bytes), &s->cap_bytes, static_cast<size_t>(nbytes) + 32)) return rc;
+    if (int rc = dev_reserve(reinterpret_cast<void **>(&s->d_offs), &s->cap_offs, sizeof(int64_t) * (nseq + 1))) return rc;
+    if (int rc = stage_copy(s, s->d_offs, h_offsets, sizeof(int64_t) * (nseq + 1), is_pinned(h_offsets))) return rc;
+    if (int rc = stage_copy(s, s->d_bytes, h_bytes + base, static_cast<size_t>(nbytes), nbytes > 0 && is_pinned(h_bytes))) return rc;
+    if (s->events.empty()) {
+        cudaEvent_t e;
+        BSQ_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->events.push_back(e);
+    }
+    BSQ_CUDA_TRY(cudaEventRecord(s->events[0], s->copy_stream));
+    BSQ_CUDA_TRY(cudaStreamWaitEvent(st, s->events[0], 0));
+    if (s->aug_chain > 0 && nseq > 0)
+        if (int rc = bsq_augment_blosum62(s->device, st, s->d_bytes - base, s->d_offs, nseq, s->aug_chain, s->aug_frac, s->aug_seed,
+                                          s->aug_base))
+            return rc;
+    // until bsq_stage_release the buffers count as in use by `stream`
+    BSQ_CUDA_TRY(cudaEventRecord(s->done, st));
+    s->busy = true;
+    *d_bytes = s->d_bytes - base;
+    *d_offsets = s->d_offs;
+    return BSQ_OK;
+}
+
+int bsq_stage_release(bsq_stager *s, void *stream) {
+    if (s == nullptr) return fail(BSQ_ERR_ARG, "null stager");
+    BSQ_CUDA_TRY(cudaSetDevice(s->device));
+    BSQ_CUDA_TRY(cudaEventRecord(s->done, static_cast<cudaStream_t>(stream)));
+    s->busy = true;
     return BSQ_OK;
 }
 

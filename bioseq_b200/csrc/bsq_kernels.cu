@@ -1140,11 +1140,7 @@ int ring_ctas_per_sm() {
     return n;
 }
 
-struct Prepared {
-    LutParam lut;
-    Specials sp;
-    Expand ex;
-};
+}  // namespace
 
 // mode 0: batch-first one-byte tokens (codes are the output bytes: ids wrap to 8 bits like
 //         the reference's int -> int8 store);
@@ -1182,6 +1178,8 @@ Prepared prepare(const bsq_tokenizer &tok, int mode) {
     p.ex.map[3] = onehot ? -1 : 0;
     return p;
 }
+
+namespace {
 
 int check_common(int device, int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int kind, const void *d_out) {
     if (tok == nullptr) return fail(BSQ_ERR_ARG, "null tokenizer");

@@ -14,6 +14,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+struct bsq_tokenizer;
+
 namespace bsq {
 
 struct LutParam {
@@ -57,6 +59,16 @@ __host__ __device__ __forceinline__ uint32_t fd_div(uint32_t n, const FastDiv &f
     const uint32_t t = static_cast<uint32_t>((static_cast<uint64_t>(n) * f.mul) >> 32);
     return (t + n) >> f.shift;
 }
+
+// Kernel-side form of a tokenizer (built on the host by prepare(), bsq_kernels.cu):
+// mode 0: batch-first one-byte tokens (codes are the output bytes), mode 1: tokens through Expand
+// (wide element types, tile kernels, embedding gather), mode 2: one-hot columns through Expand.
+struct Prepared {
+    LutParam lut;
+    Specials sp;
+    Expand ex;
+};
+Prepared prepare(const bsq_tokenizer &tok, int mode);
 
 #ifdef __CUDACC__
 

@@ -3,12 +3,14 @@
 The reference's loaders pull one Python ``bytearray`` per sequence out of the FlatFile, tokenise
 on the CPU and move the numpy result to the device.  Here a range of the file goes to the GPU as
 packed bytes + offsets (``Tokenizer.batch_tokenize_flatfile``), so no per-sequence host work is
-left.  BLOSUM62 augmentation (``augment=``; bioseq/blosum.py) is not part of this path and is
-rejected rather than silently ignored.
+left.  BLOSUM62 augmentation (``augment=``; bioseq/blosum.py:63-87) runs on the device between the copy and
+the tokeniser (``consumers``; Philox streams keyed by the dataset seed, the draw number and the sequence index),
+and ``cnn=True`` batches are written directly in the ``(batch, emb, length)`` float layout.
 """
 import numpy as np
 
 from . import cbioseq
+from . import consumers
 
 
 def FF2NP(x, tokenizer, destfile, *, batch_size=8192, device=None):
@@ -43,12 +45,11 @@ class FlatFileDataset:
     and ``(length, emb)`` for a single index, like the reference.  Tensors live on ``device``.
     """
 
-    def __init__(self, ff, tokenizer, *, augment=0, augment_frac=0.5, cnn=False, device=None, maskfrac=0.15):
+    def __init__(self, ff, tokenizer, *, augment=0, augment_frac=0.5, cnn=False, device=None, maskfrac=0.15, seed=13):
         assert isinstance(ff, cbioseq.FlatFile)
         assert isinstance(tokenizer, cbioseq.Tokenizer)
-        if augment:
-            raise NotImplementedError("BLOSUM62 augmentation (bioseq/blosum.py) is outside the GPU tokenisation path")
         self.ff, self.tokenizer = ff, tokenizer
+        self.seed, self._draw = int(seed), 0  # the reference seeds its generator with 13 (bioseq/loaders.py:49-50)
         self.maskfrac, self.augment, self.augment_frac, self.cnn, self.device = maskfrac, augment, augment_frac, cnn, device
         self.max_seq_len = ff.maxseqlen + tokenizer.includes_bos() + tokenizer.includes_eos()
         self.maxseqlen = self.max_seq_len
@@ -66,15 +67,33 @@ class FlatFileDataset:
             raise IndexError("Accessing sequence out of range")
         return index, index + 1, False
 
+    def _augment_kwargs(self, start):
+        """Every fetch is a new draw (the reference's generator advances per item, bioseq/loaders.py:71-73);
+        within a draw a sequence's stream depends on its index in the file only."""
+        self._draw += 1
+        return dict(augment=self.augment, augment_frac=self.augment_frac, seq_index_base=start,
+                    seed=(self.seed & 0xFFFFFFFF) | ((self._draw & 0xFFFFFFFF) << 32))
+
     def __getitem__(self, index):
         import torch
         start, stop, many = self._range(index)
+        aug = self._augment_kwargs(start) if self.augment else {}
         if self.cnn:
+            if many:  # (batch, emb, length) float, written in that layout by one kernel
+                return consumers.batch_onehot_encode_bcl(self.tokenizer, (self.ff, start, stop), padlen=self.max_seq_len,
+                                                         destchar='f', device=self.device, **aug)
+            if aug:
+                return consumers.batch_onehot_encode_bcl(self.tokenizer, (self.ff, start, stop), padlen=self.max_seq_len,
+                                                         destchar='f', device=self.device, **aug)[0].t()
             oh = self.tokenizer.batch_onehot_encode_flatfile(self.ff, start, stop, padlen=self.max_seq_len, destchar='f',
                                                              device=self.device)
-            return oh.permute(1, 2, 0) if many else oh[:, 0, :]
-        toks = self.tokenizer.batch_tokenize_flatfile(self.ff, start, stop, padlen=self.max_seq_len, batch_first=True,
-                                                      destchar='B', device=self.device).to(torch.long)
+            return oh[:, 0, :]
+        if aug:
+            toks = consumers.batch_tokenize_augmented(self.tokenizer, (self.ff, start, stop), padlen=self.max_seq_len,
+                                                      batch_first=True, destchar='B', device=self.device, **aug).to(torch.long)
+        else:
+            toks = self.tokenizer.batch_tokenize_flatfile(self.ff, start, stop, padlen=self.max_seq_len, batch_first=True,
+                                                          destchar='B', device=self.device).to(torch.long)
         return toks if many else toks[0]
 
     def access(self, slc, stop=None, step=None):
@@ -92,6 +111,13 @@ class FlatFileDataset:
 
     def cleanup(self):
         pass
+
+
+class AugmentedSeqDataset(FlatFileDataset):
+    """bioseq/loaders.py:117-119."""
+
+    def __init__(self, ff, tokenizer, augment=1, augment_frac=.5, **kw):
+        super().__init__(ff, tokenizer, augment=augment, augment_frac=augment_frac, **kw)
 
 
 class PyViewFF:

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BSQ_ABI_VERSION 1
+#define BSQ_ABI_VERSION 2
 
 /* ---- status codes ---------------------------------------------------------------- */
 #define BSQ_OK 0
@@ -178,6 +178,51 @@ int bsq_tokenize_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const
 int bsq_onehot_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const int64_t *h_offsets,
                     const uint8_t *h_mask, int64_t nseq, int64_t padlen, const bsq_tokenizer *tok,
                     int kind, void *d_out);
+
+/* Stage a packed host batch into the stager's device buffers without running a kernel, for the
+ * device entry points that have no *_host twin (bsq_embed, bsq_onehot_bcl, ...).  `stream` is made
+ * to wait for the copy.  *d_bytes is biased so that residue k of h_bytes is (*d_bytes)[k], i.e. it
+ * pairs with the unrebased *d_offsets exactly like h_bytes pairs with h_offsets.  The buffers stay
+ * valid until the next *_host / bsq_stage_host call on this stager; call bsq_stage_release after
+ * enqueuing the kernels that read them so that the next staging waits for those kernels. */
+int bsq_stage_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const int64_t *h_offsets, int64_t nseq,
+                   const uint8_t **d_bytes, const int64_t **d_offsets);
+int bsq_stage_release(bsq_stager *s, void *stream);
+
+/* ---- consumers fused onto the tokeniser ------------------------------ */
+/* One-hot in (nseq, alphabet_size, padlen) layout: what the reference's CNN path builds from
+ * batch_onehot_encode with einops.rearrange("length batch emb -> batch emb length") and .float()
+ * (bioseq/loaders.py:74-75, :93-94) -- two extra full-tensor passes -- written here in one pass.
+ * Element semantics are bsq_onehot's (src/tokenize.h:345-368); d_mask as there. */
+int bsq_onehot_bcl(int device, void *stream, const uint8_t *d_bytes, const int64_t *d_offsets, const uint8_t *d_mask,
+                   int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out);
+/* tokenize -> embedding gather: d_out[(i, p), :] = d_weight[token(i, p), :] with the tokens of
+ * bsq_tokenize (never materialised); d_out is (nseq, padlen, row) if batch_first else
+ * (padlen, nseq, row).  Replaces batch_tokenize -> torch.from_numpy -> .to(device) -> nn.Embedding
+ * (bioseq/__init__.py:171-188 make_embedding and its callers).  Rows are opaque: row_bytes (a
+ * multiple of 16) of any element type; nrows >= alphabet_size; d_weight 16-byte aligned. */
+int bsq_embed(int device, void *stream, const uint8_t *d_bytes, const int64_t *d_offsets, int64_t nseq, int64_t padlen,
+              const bsq_tokenizer *tok, int batch_first, const void *d_weight, int64_t nrows, int64_t row_bytes, void *d_out);
+
+/* ---- BLOSUM62 augmentation on the device ------------------------------ */
+/* augment_seq(seq, chain_len) of bioseq/blosum.py:63-87 applied in place to the packed residues of
+ * every selected sequence: chain_len times, draw a position and a substitute from the BLOSUM62
+ * row of the residue there (probabilities 2^score / row sum, blosum.py:41-43; anything that is not
+ * an upper-case amino acid uses the X row, :60) until the substitute differs, and write it.  A
+ * sequence is selected with probability augment_frac (always when >= 1), bioseq/loaders.py:71-73.
+ * Randomness is Philox4x32-10 keyed by `seed`, counter (seq_index_base + i, block): the result
+ * depends only on (seed, global sequence index), not on batching -- and not on numpy's generator,
+ * so it matches the reference in distribution, not draw for draw (oracle/bsq_oracle.c restates the
+ * exact procedure).  Empty sequences are left alone. */
+int bsq_augment_blosum62(int device, void *stream, uint8_t *d_bytes, const int64_t *d_offsets, int64_t nseq, int chain_len,
+                         double augment_frac, uint64_t seed, int64_t seq_index_base);
+/* The integer substitution table the kernel samples from: thr[21][19] (rows ARNDCQEGHILKMFPSTWYV + X;
+ * floor(2^32 * cumulative probability)), row_of[256] (residue byte -> row), aa[20].  NULLs skipped. */
+int bsq_blosum62_thresholds(uint32_t *thr, uint8_t *row_of, uint8_t *aa);
+/* Apply bsq_augment_blosum62 to every range the *_host / bsq_stage_host calls of this stager stage,
+ * between the copy and the kernel (sequence i of a call has index seq_index_base + i).
+ * chain_len 0 switches it off. */
+int bsq_stager_set_augment(bsq_stager *s, int chain_len, double augment_frac, uint64_t seed, int64_t seq_index_base);
 
 /* ---- FlatFile: the on-disk packed-sequence store that feeds the path -------------------- */
 /* The reference's FlatFile (src/fxstats.cpp:26-134) stores a FASTA/FASTQ collection as

@@ -273,3 +273,150 @@ int64_t bsqo_decode(const void *tokens, int itemsize, int64_t rows, int64_t cols
     out_offs[rows] = pos;
     return pos;
 }
+
+/* ======================================================================================
+ * Consumers and augmentation.
+ *
+ * (B,C,L) one-hot and the embedding gather have no arithmetic of their own: the tests
+ * derive their expected values from bsqo_onehot / bsqo_tokenize with a numpy transpose /
+ * index, exactly like the reference derives them (bioseq/loaders.py:74-75,
+ * bioseq/__init__.py:171-188).
+ *
+ * BLOSUM62 augmentation: bioseq/blosum.py:36-87.  The reference draws from numpy's PCG64
+ * stream (blosum.py:5-6, :61, :80); a GPU cannot reproduce a sequential generator across
+ * a batch, so the product path uses the counter-based Philox4x32-10 (Salmon et al., SC'11,
+ * "Parallel random numbers: as easy as 1, 2, 3") and this file restates that exact
+ * procedure.  Pins: Philox against the Random123 known-answer vectors; the substitution
+ * probabilities against the reference's own `normrows` (tests/golden/blosum.json,
+ * generated by oracle/make_golden_blosum.py importing bioseq/blosum.py); the procedure's
+ * output distribution against those probabilities (tests/test_oracle.py).
+ * ====================================================================================== */
+void bsqo_philox4x32_10(const uint32_t ctr_in[4], const uint32_t key_in[2], uint32_t out[4])
+{
+    uint32_t c[4] = {ctr_in[0], ctr_in[1], ctr_in[2], ctr_in[3]};
+    uint32_t k[2] = {key_in[0], key_in[1]};
+    for (int round = 0; round < 10; ++round) {
+        if (round > 0) { k[0] += 0x9E3779B9u; k[1] += 0xBB67AE85u; }   /* Weyl key schedule */
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k[0];
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k[1];
+        const uint32_t n3 = (uint32_t)p0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    }
+    memcpy(out, c, sizeof(c));
+}
+
+/* BLOSUM62 (NCBI), the 21 rows ARNDCQEGHILKMFPSTWYV + X over the 20 amino-acid columns:
+ * the block bioseq/blosum.py:36-40 cuts out of the full matrix text (:9-34). */
+static const char BLOSUM_ORDER[] = "ARNDCQEGHILKMFPSTWYV";
+static const signed char BLOSUM62_ROWS[21][20] = {
+    { 4,-1,-2,-2, 0,-1,-1, 0,-2,-1,-1,-1,-1,-2,-1, 1, 0,-3,-2, 0},
+    {-1, 5, 0,-2,-3, 1, 0,-2, 0,-3,-2, 2,-1,-3,-2,-1,-1,-3,-2,-3},
+    {-2, 0, 6, 1,-3, 0, 0, 0, 1,-3,-3, 0,-2,-3,-2, 1, 0,-4,-2,-3},
+    {-2,-2, 1, 6,-3, 0, 2,-1,-1,-3,-4,-1,-3,-3,-1, 0,-1,-4,-3,-3},
+    { 0,-3,-3,-3, 9,-3,-4,-3,-3,-1,-1,-3,-1,-2,-3,-1,-1,-2,-2,-1},
+    {-1, 1, 0, 0,-3, 5, 2,-2, 0,-3,-2, 1, 0,-3,-1, 0,-1,-2,-1,-2},
+    {-1, 0, 0, 2,-4, 2, 5,-2, 0,-3,-3, 1,-2,-3,-1, 0,-1,-3,-2,-2},
+    { 0,-2, 0,-1,-3,-2,-2, 6,-2,-4,-4,-2,-3,-3,-2, 0,-2,-2,-3,-3},
+    {-2, 0, 1,-1,-3, 0, 0,-2, 8,-3,-3,-1,-2,-1,-2,-1,-2,-2, 2,-3},
+    {-1,-3,-3,-3,-1,-3,-3,-4,-3, 4, 2,-3, 1, 0,-3,-2,-1,-3,-1, 3},
+    {-1,-2,-3,-4,-1,-2,-3,-4,-3, 2, 4,-2, 2, 0,-3,-2,-1,-2,-1, 1},
+    {-1, 2, 0,-1,-3, 1, 1,-2,-1,-3,-2, 5,-1,-3,-1, 0,-1,-3,-2,-2},
+    {-1,-1,-2,-3,-1, 0,-2,-3,-2, 1, 2,-1, 5, 0,-2,-1,-1,-1,-1, 1},
+    {-2,-3,-3,-3,-2,-3,-3,-3,-1, 0, 0,-3, 0, 6,-4,-2,-2, 1, 3,-1},
+    {-1,-2,-2,-1,-3,-1,-1,-2,-2,-3,-3,-1,-2,-4, 7,-1,-1,-4,-3,-2},
+    { 1,-1, 1, 0,-1, 0, 0, 0,-1,-2,-2, 0,-1,-2,-1, 4, 1,-3,-2,-2},
+    { 0,-1, 0,-1,-1,-1,-1,-2,-2,-1,-1,-1,-1,-2,-1, 1, 5,-2,-2, 0},
+    {-3,-3,-4,-4,-2,-2,-3,-2,-2,-3,-2,-3,-1, 1,-4,-3,-2,11, 2,-3},
+    {-2,-2,-2,-3,-2,-1,-2,-3, 2,-1,-1,-2,-1, 3,-3,-2,-2, 2, 7,-1},
+    { 0,-3,-3,-3,-1,-2,-2,-3,-3, 3, 1,-2, 1,-1,-2,-2, 0,-3,-1, 4},
+    { 0,-1,-1,-1,-2,-1,-1,-1,-1,-1,-1,-1,-1,-1,-2, 0, 0,-2,-1,-1},
+};
+
+/* normrows of bioseq/blosum.py:41-43: exp2(score) / row sum, as doubles (21 x 20). */
+void bsqo_blosum62_probs(double *out)
+{
+    for (int r = 0; r < 21; ++r) {
+        double odds[20], sum = 0.0;
+        for (int j = 0; j < 20; ++j) {
+            const int s = BLOSUM62_ROWS[r][j];
+            odds[j] = s >= 0 ? (double)(1u << s) : 1.0 / (double)(1u << -s);
+            sum += odds[j];
+        }
+        for (int j = 0; j < 20; ++j) out[r * 20 + j] = odds[j] / sum;
+    }
+}
+
+/* Integer sampling table: thr[r][j] = floor(2^32 * (p[r][0] + ... + p[r][j])), j = 0..18,
+ * computed exactly from the integers 16 * 2^score. */
+void bsqo_blosum62_thresholds(uint32_t *thr)
+{
+    for (int r = 0; r < 21; ++r) {
+        uint64_t w[20], total = 0, run = 0;
+        for (int j = 0; j < 20; ++j) {
+            w[j] = (uint64_t)1 << (BLOSUM62_ROWS[r][j] + 4);
+            total += w[j];
+        }
+        for (int j = 0; j < 19; ++j) {
+            run += w[j];
+            thr[r * 19 + j] = (uint32_t)((run * 4294967296ull) / total);
+        }
+    }
+}
+
+static int blosum_row_of(uint8_t ch)   /* probdict.get(inchar, default_transitions), blosum.py:60 */
+{
+    for (int j = 0; j < 20; ++j)
+        if ((uint8_t)BLOSUM_ORDER[j] == ch) return j;
+    return 20;
+}
+
+/* augment_seq (blosum.py:63-87) over a packed batch, in place.  Sequence i (global index
+ * base + i) is mutated iff augment_frac >= 1 or word 0 of Philox block (g, 0) is below
+ * floor(augment_frac * 2^32) (the `rng.uniform() < augment_frac` gate of loaders.py:71).
+ * Mutation m retries (blosum.py:79-82) with consecutive (position word, substitution word)
+ * pairs taken two per Philox block, blocks numbered from 1 and running on across the
+ * chain; position = (word * len) >> 32.  A chain stops retrying after 4096 pairs. */
+int bsqo_augment(uint8_t *bytes, const int64_t *offs, int64_t nseq, int chain_len, double augment_frac,
+                 uint64_t seed, int64_t base)
+{
+    uint32_t thr[21 * 19];
+    if (chain_len < 0 || !(augment_frac >= 0.0)) return BSQO_ERR_ARG;
+    if (chain_len == 0 || augment_frac == 0.0) return BSQO_OK;
+    bsqo_blosum62_thresholds(thr);
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const uint64_t gate = augment_frac >= 1.0 ? 4294967296ull : (uint64_t)(augment_frac * 4294967296.0);
+    for (int64_t i = 0; i < nseq; ++i) {
+        const uint64_t len = (uint64_t)(offs[i + 1] - offs[i]);
+        if (len == 0) continue;
+        const uint64_t g = (uint64_t)(base + i);
+        uint32_t ctr[4] = {(uint32_t)g, (uint32_t)(g >> 32), 0, 0}, rnd[4];
+        if (gate < 4294967296ull) {
+            bsqo_philox4x32_10(ctr, key, rnd);
+            if (rnd[0] >= gate) continue;
+        }
+        uint8_t *seq = bytes + offs[i];
+        uint32_t block = 0;
+        for (int m = 0; m < chain_len; ++m) {
+            int pairs = 0, mutated = 0;
+            while (!mutated && pairs < 4096) {
+                ctr[2] = ++block;
+                bsqo_philox4x32_10(ctr, key, rnd);
+                for (int h = 0; h < 2 && !mutated; ++h, ++pairs) {
+                    const uint64_t pos = ((uint64_t)rnd[2 * h] * (len > 0xffffffffull ? 0xffffffffull : len)) >> 32;
+                    const uint8_t cur = seq[pos];
+                    const uint32_t *t = thr + 19 * blosum_row_of(cur);
+                    int j = 0;
+                    while (j < 19 && t[j] <= rnd[2 * h + 1]) ++j;
+                    if ((uint8_t)BLOSUM_ORDER[j] != cur) {
+                        seq[pos] = (uint8_t)BLOSUM_ORDER[j];
+                        mutated = 1;
+                    }
+                }
+            }
+        }
+    }
+    return BSQO_OK;
+}

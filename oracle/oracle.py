@@ -51,6 +51,13 @@ def lib():
         L.bsqo_decode.argtypes = [C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                   C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_uint32)]
+        L.bsqo_philox4x32_10.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.bsqo_philox4x32_10.restype = None
+        L.bsqo_blosum62_probs.argtypes = [C.c_void_p]
+        L.bsqo_blosum62_probs.restype = None
+        L.bsqo_blosum62_thresholds.argtypes = [C.c_void_p]
+        L.bsqo_blosum62_thresholds.restype = None
+        L.bsqo_augment.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_double, C.c_uint64, C.c_int64]
         _LIB = L
     return _LIB
 
@@ -160,6 +167,43 @@ class OracleTokenizer:
         raw = chars.tobytes()
         out = [raw[offs[i]:offs[i + 1]].decode("latin-1") for i in range(rows)]
         return out[0] if arr.ndim == 1 else out
+
+
+# ---------------------------------------------------------------------------------------------
+# BLOSUM62 augmentation (bioseq/blosum.py:36-87) -- see the block comment in bsq_oracle.c.
+# ---------------------------------------------------------------------------------------------
+BLOSUM_ORDER = "ARNDCQEGHILKMFPSTWYV"
+
+
+def philox4x32_10(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32).copy()
+    k = np.asarray(key, dtype=np.uint32).copy()
+    out = np.zeros(4, dtype=np.uint32)
+    lib().bsqo_philox4x32_10(c.ctypes.data, k.ctypes.data, out.ctypes.data)
+    return out
+
+
+def blosum62_probs():
+    """normrows of bioseq/blosum.py:43 (21 x 20: ARNDCQEGHILKMFPSTWYV + X rows)."""
+    p = np.zeros((21, 20), dtype=np.float64)
+    lib().bsqo_blosum62_probs(p.ctypes.data)
+    return p
+
+
+def blosum62_thresholds():
+    t = np.zeros((21, 19), dtype=np.uint32)
+    lib().bsqo_blosum62_thresholds(t.ctypes.data)
+    return t
+
+
+def augment(buf, offs, chain_len=1, augment_frac=1.0, seed=0, seq_index_base=0):
+    """augment_seq over a packed batch (returns a mutated copy of ``buf``)."""
+    out = np.ascontiguousarray(buf, dtype=np.uint8).copy()
+    offs = np.ascontiguousarray(offs, dtype=np.int64)
+    rc = lib().bsqo_augment(out.ctypes.data, offs.ctypes.data, len(offs) - 1, chain_len, float(augment_frac),
+                            seed & 0xFFFFFFFFFFFFFFFF, seq_index_base)
+    assert rc == 0, rc
+    return out
 
 
 def load_ref(opt="O3"):

@@ -238,5 +238,8 @@ def test_gpu_loaders(tmp_path):
     assert got.dtype == torch.float32 and got.shape == (4, 23, P)
     assert np.array_equal(got.cpu().numpy(), np.transpose(oh, (1, 2, 0)))
     assert np.array_equal(cnn[5].cpu().numpy(), oh[:, 0, :])
-    with pytest.raises(NotImplementedError):
-        FlatFileDataset(ff, tok, augment=2)
+    assert got.is_contiguous()          # written in (batch, emb, length) layout, not a permuted view
+    aug = FlatFileDataset(ff, tok, augment=2, augment_frac=1.0)      # on-device BLOSUM62 augmentation (test_gpu_consumers.py)
+    a = aug[0:700].cpu().numpy()
+    nd = (a != want).sum(1)
+    assert a.shape == want.shape and nd.max() <= 2 and nd.mean() > 1.8

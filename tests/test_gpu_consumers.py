@@ -1,0 +1,287 @@
+"""GPU parity of the fused consumers and the on-device augmentation, through the
+C ABI and the Python surface, against the oracle: bit-exact.
+
+* (B,C,L) one-hot == the oracle's (P,B,C) one-hot rearranged "length batch emb -> batch emb length"
+  (what bioseq/loaders.py:74-75 does with einops), every element type.
+* embedding gather == weight[oracle tokens] (torch.nn.functional.embedding of the reference's tokens).
+* BLOSUM62 augmentation == oracle/bsq_oracle.c's restatement of the Philox procedure, byte for byte.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import bioseq_b200  # noqa: E402
+from bioseq_b200 import capi, consumers  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from oracle.oracle import OracleTokenizer  # noqa: E402
+from helpers import assert_same_bits, gen, gen_mask, as_list  # noqa: E402
+
+TORCH_DT = {0: torch.int8, 1: torch.int16, 2: torch.int32, 3: torch.int64, 4: torch.float32, 5: torch.float64}
+AA = b"ACDEFGHIKLMNPQRSTVWY"
+MIX = AA + AA.lower() + b"XBZOU*-\x80\xff"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests selected but no CUDA device is visible")
+
+
+def to_dev(a):
+    a = np.ascontiguousarray(a)
+    return torch.from_numpy(a.copy()).cuda() if a.size else torch.empty(0, dtype=torch.from_numpy(a).dtype, device="cuda")
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def split_mask(mask, offs):
+    return [mask[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+
+
+# ------------------------------------------------------------------------------------------ (B,C,L)
+@pytest.mark.parametrize("key,flags", [("DNA", {}), ("DNA", dict(bos=True, padchar=True)), ("PROTEIN", dict(bos=True, eos=True, padchar=True)),
+                                      ("SEB8", dict(eos=True)), ("DAYHOFF", dict(padchar=True)), ("BYTES", dict(bos=True, eos=True, padchar=True))])
+@pytest.mark.parametrize("destchar", ["B", "h", "i", "l", "f", "d"])
+def test_onehot_bcl_abi_all_kinds(key, flags, destchar):
+    if key == "BYTES" and destchar in ("d", "l", "i"):
+        pytest.skip("259 columns x 8 bytes: covered by the narrower kinds")
+    alpha = b"ACGTacgtNn-" if key == "DNA" else (bytes(range(1, 128)) if key == "BYTES" else MIX)
+    buf, offs = gen(11, 37, 0, 90, alpha)
+    ot, tok = OracleTokenizer(key, **flags), capi.tokenizer(key, **flags)
+    for padlen in (92, 96, 128, 611):   # unaligned (scalar kernel), aligned, > one 512 span
+        want = ot.batch_onehot_encode((buf, offs), padlen=padlen, destchar=destchar).transpose(1, 2, 0)
+        kind = capi.kind_of(destchar)
+        out = torch.empty((37, tok.alphabet_size, padlen), dtype=TORCH_DT[kind], device="cuda")
+        capi.onehot_bcl(0, stream(), to_dev(buf), to_dev(offs), None, 37, padlen, tok, kind, out)
+        assert_same_bits(np.ascontiguousarray(want), out.cpu().numpy())
+
+
+def test_onehot_bcl_mask_and_edges():
+    flags = dict(bos=True, eos=True, padchar=True)
+    ot, tok = OracleTokenizer("PROTEIN", **flags), capi.tokenizer("PROTEIN", **flags)
+    # exact fits, empty rows, every source alignment
+    seqs = [b"", b"A", AA * 3, b"", AA[:14], AA * 51 + AA[:2]] + [AA[:k] for k in range(1, 20)]
+    buf, offs = O.pack(seqs)
+    mask = gen_mask(5, buf.size)
+    padlen = 1024
+    want = ot.batch_onehot_encode((buf, offs), padlen=padlen, destchar="f", mask=split_mask(mask, offs)).transpose(1, 2, 0)
+    out = torch.empty((len(seqs), 23, padlen), dtype=torch.float32, device="cuda")
+    capi.onehot_bcl(0, stream(), to_dev(buf), to_dev(offs), to_dev(mask), len(seqs), padlen, tok, capi.F32, out)
+    assert_same_bits(np.ascontiguousarray(want), out.cpu().numpy())
+    # empty batch
+    out0 = bioseq_b200.batch_onehot_encode_bcl(bioseq_b200.Tokenizer("PROTEIN", **flags), [], padlen=16)
+    assert tuple(out0.shape) == (0, 23, 16)
+
+
+def test_onehot_bcl_python_surface_all_input_forms(tmp_path):
+    flags = dict(bos=True, eos=True, padchar=True)
+    ptk = bioseq_b200.pbeos_tokenizers["PROTEIN"]
+    ot = OracleTokenizer("PROTEIN", **flags)
+    buf, offs = gen(21, 300, 1, 250, AA)
+    padlen = 256
+    want = np.ascontiguousarray(ot.batch_onehot_encode((buf, offs), padlen=padlen, destchar="f").transpose(1, 2, 0))
+    # reference recipe on the reference-shaped output: rearrange + float
+    import einops
+    ref_like = einops.rearrange(torch.from_numpy(ot.batch_onehot_encode((buf, offs), padlen=padlen, destchar="B")),
+                                "length batch emb -> batch emb length").float().numpy()
+    assert np.array_equal(ref_like, want)
+    for batch in ((to_dev(buf), to_dev(offs)), (buf, offs), (torch.from_numpy(buf).pin_memory(), torch.from_numpy(offs).pin_memory()),
+                  as_list(buf, offs), [s.decode() for s in as_list(buf, offs)]):
+        out = bioseq_b200.batch_onehot_encode_bcl(ptk, batch, padlen=padlen)
+        assert out.dtype == torch.float32 and out.is_cuda
+        assert_same_bits(want, out.cpu().numpy())
+    # a sub-range of a packed host batch (offsets not rebased)
+    out = bioseq_b200.batch_onehot_encode_bcl(ptk, (buf, offs[100:201]), padlen=padlen)
+    assert_same_bits(want[100:200], out.cpu().numpy())
+    # host mask
+    mask = gen_mask(9, buf.size)
+    wantm = ot.batch_onehot_encode((buf, offs), padlen=padlen, destchar="f", mask=split_mask(mask, offs)).transpose(1, 2, 0)
+    out = bioseq_b200.batch_onehot_encode_bcl(ptk, (buf, offs), padlen=padlen, mask=mask)
+    assert_same_bits(np.ascontiguousarray(wantm), out.cpu().numpy())
+    out = bioseq_b200.batch_onehot_encode_bcl(ptk, (buf, offs[100:201]), padlen=padlen, mask=mask)
+    assert_same_bits(np.ascontiguousarray(wantm[100:200]), out.cpu().numpy())
+    # too long -> the reference's one-hot error type and text (src/tokenize.h:361)
+    with pytest.raises(ValueError, match="seq len \\+ bos \\+ eos > padlen: 252, vs padlen 100"):
+        bioseq_b200.batch_onehot_encode_bcl(ptk, [AA * 12 + AA[:10]], padlen=100)
+    with pytest.raises(ValueError, match="padlen is provded"):
+        bioseq_b200.batch_onehot_encode_bcl(ptk, [b"AC"])
+    # FlatFile range
+    fa = tmp_path / "x.fa"
+    fa.write_bytes(b"".join(b">s%d\n%s\n" % (i, s) for i, s in enumerate(as_list(buf, offs))))
+    ff = bioseq_b200.FlatFile(str(fa), str(tmp_path / "x.ff"))
+    ff = bioseq_b200.FlatFile(str(tmp_path / "x.ff"))
+    out = bioseq_b200.batch_onehot_encode_bcl(ptk, (ff, 10, 60), padlen=padlen)
+    assert_same_bits(want[10:60], out.cpu().numpy())
+    out = bioseq_b200.batch_onehot_encode_bcl(ptk, (ff, 10, 60))       # default padlen = maxseqlen + bos + eos
+    assert out.shape[2] == 252 and np.array_equal(out.cpu().numpy(), want[10:60, :, :252])
+
+
+# ------------------------------------------------------------------------------------------ embedding
+@pytest.mark.parametrize("key,flags", [("PROTEIN", dict(bos=True, eos=True, padchar=True)), ("DNA", {}), ("SEB10", dict(eos=True)),
+                                      ("BYTES", dict(bos=True, eos=True, padchar=True))])
+@pytest.mark.parametrize("batch_first", [True, False])
+def test_embed_abi(key, flags, batch_first):
+    alpha = bytes(range(0, 256)) if key == "BYTES" else MIX
+    buf, offs = gen(31, 77, 0, 200, alpha)
+    ot, tok = OracleTokenizer(key, **flags), capi.tokenizer(key, **flags)
+    g = torch.Generator().manual_seed(3)
+    for padlen, dim, dt in ((202, 4, torch.float32), (256, 64, torch.float32), (333, 24, torch.bfloat16), (208, 1536, torch.float32)):
+        if key == "BYTES" and dim > 64:
+            continue
+        toks = ot.batch_tokenize((buf, offs), padlen=padlen, destchar="i", batch_first=batch_first).astype(np.int64)
+        w = torch.randn(tok.alphabet_size + 2, dim, generator=g).to(dt).cuda()
+        want = torch.nn.functional.embedding(torch.from_numpy(toks).cuda(), w)
+        out = torch.empty_like(want)
+        capi.embed(0, stream(), to_dev(buf), to_dev(offs), 77, padlen, tok, batch_first, w, w.shape[0], dim * w.element_size(), out)
+        torch.cuda.synchronize()
+        assert out.shape == want.shape and torch.equal(out.view(torch.uint8), want.view(torch.uint8)), (padlen, dim, dt)
+
+
+def test_embed_python_surface_and_layers():
+    ptk = bioseq_b200.pbeos_tokenizers["PROTEIN"]
+    ot = OracleTokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    buf, offs = gen(41, 513, 5, 120, AA)
+    emb = bioseq_b200.make_embedding(ptk, 128).cuda()
+    for bf in (True, False):
+        toks = torch.from_numpy(ot.batch_tokenize((buf, offs), padlen=128, destchar="i", batch_first=bf).astype(np.int64)).cuda()
+        with torch.no_grad():
+            want = emb(toks)
+        for batch in ((to_dev(buf), to_dev(offs)), (buf, offs), as_list(buf, offs)):
+            out = bioseq_b200.batch_embed(ptk, batch, emb.weight, padlen=128, batch_first=bf)
+            assert torch.equal(out, want)
+        layer = bioseq_b200.EmbeddingTokenizerLayer(ptk, emb, padlen=128, batch_first=bf)
+        with torch.no_grad():
+            assert torch.equal(layer(as_list(buf, offs)), want)          # fused kernel
+            assert torch.equal(layer(toks), want)                       # tensors pass through the embedding
+        y = layer((buf, offs))                                          # training: graph through nn.Embedding
+        assert y.requires_grad and torch.equal(y.detach(), want)
+        tl = bioseq_b200.TokenizerLayer(ptk, padlen=128, batch_first=bf)
+        t2 = tl(as_list(buf, offs))
+        assert t2.dtype == torch.int32 and torch.equal(t2.long(), toks) and tl(toks) is toks
+    with pytest.raises(ValueError, match="rows"):
+        bioseq_b200.batch_embed(ptk, (buf, offs), torch.zeros(5, 128, device="cuda"), padlen=128)
+    with pytest.raises(ValueError, match="16 bytes"):
+        bioseq_b200.batch_embed(ptk, (buf, offs), torch.zeros(23, 3, device="cuda"), padlen=128)
+    with pytest.raises(RuntimeError, match="seq len \\+ bos \\+ eos > padlen"):
+        bioseq_b200.batch_embed(ptk, (buf, offs), emb.weight, padlen=100)
+
+
+def test_embed_full_size_property():
+    """configs[1]-sized batch: gathering rows of an identity-like table reproduces the token ids."""
+    ptk = bioseq_b200.pbeos_tokenizers["PROTEIN"]
+    buf, offs = gen(102, 16384, 50, 1022, AA)
+    d_b, d_o = to_dev(buf), to_dev(offs)
+    w = torch.arange(23, dtype=torch.float32, device="cuda").repeat_interleave(4).view(23, 4).contiguous()
+    toks = ptk.batch_tokenize_packed(d_b, d_o, padlen=1024, destchar="B", batch_first=True)
+    out = bioseq_b200.batch_embed(ptk, (d_b, d_o), w, padlen=1024, batch_first=True)
+    assert torch.equal(out[..., 0].to(torch.uint8), toks) and torch.equal(out[..., 3].to(torch.uint8), toks)
+    out = bioseq_b200.batch_embed(ptk, (d_b, d_o), w, padlen=1024, batch_first=False)
+    assert torch.equal(out[..., 1].to(torch.uint8).t(), toks)
+    # and the (B,C,L) one-hot of the same batch: argmax over channels is the token, every column sums to 1
+    oh = bioseq_b200.batch_onehot_encode_bcl(ptk, (d_b[:int(offs[2048])], d_o[:2049]), padlen=1024, destchar="B")
+    assert torch.equal(oh.sum(1, dtype=torch.int32), torch.ones((2048, 1024), dtype=torch.int32, device="cuda"))
+    assert torch.equal(oh.argmax(1).to(torch.uint8), toks[:2048])
+
+
+# ------------------------------------------------------------------------------------------ augmentation
+@pytest.mark.parametrize("chain,frac,seed,base", [(1, 1.0, 0, 0), (3, 0.5, 0xDEADBEEF12345678, 1 << 33), (7, 0.25, 42, 999)])
+def test_augment_matches_restatement(chain, frac, seed, base):
+    buf, offs = gen(51, 5000, 0, 80, AA + b"xX*")
+    d_b, d_o = to_dev(buf), to_dev(offs)
+    capi.augment_blosum62(0, stream(), d_b, d_o, 5000, chain, frac, seed, base)
+    want = O.augment(buf, offs, chain, frac, seed, base)
+    assert np.array_equal(d_b.cpu().numpy(), want)
+    assert not np.array_equal(want, buf)
+
+
+def test_augment_pathological_and_surface():
+    # poly-W: the substitute equals W with p = 0.9956 per try; both sides keep retrying the same way
+    buf = np.frombuffer(b"W" * 4000, dtype=np.uint8).copy()
+    offs = np.arange(0, 4001, 40, dtype=np.int64)
+    d_b = to_dev(buf)
+    bioseq_b200.augment_packed(d_b, to_dev(offs), augment=2, augment_frac=1.0, seed=7)
+    want = O.augment(buf, offs, 2, 1.0, 7)
+    assert np.array_equal(d_b.cpu().numpy(), want) and (want != buf).sum() >= 100
+    # augmented tokenisation: staged host batch, device batch and FlatFile-style sub-range agree with
+    # tokenising the oracle-augmented residues; the caller's tensors are left untouched
+    ptk = bioseq_b200.pbeos_tokenizers["PROTEIN"]
+    ot = OracleTokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    buf, offs = gen(61, 3000, 1, 300, AA)
+    kw = dict(augment=2, augment_frac=0.7, seed=2024)
+    want = ot.batch_tokenize((O.augment(buf, offs, 2, 0.7, 2024), offs), padlen=304, destchar="B", batch_first=True)
+    d_b, d_o = to_dev(buf), to_dev(offs)
+    for batch in ((d_b, d_o), (buf, offs), as_list(buf, offs)):
+        out = bioseq_b200.batch_tokenize_augmented(ptk, batch, padlen=304, batch_first=True, **kw)
+        assert_same_bits(want, out.cpu().numpy())
+    assert np.array_equal(d_b.cpu().numpy(), buf)
+    out = bioseq_b200.batch_tokenize_augmented(ptk, (buf, offs[1000:2001]), padlen=304, batch_first=True, seq_index_base=1000, **kw)
+    assert_same_bits(want[1000:2000], out.cpu().numpy())
+    # the staged path with augmentation off is plain tokenisation again (the stager's setting does not stick)
+    plain = ptk.batch_tokenize_packed(buf, offs, padlen=304, destchar="B", batch_first=True)
+    assert_same_bits(ot.batch_tokenize((buf, offs), padlen=304, destchar="B", batch_first=True), plain.cpu().numpy())
+    # one-hot (B,C,L) and embedding of the augmented batch
+    wb = O.augment(buf, offs, 2, 0.7, 2024)
+    oh = bioseq_b200.batch_onehot_encode_bcl(ptk, (buf, offs), padlen=304, destchar="B", **kw)
+    assert_same_bits(np.ascontiguousarray(ot.batch_onehot_encode((wb, offs), padlen=304, destchar="B").transpose(1, 2, 0)), oh.cpu().numpy())
+
+
+def test_augment_statistics_on_gpu():
+    """Distribution check at scale, independent of the restatement: substitutions follow the reference's normrows
+    (tests/golden/blosum.json) conditioned on being different."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "blosum.json")))
+    p = np.array(g["normrows"])[:20]
+    order = g["order"]
+    buf, offs = gen(71, 400000, 20, 40, AA)
+    d_b = to_dev(buf)
+    bioseq_b200.augment_packed(d_b, to_dev(offs), augment=1, augment_frac=1.0, seed=31337)
+    out = d_b.cpu().numpy()
+    diff = np.flatnonzero(out != buf)
+    assert diff.size == 400000
+    lut = np.full(256, -1)
+    for i, c in enumerate(order):
+        lut[ord(c)] = i
+    counts = np.zeros((20, 20))
+    np.add.at(counts, (lut[buf[diff]], lut[out[diff]]), 1)
+    want = p.copy()
+    np.fill_diagonal(want, 0.0)
+    want /= want.sum()
+    got = counts / counts.sum()
+    assert np.abs(got - want).max() < 0.002          # largest cell 0.046; sigma of a cell <= 3.4e-4
+    # positions are uniform along the sequence (relative position of the hit)
+    seq = np.searchsorted(offs, diff, side="right") - 1
+    rel = (diff - offs[seq]) / (offs[seq + 1] - offs[seq])
+    lens = np.diff(offs)
+    assert abs(rel.mean() - (0.5 - 0.5 * np.mean(1.0 / lens))) < 0.002
+
+
+def test_flatfile_dataset_augment_and_cnn(tmp_path):
+    ptk = bioseq_b200.pbeos_tokenizers["PROTEIN"]
+    ot = OracleTokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    buf, offs = gen(81, 500, 10, 120, AA)
+    fa = tmp_path / "d.fa"
+    fa.write_bytes(b"".join(b">s%d\n%s\n" % (i, s) for i, s in enumerate(as_list(buf, offs))))
+    bioseq_b200.FlatFile(str(fa), str(tmp_path / "d.ff"))
+    ff = bioseq_b200.FlatFile(str(tmp_path / "d.ff"))
+    P = ff.maxseqlen + 2
+    from bioseq_b200.loaders import FlatFileDataset, AugmentedSeqDataset
+    ds = FlatFileDataset(ff, ptk, cnn=True)
+    x = ds[20:90]
+    want = ot.batch_onehot_encode((buf, offs), padlen=P, destchar="f").transpose(1, 2, 0)
+    assert x.dtype == torch.float32 and x.is_contiguous() and np.array_equal(x.cpu().numpy(), want[20:90])
+    assert np.array_equal(ds[7].cpu().numpy(), want[7].T)
+    ds = AugmentedSeqDataset(ff, ptk, augment=2, augment_frac=1.0, seed=5)
+    a = ds[0:500]
+    seed1 = 5 | (1 << 32)
+    want = ot.batch_tokenize((O.augment(buf, offs, 2, 1.0, seed1), offs), padlen=P, destchar="B", batch_first=True)
+    assert a.dtype == torch.long and np.array_equal(a.cpu().numpy(), want.astype(np.int64))
+    b = ds[0:500]                       # a new draw: different mutations
+    assert not torch.equal(a, b)
+    one = ds[17]                        # third draw, single item keeps its file index
+    w1 = ot.batch_tokenize((O.augment(buf, offs, 2, 1.0, 5 | (3 << 32)), offs), padlen=P, destchar="B", batch_first=True)
+    assert np.array_equal(one.cpu().numpy(), w1[17].astype(np.int64))
