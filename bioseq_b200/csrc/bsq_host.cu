@@ -8,8 +8,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -32,6 +37,77 @@ void count_launch(int n) { g_launches += n; }
 }  // namespace bsq
 
 using bsq::fail;
+
+// ---------------------------------------------------------------------------------------
+// worker pool: persistent host threads for the gather (items -> pinned pack) and scatter
+// (pinned ring -> Python string bodies) loops.  One job at a time; the submitting thread keeps
+// running (it issues the CUDA copies and launches) and joins with wait().
+// ---------------------------------------------------------------------------------------
+namespace {
+
+class Pool {
+public:
+    static Pool &get() {
+        static Pool *p = new Pool();  // leaked: worker threads must not be torn down under a running job at exit
+        return *p;
+    }
+    // run fn(t) for t in [0, nt) on pool threads; returns at once.  Pair with wait().
+    void start(int nt, std::function<void(int)> fn) {
+        job_mu_.lock();  // released by wait()
+        std::unique_lock<std::mutex> lk(mu_);
+        while (static_cast<int>(threads_.size()) < nt) {
+            const int id = static_cast<int>(threads_.size());
+            threads_.emplace_back([this, id] { loop(id); });
+            threads_.back().detach();
+        }
+        fn_ = std::move(fn);
+        nt_ = nt;
+        pending_ = nt;
+        ++generation_;
+        lk.unlock();
+        cv_.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+        fn_ = nullptr;
+        lk.unlock();
+        job_mu_.unlock();
+    }
+
+private:
+    void loop(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            std::function<void(int)> fn;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (id >= nt_) continue;
+                fn = fn_;
+            }
+            fn(id);
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_cv_.notify_all();
+        }
+    }
+    std::mutex job_mu_, mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> threads_;
+    std::function<void(int)> fn_;
+    int nt_ = 0, pending_ = 0;
+    uint64_t generation_ = 0;
+};
+
+inline void spin_until(const std::function<bool()> &ready) {
+    for (int i = 0; !ready(); ++i) {
+        if (i < 64) std::this_thread::yield();
+        else std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+}
+
+}  // namespace
 
 // ---------------------------------------------------------------------------------------
 // pack layer
@@ -181,6 +257,7 @@ namespace {
 constexpr int kRingSlots = 3;
 constexpr size_t kChunkBytes = size_t(4) << 20;  // residues per pipeline stage
 constexpr int64_t kSeqAlign = 128;               // chunk boundaries: whole tiles / 16-byte aligned rows
+constexpr size_t kFetchBytes = size_t(8) << 20;  // decoded characters per device -> host stage
 }  // namespace
 
 struct bsq_stager {
@@ -196,6 +273,9 @@ struct bsq_stager {
     bool ring_used[kRingSlots] = {false, false, false};
     int ring_next = 0;
     std::vector<cudaEvent_t> events;  // one per chunk in flight
+    // device -> host ring of bsq_fetch_rows
+    uint8_t *fetch_ring[kRingSlots] = {nullptr, nullptr, nullptr};
+    cudaEvent_t fetch_ev[kRingSlots] = {nullptr, nullptr, nullptr};
     // BLOSUM62 augmentation applied to every staged range before it is tokenised (chain_len 0 = off)
     int aug_chain = 0;
     double aug_frac = 0.0;
@@ -252,6 +332,74 @@ int stage_copy(bsq_stager *s, void *dst, const void *src, size_t n, bool src_pin
     return BSQ_OK;
 }
 
+struct RunArgs {
+    cudaStream_t st;
+    const uint8_t *h_bytes;  // indexed by the offsets' own values (h_bytes + offs[i] = sequence i)
+    const int64_t *h_offs;
+    const uint8_t *h_mask;
+    int64_t nseq, padlen, base;
+    const bsq_tokenizer *tok;
+    int onehot, batch_first, kind;
+    void *d_out;
+    bool pin_b, pin_m;
+};
+
+// Reserves the device-side staging buffers of a batch and copies its offsets.
+int stage_begin(bsq_stager *s, const RunArgs &a) {
+    const int64_t nbytes = a.h_offs[a.nseq] - a.base;
+    if (s->busy) BSQ_CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->done, 0));  // staging buffers still in use
+    if (int rc = dev_reserve(reinterpret_cast<void **>(&s->d_bytes), &s->cap_bytes, static_cast<size_t>(nbytes) + 32)) return rc;
+    if (int rc = dev_reserve(reinterpret_cast<void **>(&s->d_offs), &s->cap_offs, sizeof(int64_t) * (a.nseq + 1))) return rc;
+    if (a.h_mask != nullptr)
+        if (int rc = dev_reserve(reinterpret_cast<void **>(&s->d_mask), &s->cap_mask, static_cast<size_t>(nbytes) + 32)) return rc;
+    // offsets first (small); the kernels index d_bytes with (offset - base) via a shifted pointer
+    return stage_copy(s, s->d_offs, a.h_offs, sizeof(int64_t) * (a.nseq + 1), is_pinned(a.h_offs));
+}
+
+// End of the staged range that starts at sequence i0: whole 128-sequence groups holding ~kChunkBytes of residues.
+int64_t range_end(const int64_t *h_offs, int64_t nseq, int64_t i0) {
+    const int64_t want = h_offs[i0] + static_cast<int64_t>(kChunkBytes);
+    int64_t i1 = std::upper_bound(h_offs + i0, h_offs + nseq + 1, want) - h_offs - 1;
+    i1 = std::max(i1, i0 + 1);
+    return std::min(nseq, (i1 + kSeqAlign - 1) / kSeqAlign * kSeqAlign);
+}
+
+// Copies the residues (and mask) of sequences [i0, i1) and launches their kernel behind the copy.
+int stage_range(bsq_stager *s, const RunArgs &a, int64_t i0, int64_t i1, size_t nchunk) {
+    const int64_t base = a.base;
+    const int64_t b0 = a.h_offs[i0] - base, b1 = a.h_offs[i1] - base;
+    if (int rc = stage_copy(s, s->d_bytes + b0, a.h_bytes + base + b0, static_cast<size_t>(b1 - b0), a.pin_b)) return rc;
+    if (a.h_mask)
+        if (int rc = stage_copy(s, s->d_mask + b0, a.h_mask + base + b0, static_cast<size_t>(b1 - b0), a.pin_m)) return rc;
+    while (nchunk >= s->events.size()) {
+        cudaEvent_t e;
+        BSQ_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->events.push_back(e);
+    }
+    BSQ_CUDA_TRY(cudaEventRecord(s->events[nchunk], s->copy_stream));
+    BSQ_CUDA_TRY(cudaStreamWaitEvent(a.st, s->events[nchunk], 0));
+    const uint8_t *d_bytes_shifted = s->d_bytes - base;
+    const uint8_t *d_mask_shifted = a.h_mask ? s->d_mask - base : nullptr;
+    const size_t esize = bsq_kind_size(a.kind);
+    const int64_t ncols = a.onehot ? a.tok->alphabet_size : 1;
+    if (s->aug_chain > 0)
+        if (int rc = bsq_augment_blosum62(s->device, a.st, s->d_bytes - base, s->d_offs + i0, i1 - i0, s->aug_chain, s->aug_frac,
+                                          s->aug_seed, s->aug_base + i0))
+            return rc;
+    if (a.onehot)
+        return bsq::launch_onehot(a.st, d_bytes_shifted, s->d_offs + i0, d_mask_shifted, i1 - i0, a.nseq, a.padlen, *a.tok, a.kind,
+                                  static_cast<uint8_t *>(a.d_out) + static_cast<size_t>(i0) * ncols * esize);
+    const size_t off = a.batch_first ? static_cast<size_t>(i0) * a.padlen * esize : static_cast<size_t>(i0) * esize;
+    return bsq::launch_tokenize(a.st, d_bytes_shifted, s->d_offs + i0, i1 - i0, a.nseq, a.padlen, *a.tok, a.batch_first, a.kind,
+                                static_cast<uint8_t *>(a.d_out) + off, /*first_off=*/a.h_offs[i0]);
+}
+
+int stage_end(bsq_stager *s, const RunArgs &a) {
+    BSQ_CUDA_TRY(cudaEventRecord(s->done, a.st));
+    s->busy = true;
+    return BSQ_OK;
+}
+
 int staged_run(bsq_stager *s, cudaStream_t st, const uint8_t *h_bytes, const int64_t *h_offs, const uint8_t *h_mask,
                int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int onehot, int batch_first, int kind, void *d_out) {
     if (s == nullptr) return fail(BSQ_ERR_ARG, "null stager");
@@ -262,61 +410,181 @@ int staged_run(bsq_stager *s, cudaStream_t st, const uint8_t *h_bytes, const int
         return rc;
     }
     if (nseq == 0) return BSQ_OK;
-    const int64_t base = h_offs[0], nbytes = h_offs[nseq] - base;
-    if (nbytes > 0 && h_bytes == nullptr) return fail(BSQ_ERR_ARG, "null residue buffer");
-    if (s->busy) BSQ_CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->done, 0));  // staging buffers still in use
-    if (int rc = dev_reserve(reinterpret_cast<void **>(&s->d_bytes), &s->cap_bytes, static_cast<size_t>(nbytes) + 32)) return rc;
-    if (int rc = dev_reserve(reinterpret_cast<void **>(&s->d_offs), &s->cap_offs, sizeof(int64_t) * (nseq + 1))) return rc;
-    if (h_mask != nullptr)
-        if (int rc = dev_reserve(reinterpret_cast<void **>(&s->d_mask), &s->cap_mask, static_cast<size_t>(nbytes) + 32)) return rc;
-
-    const bool pin_b = is_pinned(h_bytes), pin_o = is_pinned(h_offs), pin_m = h_mask && is_pinned(h_mask);
-    // offsets first (small); the kernels index d_bytes with (offset - base) via a shifted pointer
-    if (int rc = stage_copy(s, s->d_offs, h_offs, sizeof(int64_t) * (nseq + 1), pin_o)) return rc;
-    const uint8_t *d_bytes_shifted = s->d_bytes - base;
-    const uint8_t *d_mask_shifted = h_mask ? s->d_mask - base : nullptr;
-    const size_t esize = bsq_kind_size(kind);
-    const int64_t ncols = onehot ? tok->alphabet_size : 1;
-
+    RunArgs a{st, h_bytes, h_offs, h_mask, nseq, padlen, h_offs[0], tok, onehot, batch_first, kind, d_out, false, false};
+    if (h_offs[nseq] - a.base > 0 && h_bytes == nullptr) return fail(BSQ_ERR_ARG, "null residue buffer");
+    a.pin_b = is_pinned(h_bytes);
+    a.pin_m = h_mask && is_pinned(h_mask);
+    if (int rc = stage_begin(s, a)) return rc;
     size_t nchunk = 0;
     for (int64_t i0 = 0; i0 < nseq;) {
-        // grow the range in whole 128-sequence groups until it holds ~kChunkBytes of residues
-        const int64_t want = h_offs[i0] + static_cast<int64_t>(kChunkBytes);
-        int64_t i1 = std::upper_bound(h_offs + i0, h_offs + nseq + 1, want) - h_offs - 1;
-        i1 = std::max(i1, i0 + 1);
-        i1 = std::min(nseq, (i1 + kSeqAlign - 1) / kSeqAlign * kSeqAlign);
-        const int64_t b0 = h_offs[i0] - base, b1 = h_offs[i1] - base;
-        if (int rc = stage_copy(s, s->d_bytes + b0, h_bytes + base + b0, static_cast<size_t>(b1 - b0), pin_b)) return rc;
-        if (h_mask)
-            if (int rc = stage_copy(s, s->d_mask + b0, h_mask + base + b0, static_cast<size_t>(b1 - b0), pin_m)) return rc;
-        if (nchunk == s->events.size()) {
-            cudaEvent_t e;
-            BSQ_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-            s->events.push_back(e);
-        }
-        BSQ_CUDA_TRY(cudaEventRecord(s->events[nchunk], s->copy_stream));
-        BSQ_CUDA_TRY(cudaStreamWaitEvent(st, s->events[nchunk], 0));
-        ++nchunk;
-        int rc;
-        if (s->aug_chain > 0) {
-            rc = bsq_augment_blosum62(s->device, st, s->d_bytes - base, s->d_offs + i0, i1 - i0, s->aug_chain, s->aug_frac,
-                                      s->aug_seed, s->aug_base + i0);
-            if (rc) return rc;
-        }
-        if (onehot) {
-            rc = bsq::launch_onehot(st, d_bytes_shifted, s->d_offs + i0, d_mask_shifted, i1 - i0, nseq, padlen, *tok, kind,
-                                    static_cast<uint8_t *>(d_out) + static_cast<size_t>(i0) * ncols * esize);
-        } else {
-            const size_t off = batch_first ? static_cast<size_t>(i0) * padlen * esize : static_cast<size_t>(i0) * esize;
-            rc = bsq::launch_tokenize(st, d_bytes_shifted, s->d_offs + i0, i1 - i0, nseq, padlen, *tok, batch_first, kind,
-                                      static_cast<uint8_t *>(d_out) + off, /*first_off=*/h_offs[i0]);
-        }
-        if (rc) return rc;
+        const int64_t i1 = range_end(h_offs, nseq, i0);
+        if (int rc = stage_range(s, a, i0, i1, nchunk++)) return rc;
         i0 = i1;
     }
-    BSQ_CUDA_TRY(cudaEventRecord(s->done, st));
-    s->busy = true;
-    return BSQ_OK;
+    return stage_end(s, a);
+}
+
+// Items (borrowed host pointers, the reference's unpacked batch: src/tokenize.h:389-419) -> pinned pack ->
+// device -> kernels, range by range: while the DMA engine moves range k the host threads are already
+// gathering range k+1, so that the call costs max(gather, copy) rather than their sum.
+int items_run(bsq_stager *s, bsq_pack *p, cudaStream_t st, const void *const *ptrs, const int64_t *lens, int64_t n,
+              int64_t padlen, const bsq_tokenizer *tok, int onehot, int batch_first, int kind, void *d_out, int nthreads) {
+    if (s == nullptr || p == nullptr) return fail(BSQ_ERR_ARG, "null stager / pack");
+    if (!p->pinned) return fail(BSQ_ERR_ARG, "bsq_*_items needs a pinned pack");
+    if (n < 0 || (n > 0 && (ptrs == nullptr || lens == nullptr))) return fail(BSQ_ERR_ARG, "bad pack arguments");
+    if (int rc = bsq::check_launch_args(s->device, n, padlen, tok, kind, d_out)) return rc;
+    int64_t total = 0, maxlen = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        if (lens[i] < 0) return fail(BSQ_ERR_ARG, "negative sequence length");
+        total += lens[i];
+        maxlen = std::max(maxlen, lens[i]);
+    }
+    const int64_t extra = (tok->bos_id >= 0) + (tok->eos_id >= 0);
+    if (maxlen + extra > padlen)  // src/tokenize.h:456-459
+        return fail(BSQ_ERR_TOO_LONG, "seq len + bos + eos > padlen: " + std::to_string(maxlen + extra) + ", vs padlen " +
+                                          std::to_string(padlen));
+    // the pinned pack of the previous call may still be feeding the DMA engine
+    BSQ_CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+    if (int rc = pack_reserve(p, total, n)) return rc;
+    int64_t acc = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        p->offs[i] = acc;
+        acc += lens[i];
+    }
+    p->offs[n] = acc;
+    p->nseq = n;
+    p->nbytes = total;
+    p->maxlen = maxlen;
+    std::memset(p->bytes + total, 0, 32);
+    if (n == 0) return BSQ_OK;
+
+    RunArgs a{st, p->bytes, p->offs, nullptr, n, padlen, 0, tok, onehot, batch_first, kind, d_out, true, false};
+    if (int rc = stage_begin(s, a)) return rc;
+    std::vector<int64_t> bounds{0};
+    while (bounds.back() < n) bounds.push_back(range_end(p->offs, n, bounds.back()));
+    const size_t nranges = bounds.size() - 1;
+
+    auto copy_seqs = [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i)
+            if (lens[i] > 0) std::memcpy(p->bytes + p->offs[i], ptrs[i], static_cast<size_t>(lens[i]));
+    };
+    int nt = std::max(1, nthreads);
+    nt = static_cast<int>(std::min<int64_t>(nt, std::max<int64_t>(1, total >> 19)));  // >= 512 KiB per thread
+    nt = std::min(nt, 64);
+    if (nt <= 1) {
+        for (size_t k = 0; k < nranges; ++k) {
+            copy_seqs(bounds[k], bounds[k + 1]);
+            if (int rc = stage_range(s, a, bounds[k], bounds[k + 1], k)) return rc;
+        }
+        return stage_end(s, a);
+    }
+    // every worker copies its byte-balanced share of range 0, then of range 1, ...: ranges complete in order
+    std::vector<std::atomic<int>> done(nranges);
+    for (auto &d : done) d.store(0, std::memory_order_relaxed);
+    Pool &pool = Pool::get();
+    pool.start(nt, [&, nt](int t) {
+        for (size_t k = 0; k < nranges; ++k) {
+            const int64_t i0 = bounds[k], i1 = bounds[k + 1];
+            const int64_t b0 = p->offs[i0], nb = p->offs[i1] - b0;
+            auto cut = [&](int u) {  // first sequence of share u
+                if (u <= 0) return i0;
+                if (u >= nt) return i1;
+                return static_cast<int64_t>(std::lower_bound(p->offs + i0, p->offs + i1, b0 + nb * u / nt) - p->offs);
+            };
+            copy_seqs(cut(t), cut(t + 1));
+            done[k].fetch_add(1, std::memory_order_release);
+        }
+    });
+    int rc = BSQ_OK;
+    for (size_t k = 0; k < nranges && rc == BSQ_OK; ++k) {
+        spin_until([&] { return done[k].load(std::memory_order_acquire) == nt; });
+        rc = stage_range(s, a, bounds[k], bounds[k + 1], k);
+    }
+    pool.wait();  // also on error: the workers borrow this frame
+    if (rc) return rc;
+    return stage_end(s, a);
+}
+
+// Rows of a device byte buffer -> separate host destinations (the bodies of the Python strings that
+// decode_tokens returns): device -> pinned ring in ~8 MiB stages on `st`, host threads scatter stage k
+// while stage k+1 is in flight.  Returns when every row has arrived.
+int fetch_rows(bsq_stager *s, cudaStream_t st, const uint8_t *d_chars, const int64_t *h_offs, int64_t rows, void *const *dst,
+               int nthreads) {
+    if (s == nullptr) return fail(BSQ_ERR_ARG, "null stager");
+    if (rows < 0 || (rows > 0 && (h_offs == nullptr || dst == nullptr))) return fail(BSQ_ERR_ARG, "bad fetch arguments");
+    if (rows == 0) return BSQ_OK;
+    BSQ_CUDA_TRY(cudaSetDevice(s->device));
+    const int64_t base = h_offs[0], total = h_offs[rows] - base;
+    if (total < 0) return fail(BSQ_ERR_ARG, "offsets must be non-decreasing");
+    if (total == 0) return BSQ_OK;
+    if (d_chars == nullptr) return fail(BSQ_ERR_ARG, "null character buffer");
+    for (int k = 0; k < kRingSlots; ++k)
+        if (s->fetch_ring[k] == nullptr) {
+            BSQ_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&s->fetch_ring[k]), kFetchBytes, cudaHostAllocDefault));
+            BSQ_CUDA_TRY(cudaEventCreateWithFlags(&s->fetch_ev[k], cudaEventDisableTiming));
+        }
+    const int64_t S = static_cast<int64_t>(kFetchBytes);
+    const int64_t nstages = (total + S - 1) / S;
+    int nt = std::max(1, std::min(nthreads, 64));
+    nt = static_cast<int>(std::min<int64_t>(nt, std::max<int64_t>(1, total >> 19)));
+
+    // bytes [lo, hi) of the character stream (relative to base), now in `src` (src[0] = byte stage_lo), go to their rows
+    auto scatter = [&](const uint8_t *src, int64_t stage_lo, int64_t lo, int64_t hi) {
+        if (lo >= hi) return;
+        int64_t r = std::upper_bound(h_offs, h_offs + rows + 1, base + lo) - h_offs - 1;  // row holding byte lo
+        for (; r < rows && h_offs[r] - base < hi; ++r) {
+            const int64_t r0 = h_offs[r] - base, r1 = h_offs[r + 1] - base;
+            const int64_t c0 = std::max(r0, lo), c1 = std::min(r1, hi);
+            if (c1 > c0) std::memcpy(static_cast<uint8_t *>(dst[r]) + (c0 - r0), src + (c0 - stage_lo), static_cast<size_t>(c1 - c0));
+        }
+    };
+    auto issue = [&](int64_t k) -> int {
+        const int64_t lo = k * S, m = std::min(S, total - lo);
+        BSQ_CUDA_TRY(cudaMemcpyAsync(s->fetch_ring[k % kRingSlots], d_chars + base + lo, static_cast<size_t>(m), cudaMemcpyDeviceToHost, st));
+        BSQ_CUDA_TRY(cudaEventRecord(s->fetch_ev[k % kRingSlots], st));
+        return BSQ_OK;
+    };
+    if (nt <= 1) {
+        for (int64_t k = 0; k < std::min<int64_t>(nstages, kRingSlots); ++k)
+            if (int rc = issue(k)) return rc;
+        for (int64_t k = 0; k < nstages; ++k) {
+            BSQ_CUDA_TRY(cudaEventSynchronize(s->fetch_ev[k % kRingSlots]));
+            scatter(s->fetch_ring[k % kRingSlots], k * S, k * S, std::min(total, (k + 1) * S));
+            if (k + kRingSlots < nstages)
+                if (int rc = issue(k + kRingSlots)) return rc;
+        }
+        return BSQ_OK;
+    }
+    std::atomic<int64_t> ready{0};
+    std::atomic<bool> abort{false};
+    std::vector<std::atomic<int>> done(static_cast<size_t>(nstages));
+    for (auto &d : done) d.store(0, std::memory_order_relaxed);
+    Pool &pool = Pool::get();
+    pool.start(nt, [&, nt](int t) {
+        for (int64_t k = 0; k < nstages; ++k) {
+            spin_until([&] { return ready.load(std::memory_order_acquire) > k || abort.load(std::memory_order_relaxed); });
+            if (abort.load(std::memory_order_relaxed)) return;
+            const int64_t lo = k * S, m = std::min(S, total - lo);
+            scatter(s->fetch_ring[k % kRingSlots], lo, lo + m * t / nt, lo + m * (t + 1) / nt);
+            done[static_cast<size_t>(k)].fetch_add(1, std::memory_order_release);
+        }
+    });
+    int rc = BSQ_OK;
+    for (int64_t k = 0; k < std::min<int64_t>(nstages, kRingSlots) && rc == BSQ_OK; ++k) rc = issue(k);
+    for (int64_t k = 0; k < nstages && rc == BSQ_OK; ++k) {
+        if (cudaEventSynchronize(s->fetch_ev[k % kRingSlots]) != cudaSuccess) {
+            rc = fail(BSQ_ERR_CUDA, "bsq_fetch_rows: device -> host copy failed");
+            break;
+        }
+        ready.store(k + 1, std::memory_order_release);
+        if (k + kRingSlots < nstages) {  // slot k is needed again: wait until it has been scattered
+            spin_until([&] { return done[static_cast<size_t>(k)].load(std::memory_order_acquire) == nt; });
+            rc = issue(k + kRingSlots);
+        }
+    }
+    if (rc) abort.store(true);
+    pool.wait();
+    return rc;
 }
 
 }  // namespace
@@ -350,6 +618,10 @@ void bsq_stager_destroy(bsq_stager *s) {
         if (s->ring_free[k]) cudaEventDestroy(s->ring_free[k]);
     }
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    for (int k = 0; k < kRingSlots; ++k) {
+        if (s->fetch_ring[k]) cudaFreeHost(s->fetch_ring[k]);
+        if (s->fetch_ev[k]) cudaEventDestroy(s->fetch_ev[k]);
+    }
     if (s->done) cudaEventDestroy(s->done);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
@@ -421,6 +693,21 @@ int bsq_tokenize_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const
 int bsq_onehot_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const int64_t *h_offsets, const uint8_t *h_mask,
                     int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out) {
     return staged_run(s, static_cast<cudaStream_t>(stream), h_bytes, h_offsets, h_mask, nseq, padlen, tok, 1, 0, kind, d_out);
+}
+
+int bsq_tokenize_items(bsq_stager *s, bsq_pack *p, void *stream, const void *const *ptrs, const int64_t *lens, int64_t n,
+                       int64_t padlen, const bsq_tokenizer *tok, int batch_first, int kind, void *d_out, int nthreads) {
+    return items_run(s, p, static_cast<cudaStream_t>(stream), ptrs, lens, n, padlen, tok, 0, batch_first, kind, d_out, nthreads);
+}
+
+int bsq_onehot_items(bsq_stager *s, bsq_pack *p, void *stream, const void *const *ptrs, const int64_t *lens, int64_t n,
+                     int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out, int nthreads) {
+    return items_run(s, p, static_cast<cudaStream_t>(stream), ptrs, lens, n, padlen, tok, 1, 0, kind, d_out, nthreads);
+}
+
+int bsq_fetch_rows(bsq_stager *s, void *stream, const uint8_t *d_chars, const int64_t *h_offsets, int64_t rows, void *const *dst,
+                   int nthreads) {
+    return fetch_rows(s, static_cast<cudaStream_t>(stream), d_chars, h_offsets, rows, dst, nthreads);
 }
 
 }  // extern "C"

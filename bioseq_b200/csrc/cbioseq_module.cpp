@@ -17,6 +17,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -537,20 +538,32 @@ public:
         py::object d_chars = new_tensor({total}, t.uint8, dev);
         check(bsq_decode_chars(dev, st, data_ptr(tens), itemsize, rows, cols, rs, cs, &tok_,
                                static_cast<const int64_t *>(data_ptr(d_offs)), static_cast<uint8_t *>(data_ptr(d_chars))));
-        py::array_t<uint8_t> h_chars = d_chars.attr("cpu")().attr("numpy")();
         py::array_t<int64_t> h_offs = d_offs.attr("cpu")().attr("numpy")();
-        const char *c = reinterpret_cast<const char *>(h_chars.data());
         const int64_t *o = h_offs.data();
-        auto make_str = [&](int64_t r) {
-            // every decoded character is < 0x80 (ids of bytes >= 0x80 are rejected), so ASCII
+        // The string objects are created first (sizes are known from the offsets); their bodies are then
+        // filled straight from the device -> host ring by pool threads, without the GIL.  Every decoded
+        // character is < 0x80 (ids of bytes >= 0x80 are rejected), so the strings are ASCII.
+        py::list out(static_cast<size_t>(rows));
+        std::vector<void *> dst(static_cast<size_t>(rows));
+        for (int64_t r = 0; r < rows; ++r) {
             PyObject *s = PyUnicode_New(o[r + 1] - o[r], 127);
             if (s == nullptr) throw py::error_already_set();
-            std::memcpy(PyUnicode_1BYTE_DATA(s), c + o[r], static_cast<size_t>(o[r + 1] - o[r]));
-            return py::reinterpret_steal<py::object>(s);
-        };
-        if (nd == 1) return make_str(0);
-        py::list out(static_cast<size_t>(rows));
-        for (int64_t r = 0; r < rows; ++r) PyList_SET_ITEM(out.ptr(), r, make_str(r).release().ptr());
+            PyList_SET_ITEM(out.ptr(), r, s);
+            dst[static_cast<size_t>(r)] = PyUnicode_1BYTE_DATA(s);
+        }
+        {
+            DeviceCtx &ctx = device_ctx(dev);
+            const uint8_t *chars_ptr = total > 0 ? static_cast<const uint8_t *>(data_ptr(d_chars)) : nullptr;
+            const int nt = static_cast<int>(std::min<py::ssize_t>(get_num_threads(), 16));
+            int rc;
+            {
+                py::gil_scoped_release nogil;
+                std::lock_guard<std::mutex> g(ctx.mu);
+                rc = bsq_fetch_rows(ctx.stager, st, chars_ptr, o, rows, dst.data(), nt);
+            }
+            check(rc);
+        }
+        if (nd == 1) return py::reinterpret_borrow<py::object>(PyList_GET_ITEM(out.ptr(), 0));
         return out;
     }
 
@@ -580,17 +593,20 @@ private:
         {
             py::gil_scoped_release nogil;
             std::lock_guard<std::mutex> g(ctx.mu);
-            rc = bsq_stager_sync_copies(ctx.stager);  // the pinned pack buffer may still be in flight
-            if (rc == BSQ_OK) rc = bsq_pack_gather(ctx.pack, ptrs, lens, n, nthreads > 0 ? nthreads : 1);
-            if (rc == BSQ_OK) {
-                if (onehot)
+            const int nt = nthreads > 0 ? nthreads : 1;
+            if (mask == nullptr) {
+                // gather -> copy -> kernel pipelined range by range (the pinned pack of the previous call is
+                // waited for inside)
+                if (onehot) rc = bsq_onehot_items(ctx.stager, ctx.pack, st, ptrs, lens, n, padlen, &tok_, kind, optr, nt);
+                else rc = bsq_tokenize_items(ctx.stager, ctx.pack, st, ptrs, lens, n, padlen, &tok_, batch_first, kind, optr, nt);
+            } else {
+                rc = bsq_stager_sync_copies(ctx.stager);  // the pinned pack buffer may still be in flight
+                if (rc == BSQ_OK) rc = bsq_pack_gather(ctx.pack, ptrs, lens, n, nt);
+                if (rc == BSQ_OK)
                     rc = bsq_onehot_host(ctx.stager, st, bsq_pack_bytes(ctx.pack), bsq_pack_offsets(ctx.pack), mask, n, padlen,
                                          &tok_, kind, optr);
-                else
-                    rc = bsq_tokenize_host(ctx.stager, st, bsq_pack_bytes(ctx.pack), bsq_pack_offsets(ctx.pack), n, padlen, &tok_,
-                                           batch_first, kind, optr);
+                if (rc == BSQ_OK) rc = bsq_stager_sync_copies(ctx.stager);  // mask is a local buffer
             }
-            if (rc == BSQ_OK && mask != nullptr) rc = bsq_stager_sync_copies(ctx.stager);  // mask is a local buffer
         }
         check(rc, onehot);
         return out;

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BSQ_ABI_VERSION 2
+#define BSQ_ABI_VERSION 3
 
 /* ---- status codes ---------------------------------------------------------------- */
 #define BSQ_OK 0
@@ -178,6 +178,27 @@ int bsq_tokenize_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const
 int bsq_onehot_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const int64_t *h_offsets,
                     const uint8_t *h_mask, int64_t nseq, int64_t padlen, const bsq_tokenizer *tok,
                     int kind, void *d_out);
+
+/* The reference's own calling convention: n borrowed host pointers + lengths (what its unpack loop collects
+ * from the Python str/bytes/bytearray items, src/tokenize.h:389-419 / :289-322).  Gather into the pinned pack `p`
+ * (created with pinned = 1), host->device copy and kernel run range by range (~4 MiB of residues each):
+ * `nthreads` pool threads gather range k+1 while the DMA engine moves range k, so that the call costs
+ * max(gather, copy) instead of their sum.  Lengths are checked before anything is copied.  Returns once all
+ * work is enqueued; ptrs/lens are not referenced after the return.  `p` afterwards describes the batch
+ * (bsq_pack_bytes/offsets) and must stay untouched until bsq_stager_sync_copies(s) or the next call on `s`. */
+int bsq_tokenize_items(bsq_stager *s, bsq_pack *p, void *stream, const void *const *ptrs, const int64_t *lens,
+                       int64_t n, int64_t padlen, const bsq_tokenizer *tok, int batch_first, int kind,
+                       void *d_out, int nthreads);
+int bsq_onehot_items(bsq_stager *s, bsq_pack *p, void *stream, const void *const *ptrs, const int64_t *lens,
+                     int64_t n, int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out, int nthreads);
+
+/* Second half of decode_tokens (src/tokenize.h:131-179 builds one std::string per row): row r of the
+ * decoded characters, d_chars[h_offsets[r] .. h_offsets[r+1]), is delivered to host address dst[r] (the body
+ * of the string object the caller created for it).  Device->host copies go through a pinned ring in 8 MiB
+ * stages on `stream`; `nthreads` pool threads scatter stage k into the rows while stage k+1 is in flight.
+ * h_offsets (rows+1 entries) is on the host.  Blocks until every row has arrived. */
+int bsq_fetch_rows(bsq_stager *s, void *stream, const uint8_t *d_chars, const int64_t *h_offsets, int64_t rows,
+                   void *const *dst, int nthreads);
 
 /* Stage a packed host batch into the stager's device buffers without running a kernel, for the
  * device entry points that have no *_host twin (bsq_embed, bsq_onehot_bcl, ...).  `stream` is made

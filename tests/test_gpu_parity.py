@@ -463,3 +463,47 @@ def test_sharded_equals_single_device():
         assert torch.equal(torch.cat([p[0] for p in parts], dim=0), full_bf)
         parts = [tokenize_sharded(t, buf, offs, 608, world, r, batch_first=False)[0] for r in range(world)]
         assert torch.equal(torch.cat(parts, dim=1), full_sf)
+
+
+@pytest.mark.parametrize("nthreads", [1, 3, 16])
+def test_list_api_pipelined_gather(nthreads):
+    # the reference's calling convention (a Python list of bytes) on a batch of several staged ranges:
+    # gather -> copy -> kernel pipelined range by range (bsq_tokenize_items / bsq_onehot_items), every
+    # thread count, both layouts, back-to-back calls reusing the pinned pack, one-hot without a mask
+    buf, offs = gen(300 + nthreads, 30_011, 0, 1000, MIX)
+    assert buf.size > 12 * (1 << 20)
+    seqs = as_list(buf, offs)
+    t = bioseq_b200.pbeos_tokenizers["PROTEIN"]
+    dev_bf = t.batch_tokenize_packed(to_dev(buf), to_dev(offs), padlen=1002, batch_first=True)
+    for _ in range(2):
+        got = t.batch_tokenize(seqs, padlen=1002, batch_first=True, nthreads=nthreads)
+        got_sf = t.batch_tokenize(seqs, padlen=1002, destchar="h", nthreads=nthreads)
+        assert torch.equal(got, dev_bf)
+        assert torch.equal(got_sf, dev_bf.T.to(torch.int16))
+    small = seqs[:2001]
+    orc = OracleTokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    want = orc.batch_onehot_encode((buf[:offs[2001]], offs[:2002]), padlen=1002, destchar="B")
+    assert_same_bits(want, t.batch_onehot_encode(small, padlen=1002, nthreads=nthreads).cpu().numpy())
+    # the length check fires before anything is copied, with the reference's text
+    with pytest.raises(RuntimeError, match=r"seq len \+ bos \+ eos > padlen: 1002, vs padlen 1001"):
+        t.batch_tokenize(seqs + [b"A" * 1000], padlen=1001, nthreads=nthreads)
+    assert torch.equal(t.batch_tokenize(seqs, padlen=1002, batch_first=True, nthreads=nthreads), dev_bf)
+
+
+def test_python_decode_streams_many_stages():
+    # decoded characters leave the device through the pinned ring in 8 MiB stages (bsq_fetch_rows): enough rows
+    # for > 3 stages (ring reuse), ragged rows with 5-character specials, rows straddling stage boundaries
+    t = bioseq_b200.pbeos_tokenizers["DAYHOFF"]
+    orc = OracleTokenizer("DAYHOFF", bos=True, eos=True, padchar=True)
+    buf, offs = gen(45, 40_000, 0, 500, b"ACDEFGHIKLMNPQRSTVWY")
+    toks = t.batch_tokenize_packed(buf, offs, padlen=512, batch_first=True)
+    got = t.decode_tokens(toks)
+    assert sum(map(len, got)) > 4 * (8 << 20)
+    ref_rows = np.r_[0:300, 20_000:20_300, 39_700:40_000]
+    sub = orc.batch_tokenize((buf, offs), padlen=512, batch_first=True)[ref_rows]
+    assert [got[i] for i in ref_rows] == orc.decode_tokens(sub)
+    assert got == abi_decode(capi.tokenizer("DAYHOFF", bos=True, eos=True, padchar=True), toks)
+    # 1-D input, one row, and empty rows
+    assert t.decode_tokens(toks[7]) == got[7]
+    assert t.decode_tokens(toks[:1]) == got[:1]
+    assert t.decode_tokens(toks[:0]) == []
