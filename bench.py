@@ -282,7 +282,7 @@ def run_ours(args):
     if "e2e" in sections and rank == 0:
         from bioseq_b200.synth import as_list
         seqs = as_list(sets[0]["buf"], sets[0]["offs"])
-        nthreads = min(16, os.cpu_count() or 1)
+        nthreads = os.cpu_count() or 1   # libbsq caps its pool at half the hardware threads
         for _ in range(2):
             ptok.batch_tokenize(seqs, padlen=PADLEN, destchar="B", batch_first=True, nthreads=nthreads)
         torch.cuda.synchronize()

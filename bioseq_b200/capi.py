@@ -66,6 +66,7 @@ def lib():
         "bsq_onehot_host": (i32, [vp, vp, vp, vp, vp, i64, i64, tokp, i32, vp]),
         "bsq_tokenize_items": (i32, [vp, vp, vp, C.POINTER(vp), C.POINTER(i64), i64, i64, tokp, i32, i32, vp, i32]),
         "bsq_onehot_items": (i32, [vp, vp, vp, C.POINTER(vp), C.POINTER(i64), i64, i64, tokp, i32, vp, i32]),
+        "bsq_parallel_for": (i32, [i32, vp, vp]),
         "bsq_fetch_rows": (i32, [vp, vp, vp, vp, i64, C.POINTER(vp), i32]),
         "bsq_stage_host": (i32, [vp, vp, vp, vp, i64, C.POINTER(vp), C.POINTER(vp)]),
         "bsq_stage_release": (i32, [vp, vp]),
@@ -101,7 +102,7 @@ EXPORTS = ("bsq_abi_version bsq_last_error bsq_launch_count bsq_launch_count_res
            "bsq_flatfile_make bsq_flatfile_open bsq_flatfile_close bsq_flatfile_nseqs bsq_flatfile_seq_offset "
            "bsq_flatfile_max_seq_len bsq_flatfile_offsets bsq_flatfile_bytes bsq_flatfile_is_pinned bsq_fastx_lengths "
            "bsq_free bsq_stage_host bsq_stage_release bsq_stager_set_augment bsq_onehot_bcl bsq_embed bsq_augment_blosum62 "
-           "bsq_blosum62_thresholds bsq_tokenize_items bsq_onehot_items bsq_fetch_rows").split()
+           "bsq_blosum62_thresholds bsq_tokenize_items bsq_onehot_items bsq_fetch_rows bsq_parallel_for").split()
 
 
 def last_error():

@@ -926,6 +926,12 @@ __device__ __forceinline__ uint32_t inv_lookup(const uint16_t *inv, int32_t key)
 // contiguous along the row, every row 4-byte aligned -> four tokens per 32-bit load.
 constexpr int kDecWarps = 8;
 
+// character j of the text of special k: <BOS> <EOS> <PAD> (src/tokenize.h:92-100)
+__device__ __forceinline__ uint8_t special_char(int k, int j) {
+    const uint32_t mid = k == 0 ? 0x00534f42u : (k == 1 ? 0x00534f45u : 0x00444150u);  // "BOS" "EOS" "PAD", little-endian
+    return j == 0 ? '<' : (j == 4 ? '>' : static_cast<uint8_t>(mid >> (8 * (j - 1))));
+}
+
 __device__ __forceinline__ void decode_fetch4(const uint8_t *rp, int itemsize, int64_t col_stride, int64_t c, int64_t cols,
                                               const uint16_t *inv, bool fast, uint32_t e[4]) {
     // entries of tokens c .. c+3 of a row (kInvNone beyond the row end is reported as 0xFFFE = "absent")
@@ -972,6 +978,54 @@ decode_len_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t rows
             row_len[r] = cols + 4ll * specials;
             if (bad != ~0ull) atomicMin(first_bad, bad);
         }
+    }
+}
+
+// pass 1, lean form for one-byte tokens in 16-byte aligned rows whose length is a multiple of 16 (what
+// batch_tokenize itself produces): 16 tokens per lane and load, a 256-entry class table (0 = one character,
+// 1 = five-character special, 0x100 = no entry) summed per vector -- 2.5 instructions per token instead of 31
+// (profiles/r01e: the general kernel was issue-bound at 0.78 TB/s).  A row that holds a token without an
+// entry (the error path) is rescanned for the exact position.
+__global__ void __launch_bounds__(kDecWarps * 32)
+decode_len16_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t cols, int64_t row_stride, InvParam invp,
+                    int64_t *__restrict__ row_len, unsigned long long *first_bad) {
+    __shared__ uint16_t cls[256];
+    for (int i = threadIdx.x; i < 256; i += kDecWarps * 32) {
+        const uint16_t e = invp.e[i + 128];
+        cls[i] = e == kInvNone ? 0x100 : ((e >> 8) & 1);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kDecWarps + (threadIdx.x >> 5);
+    const int64_t GW = static_cast<int64_t>(gridDim.x) * kDecWarps;
+    const int64_t nvec = cols >> 4;
+    for (int64_t r = gw; r < rows; r += GW) {
+        const uint4 *rp = reinterpret_cast<const uint4 *>(tokens + r * row_stride);
+        uint32_t specials = 0, bad = 0;
+#pragma unroll 2
+        for (int64_t v = lane; v < nvec; v += 32) {
+            const uint4 x = __ldcs(rp + v);
+            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+            uint32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                sum += cls[w[k] & 0xffu] + cls[__byte_perm(w[k], 0, 0x4441)] + cls[__byte_perm(w[k], 0, 0x4442)] + cls[w[k] >> 24];
+            specials += sum & 0xffu;
+            bad |= sum >> 8;
+        }
+        for (int o = 16; o > 0; o >>= 1) specials += __shfl_xor_sync(0xffffffffu, specials, o);
+        if (__any_sync(0xffffffffu, bad != 0)) {
+            const uint8_t *rb = tokens + r * row_stride;
+            unsigned long long b = ~0ull;
+            for (int64_t c = lane; c < cols; c += 32)
+                if (cls[rb[c]] & 0x100) {
+                    b = static_cast<unsigned long long>(r * cols + c);
+                    break;
+                }
+            for (int o = 16; o > 0; o >>= 1) b = min(b, __shfl_xor_sync(0xffffffffu, b, o));
+            if (lane == 0) atomicMin(first_bad, b);
+        }
+        if (lane == 0) row_len[r] = cols + 4ll * specials;
     }
 }
 
@@ -1048,10 +1102,19 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
                     uint8_t *__restrict__ chars) {
     __shared__ uint16_t inv[512];
     __shared__ __align__(16) uint8_t stage_all[kDecWarps][kDecStage];
+    __shared__ uint32_t patw[3][8];  // patw[k][ph]: four bytes of special k's text repeated, starting at phase ph
     for (int i = threadIdx.x; i < 512; i += kDecWarps * 32) inv[i] = invp.e[i];
+    if (threadIdx.x < 15) {
+        const int k = threadIdx.x / 5, ph = threadIdx.x % 5;
+        uint32_t w = 0;
+        for (int j = 0; j < 4; ++j) w |= static_cast<uint32_t>(special_char(k, (ph + j) % 5)) << (8 * j);
+        patw[k][ph] = w;
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *stage = stage_all[warp];
+    uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage);
+    const bool rows16 = fast == 2;  // rows are 16-byte aligned: 16 tokens per lane where a whole 512-token step is plain text
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * kDecWarps + warp;
     const int64_t GW = static_cast<int64_t>(gridDim.x) * kDecWarps;
     for (int64_t r = gw; r < rows; r += GW) {
@@ -1060,32 +1123,90 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
         int fill = static_cast<int>(reinterpret_cast<uintptr_t>(dst) & 15u);  // bytes of the stage in front of the data
         uint8_t *gal = dst - fill;                                             // aligned address of stage[0]
         int head = fill;                                                       // > 0: stage[0 .. head) is not ours
-        for (int64_t c0 = 0; c0 < cols; c0 += 128) {
-            uint32_t e[4];
-            decode_fetch4(rp, itemsize, col_stride, c0 + 4 * lane, cols, inv, fast != 0, e);
-            int mylen = 0;
+        int step = 128;
+        for (int64_t c0 = 0; c0 < cols; c0 += step) {
+            step = 128;
+            int total;
+            bool done = false;
+            // Steps of plain text or of one repeated special (the <PAD> run behind a sequence) -- nearly all of
+            // them -- are laid into the stage as whole 32-bit words shifted by the carry (fill & 3 bytes):
+            // one shuffle and one funnel shift per word instead of a scan and a byte store per character.
+            if (rows16 && c0 + 512 <= cols) {
+                const uint4 x = *reinterpret_cast<const uint4 *>(rp + c0 + 16 * lane);
+                const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+                uint32_t w[4], any = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mylen += e[k] >= 0xFFFEu ? 0 : ((e[k] & 0x100u) ? 5 : 1);
-            int incl = mylen;
-            for (int o = 1; o < 32; o <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += y;
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t e0 = inv[(xs[k] & 0xffu) + 128], e1 = inv[__byte_perm(xs[k], 0, 0x4441) + 128],
+                                   e2 = inv[__byte_perm(xs[k], 0, 0x4442) + 128], e3 = inv[(xs[k] >> 24) + 128];
+                    any |= e0 | e1 | e2 | e3;
+                    w[k] = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
+                }
+                if (!__any_sync(0xffffffffu, (any & 0x100u) != 0)) {
+                    const int r8 = (fill & 3) * 8, kw = fill >> 2;
+                    uint32_t lo = __shfl_up_sync(0xffffffffu, w[3], 1);
+                    if (lane == 0) lo = r8 ? stage_w[kw] << (32 - r8) : 0u;
+                    uint32_t *d = stage_w + kw + 4 * lane;
+                    d[0] = __funnelshift_l(lo, w[0], r8);
+                    d[1] = __funnelshift_l(w[0], w[1], r8);
+                    d[2] = __funnelshift_l(w[1], w[2], r8);
+                    d[3] = __funnelshift_l(w[2], w[3], r8);
+                    if (lane == 31 && r8) d[4] = w[3] >> (32 - r8);
+                    total = 512;
+                    step = 512;
+                    done = true;
+                }
             }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            uint8_t *w = stage + fill + incl - mylen;
+            if (!done && fast && c0 + 128 <= cols) {
+                const uint32_t x = *reinterpret_cast<const uint32_t *>(rp + c0 + 4 * lane);
+                const uint32_t e0 = inv[(x & 0xffu) + 128], e1 = inv[__byte_perm(x, 0, 0x4441) + 128],
+                               e2 = inv[__byte_perm(x, 0, 0x4442) + 128], e3 = inv[(x >> 24) + 128];
+                const bool sp_here = ((e0 | e1 | e2 | e3) & 0x100u) != 0;
+                const uint32_t x0 = __shfl_sync(0xffffffffu, x, 0);
+                if (!__any_sync(0xffffffffu, sp_here)) {
+                    const uint32_t w = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
+                    const int r8 = (fill & 3) * 8, kw = fill >> 2;
+                    uint32_t lo = __shfl_up_sync(0xffffffffu, w, 1);
+                    if (lane == 0) lo = r8 ? stage_w[kw] << (32 - r8) : 0u;
+                    stage_w[kw + lane] = __funnelshift_l(lo, w, r8);
+                    if (lane == 31 && r8) stage_w[kw + 32] = w >> (32 - r8);
+                    total = 128;
+                    done = true;
+                } else if (__all_sync(0xffffffffu, x == x0 && x == __byte_perm(x, 0, 0x0000))) {
+                    // 128 x the same special: bytes fill .. fill+640 of the stage repeat its five characters
+                    const int k = static_cast<int>(e0 & 3u);
+                    const int k0 = (fill + 3) >> 2, kend = (fill + 640) >> 2;
+                    if (lane < 4 * k0 - fill) stage[fill + lane] = special_char(k, lane);
+                    for (int q = k0 + lane; q < kend; q += 32) stage_w[q] = patw[k][(4 * q - fill) % 5];
+                    if (lane < ((fill + 640) & 3)) stage[4 * kend + lane] = special_char(k, (4 * kend + lane - fill) % 5);
+                    total = 640;
+                    done = true;
+                }
+            }
+            if (!done) {
+                uint32_t e[4];
+                decode_fetch4(rp, itemsize, col_stride, c0 + 4 * lane, cols, inv, fast != 0, e);
+                int mylen = 0;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (e[k] >= 0xFFFEu) continue;
-                if (e[k] & 0x100u) {
-                    const uint32_t sp = e[k] & 3u;  // <BOS> <EOS> <PAD>
-                    w[0] = '<';
-                    w[1] = sp == 0 ? 'B' : (sp == 1 ? 'E' : 'P');
-                    w[2] = sp == 2 ? 'A' : 'O';
-                    w[3] = sp == 2 ? 'D' : 'S';
-                    w[4] = '>';
-                    w += 5;
-                } else {
-                    *w++ = static_cast<uint8_t>(e[k]);
+                for (int k = 0; k < 4; ++k) mylen += e[k] >= 0xFFFEu ? 0 : ((e[k] & 0x100u) ? 5 : 1);
+                int incl = mylen;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += y;
+                }
+                total = __shfl_sync(0xffffffffu, incl, 31);
+                uint8_t *w = stage + fill + incl - mylen;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (e[k] >= 0xFFFEu) continue;
+                    if (e[k] & 0x100u) {
+                        const int sp = static_cast<int>(e[k] & 3u);  // <BOS> <EOS> <PAD>
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) w[j] = special_char(sp, j);
+                        w += 5;
+                    } else {
+                        *w++ = static_cast<uint8_t>(e[k]);
+                    }
                 }
             }
             __syncwarp();
@@ -1319,9 +1440,13 @@ int launch_sf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t ld, int64
     return BSQ_OK;
 }
 
-// one-byte tokens, contiguous along the row, every row 4-byte aligned: four tokens per 32-bit load
+// one-byte tokens, contiguous along the row: 1 = every row 4-byte aligned (four tokens per 32-bit load),
+// 2 = every row 16-byte aligned (sixteen tokens per 128-bit load where a step allows it)
 int decode_fast_path(const void *d_tokens, int itemsize, int64_t row_stride, int64_t col_stride) {
-    return itemsize == 1 && col_stride == 1 && row_stride % 4 == 0 && (reinterpret_cast<uintptr_t>(d_tokens) & 3u) == 0;
+    if (itemsize != 1 || col_stride != 1) return 0;
+    const uintptr_t a = reinterpret_cast<uintptr_t>(d_tokens);
+    if (row_stride % 16 == 0 && (a & 15u) == 0) return 2;
+    return row_stride % 4 == 0 && (a & 3u) == 0;
 }
 unsigned decode_grid(int64_t rows) {  // persistent: one warp per row, rows dealt round-robin
     return static_cast<unsigned>(std::min<int64_t>((rows + kDecWarps - 1) / kDecWarps, 148 * 8));
@@ -1476,9 +1601,13 @@ int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int items
     BSQ_CUDA_TRY(cudaMemsetAsync(d_work, 0xff, sizeof(int64_t), st));
     const InvParam inv = make_inv(*tok);
     const int fast = decode_fast_path(d_tokens, itemsize, row_stride, col_stride);
-    decode_len_kernel<<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
-        static_cast<const uint8_t *>(d_tokens), itemsize, rows, cols, row_stride, col_stride, fast, inv, d_row_offsets,
-        reinterpret_cast<unsigned long long *>(d_work));
+    if (fast == 2 && cols % 16 == 0)
+        decode_len16_kernel<<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
+            static_cast<const uint8_t *>(d_tokens), rows, cols, row_stride, inv, d_row_offsets, reinterpret_cast<unsigned long long *>(d_work));
+    else
+        decode_len_kernel<<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
+            static_cast<const uint8_t *>(d_tokens), itemsize, rows, cols, row_stride, col_stride, fast, inv, d_row_offsets,
+            reinterpret_cast<unsigned long long *>(d_work));
     scan_local_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2);
     scan_totals_kernel<<<1, kScanBlock, 0, st>>>(d_work + 2, nblocks, d_work + 1);
     scan_add_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2, d_work + 1);

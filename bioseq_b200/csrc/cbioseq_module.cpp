@@ -150,7 +150,52 @@ struct Unpacked {
     std::vector<int64_t> lens;
 };
 
-void unpack_items(const py::sequence &batch, Unpacked &u) {
+// One item -> borrowed pointer + length.  Returns false for a type the reference rejects.
+inline bool unpack_one(PyObject *it, const void *&ptr, int64_t &len) {
+    if (PyUnicode_Check(it)) {
+        Py_ssize_t size;
+        const char *s = PyUnicode_AsUTF8AndSize(it, &size);
+        if (s == nullptr) throw py::error_already_set();
+        ptr = s;
+        len = size;
+    } else if (PyBytes_Check(it)) {
+        ptr = PyBytes_AS_STRING(it);
+        len = PyBytes_GET_SIZE(it);
+    } else if (PyByteArray_Check(it)) {
+        ptr = PyByteArray_AS_STRING(it);
+        len = PyByteArray_GET_SIZE(it);
+    } else {
+        return false;
+    }
+    return true;
+}
+
+struct WalkCtx {
+    PyObject **items;
+    const void **ptrs;
+    int64_t *lens;
+    Py_ssize_t n;
+};
+// Pool-thread share of the walk: bytes / bytearray items only (plain field reads of objects that the
+// calling thread keeps alive and, holding the GIL, unchanged); anything else is left to the caller (-1).
+void walk_share(int t, int nt, void *vctx) {
+    const WalkCtx &c = *static_cast<const WalkCtx *>(vctx);
+    const Py_ssize_t lo = c.n * t / nt, hi = c.n * (t + 1) / nt;
+    for (Py_ssize_t i = lo; i < hi; ++i) {
+        PyObject *it = c.items[i];
+        if (PyBytes_Check(it)) {
+            c.ptrs[i] = PyBytes_AS_STRING(it);
+            c.lens[i] = PyBytes_GET_SIZE(it);
+        } else if (PyByteArray_Check(it)) {
+            c.ptrs[i] = PyByteArray_AS_STRING(it);
+            c.lens[i] = PyByteArray_GET_SIZE(it);
+        } else {
+            c.lens[i] = -1;
+        }
+    }
+}
+
+void unpack_items(const py::sequence &batch, Unpacked &u, int nthreads = 1) {
     PyObject *fast = PySequence_Fast(batch.ptr(), "batch must be a sequence");
     if (fast == nullptr) throw py::error_already_set();
     u.keepalive = py::reinterpret_steal<py::object>(fast);
@@ -158,24 +203,18 @@ void unpack_items(const py::sequence &batch, Unpacked &u) {
     PyObject **items = PySequence_Fast_ITEMS(fast);
     u.ptrs.resize(static_cast<size_t>(n));
     u.lens.resize(static_cast<size_t>(n));
-    for (Py_ssize_t i = 0; i < n; ++i) {
-        PyObject *it = items[i];
-        if (PyUnicode_Check(it)) {
-            Py_ssize_t size;
-            const char *s = PyUnicode_AsUTF8AndSize(it, &size);
-            if (s == nullptr) throw py::error_already_set();
-            u.ptrs[i] = s;
-            u.lens[i] = size;
-        } else if (PyBytes_Check(it)) {
-            u.ptrs[i] = PyBytes_AS_STRING(it);
-            u.lens[i] = PyBytes_GET_SIZE(it);
-        } else if (PyByteArray_Check(it)) {
-            u.ptrs[i] = PyByteArray_AS_STRING(it);
-            u.lens[i] = PyByteArray_GET_SIZE(it);
-        } else {
-            throw py::value_error("item was none of string, bytes, or numpy array of 8-bit integers. ");
-        }
+    const char *bad = "item was none of string, bytes, or numpy array of 8-bit integers. ";
+    if (nthreads > 1 && n >= 8192) {
+        // touching 10^5 object headers is a chain of cache misses: spread it over the pool (the GIL stays with
+        // this thread, so nothing can mutate the items meanwhile); str items need the C API and are done here
+        WalkCtx c{items, u.ptrs.data(), u.lens.data(), n};
+        check(bsq_parallel_for(static_cast<int>(std::min<Py_ssize_t>(nthreads, n / 4096)), walk_share, &c));
+        for (Py_ssize_t i = 0; i < n; ++i)
+            if (u.lens[i] < 0 && !unpack_one(items[i], u.ptrs[i], u.lens[i])) throw py::value_error(bad);
+        return;
     }
+    for (Py_ssize_t i = 0; i < n; ++i)
+        if (!unpack_one(items[i], u.ptrs[i], u.lens[i])) throw py::value_error(bad);
 }
 
 // A host or device array argument of the *_packed entry points.
@@ -384,7 +423,7 @@ public:
             return run_flatfile(batch.cast<const FlatFile &>(), 0, py::none(), py::none(), padlen, dc, kind, false, batch_first, device);
         if (padlen <= 0) throw py::value_error("batch tokenize requires padlen is provded.");
         Unpacked u;
-        unpack_items(batch, u);
+        unpack_items(batch, u, nthreads);
         return run_host(u.ptrs.data(), u.lens.data(), static_cast<int64_t>(u.lens.size()), nullptr, padlen, dc, kind,
                         /*onehot=*/false, batch_first, nthreads, device);
     }
@@ -399,7 +438,7 @@ public:
             return run_flatfile(batch.cast<const FlatFile &>(), 0, py::none(), mask, padlen, dc, kind, true, false, device);
         if (padlen <= 0) throw py::value_error("batch tokenize requires padlen is provded.");
         Unpacked u;
-        unpack_items(batch, u);
+        unpack_items(batch, u, nthreads);
         // mask: a list with one uint8 array per sequence; entries that are not arrays mean
         // "no mask for this sequence" (getmaskptr, src/tokenize.h:372-380).
         std::vector<uint8_t> maskbuf;

@@ -192,6 +192,12 @@ int bsq_tokenize_items(bsq_stager *s, bsq_pack *p, void *stream, const void *con
 int bsq_onehot_items(bsq_stager *s, bsq_pack *p, void *stream, const void *const *ptrs, const int64_t *lens,
                      int64_t n, int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out, int nthreads);
 
+/* Run fn(t, nthreads, ctx) for t = 0 .. nthreads-1 on the library's persistent host worker pool (the one the
+ * gather / scatter loops above use) and return when all have finished.  The reference's counterpart is its
+ * OpenMP team (`#pragma omp parallel for num_threads(nthreads)`, src/tokenize.h:340,452); the Python shim uses
+ * this for the per-item pointer/length walk of large batches.  fn must not call back into the pool. */
+int bsq_parallel_for(int nthreads, void (*fn)(int t, int nthreads, void *ctx), void *ctx);
+
 /* Second half of decode_tokens (src/tokenize.h:131-179 builds one std::string per row): row r of the
  * decoded characters, d_chars[h_offsets[r] .. h_offsets[r+1]), is delivered to host address dst[r] (the body
  * of the string object the caller created for it).  Device->host copies go through a pinned ring in 8 MiB

@@ -507,3 +507,48 @@ def test_python_decode_streams_many_stages():
     assert t.decode_tokens(toks[7]) == got[7]
     assert t.decode_tokens(toks[:1]) == got[:1]
     assert t.decode_tokens(toks[:0]) == []
+
+
+@pytest.mark.parametrize("cols,row_pad,shift", [(1024, 0, 0), (1040, 0, 0), (1000, 0, 0), (1024, 16, 0), (1024, 4, 0), (640, 1, 0),
+                                                (1024, 0, 4), (1024, 0, 3), (130, 0, 0), (512, 0, 0)])
+def test_decode_fast_steps_every_alignment(cols, row_pad, shift):
+    # K4 lays plain-text steps and runs of one special into its stage as whole words (512-token steps for
+    # 16-byte aligned rows, 128-token steps for 4-byte aligned ones) and falls back to the byte-wise step for
+    # mixed ones: random mixtures of text runs, special runs and single specials, every row/carry alignment,
+    # against a direct table decode
+    flags = dict(bos=True, eos=True, padchar=True)
+    tok = capi.tokenizer("PROTEIN", **flags)
+    orc = OracleTokenizer("PROTEIN", **flags)
+    rng = np.random.default_rng(cols * 31 + row_pad * 7 + shift)
+    rows = 300
+    a = np.empty((rows, cols), dtype=np.uint8)
+    for r in range(rows):
+        c = 0
+        while c < cols:
+            kind = rng.integers(0, 10)
+            n = int(rng.integers(1, 700)) if kind < 8 else int(rng.integers(1, 4))
+            n = min(n, cols - c)
+            if kind < 5:
+                a[r, c:c + n] = rng.integers(0, 20, size=n)
+            elif kind < 8:
+                a[r, c:c + n] = rng.integers(20, 23)
+            else:
+                a[r, c:c + n] = rng.integers(0, 23, size=n)
+            c += n
+    a[0] = 22
+    a[1] = 3
+    a[2, :] = np.arange(cols) % 20
+    want = orc.decode_tokens(a)
+    assert want[0] == "<PAD>" * cols and want[1] == "E" * cols
+    flat = torch.zeros(rows * (cols + row_pad) + 64, dtype=torch.uint8, device="cuda")
+    view = flat[shift:shift + rows * (cols + row_pad)].view(rows, cols + row_pad)[:, :cols]
+    view.copy_(torch.from_numpy(a))
+    assert abi_decode(tok, view) == want
+    # a token without an entry: reported with the reference's message, at its first position in row-major order
+    for (r, c) in ((rows - 1, cols - 1), (5, 17), (5, 16)):
+        old = int(view[r, c])
+        view[r, c] = 23
+        with pytest.raises(RuntimeError, match="Unexpected/invalid token 23"):
+            abi_decode(tok, view)
+        view[r, c] = old
+    assert abi_decode(tok, view) == want
