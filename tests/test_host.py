@@ -176,3 +176,19 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in text.lower() or f == "synth.py", f"{f} mentions the oracle"
+
+
+def test_parallel_for_runs_every_share_once():
+    # the persistent host worker pool behind the gather / scatter loops (no GPU involved)
+    L = capi.lib()
+    CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_void_p)
+    for nthreads in (1, 2, 5):
+        seen = []
+        cb = CB(lambda t, nt, ctx: seen.append((t, nt)))
+        for _ in range(3):                       # the pool is reused job after job
+            seen.clear()
+            assert L.bsq_parallel_for(nthreads, C.cast(cb, C.c_void_p), None) == 0
+            nt = seen[0][1]
+            assert 1 <= nt <= nthreads           # capped at half the hardware threads
+            assert sorted(seen) == [(t, nt) for t in range(nt)]
+    assert L.bsq_parallel_for(2, None, None) == capi.ERR_ARG
