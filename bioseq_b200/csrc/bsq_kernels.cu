@@ -762,6 +762,11 @@ seqfirst_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, LutParam lutp, 
 //   * everything a thread needs per chunk is either thread-constant (chunk column, BOS predicate,
 //     shared-memory addresses) or one LDS.128 of per-sequence data resolved once per CTA;
 //   * phase 2 runs unguarded on full tiles (the common case) and keeps its addresses in registers.
+// A persistent, software-pipelined form of this kernel (offsets of tile k+2 and windows of tile k+1 prefetched,
+// double-buffered code tile, one block barrier per tile; 58 KB and 70 registers -> 3 CTAs per SM) was measured
+// and rejected: C2x4 118 us vs 101 us, C1x64 124 us vs 112 us (132 / 138 us at 2 CTAs per SM).  The kernel is
+// bound by shared-memory wavefronts and dependent LDS chains (profiles/r01e: LSU data pipe 65 % busy, issue-active
+// 63 %), which 48 resident warps of independent one-shot CTAs cover better than 24 pipelined ones.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
