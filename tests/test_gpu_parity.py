@@ -552,3 +552,38 @@ def test_decode_fast_steps_every_alignment(cols, row_pad, shift):
             abi_decode(tok, view)
         view[r, c] = old
     assert abi_decode(tok, view) == want
+
+
+def test_concurrent_python_threads_share_pool_and_stager():
+    # four Python threads hammer the list API (worker pool + pinned pack + stager, per-device mutex) and
+    # decode_tokens (pinned device->host ring) at once, each on its own stream: no deadlock, no cross-talk
+    import threading
+    t = bioseq_b200.pbeos_tokenizers["PROTEIN"]
+    work = []
+    for k in range(4):
+        buf, offs = gen(500 + k, 9000 + 1000 * k, 0, 800, MIX)
+        seqs = as_list(buf, offs)
+        want = t.batch_tokenize_packed(to_dev(buf), to_dev(offs), padlen=802, batch_first=True)
+        work.append((seqs, want, t.decode_tokens(want[:2000])))
+    errors = []
+
+    def run(k):
+        try:
+            seqs, want, want_txt = work[k]
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for it in range(6):
+                    got = t.batch_tokenize(seqs, padlen=802, batch_first=True, nthreads=2 + 3 * (it % 3))
+                    s.synchronize()
+                    assert torch.equal(got, want), f"thread {k} iteration {it}: tokens differ"
+                    assert t.decode_tokens(got[:2000]) == want_txt, f"thread {k} iteration {it}: text differs"
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=run, args=(k,)) for k in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=120)
+    assert not any(th.is_alive() for th in threads), "deadlock in the host pipeline"
+    assert not errors, errors
