@@ -331,7 +331,21 @@ int stage_copy(bsq_stager *s, void *dst, const void *src, size_t n, bool src_pin
             BSQ_CUDA_TRY(cudaEventCreateWithFlags(&s->ring_free[k], cudaEventDisableTiming));
         }
         if (s->ring_used[k]) BSQ_CUDA_TRY(cudaEventSynchronize(s->ring_free[k]));
-        std::memcpy(s->ring[k], static_cast<const uint8_t *>(src) + done, m);
+        // one thread copies at ~11 GB/s, a fifth of the link: spread the bounce copy over the worker pool
+        // (35 MB batch from a pageable numpy array: 3.3 ms -> ~1 ms)
+        const uint8_t *from = static_cast<const uint8_t *>(src) + done;
+        uint8_t *to = s->ring[k];
+        const int nt = static_cast<int>(std::min<size_t>(static_cast<size_t>(pool_threads(1 << 20)), std::max<size_t>(1, m >> 19)));
+        if (nt > 1) {
+            Pool &pool = Pool::get();
+            pool.start(nt, [=](int t) {
+                const size_t lo = m * static_cast<size_t>(t) / nt, hi = m * static_cast<size_t>(t + 1) / nt;
+                std::memcpy(to + lo, from + lo, hi - lo);
+            });
+            pool.wait();
+        } else {
+            std::memcpy(to, from, m);
+        }
         BSQ_CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(dst) + done, s->ring[k], m, cudaMemcpyHostToDevice, s->copy_stream));
         BSQ_CUDA_TRY(cudaEventRecord(s->ring_free[k], s->copy_stream));
         s->ring_used[k] = true;
