@@ -335,6 +335,8 @@ def run_ours(args):
     if rank == 0:
         if "extra" in sections:
             extra = secondary_measurements(torch, capi, L, dev, st)
+        if "frows" in sections:
+            extra["f_rows"] = f_rows_measurements(torch, capi, L, dev, st)
         if "c4" in sections and world == 1:
             extra["c4_reduced_alphabets_1M_roundtrip"] = c4_measurements(torch, capi, L, dev, st, with_cpu="cpu" in sections)
         clocks = clocks_early if clocks_early is not None else sampler.stop()
@@ -548,6 +550,106 @@ def c5_slice(torch, capi, L, dev, st, rank, nchunks=8, chunk=131072):
             "nchunks": nchunks, "chunk": chunk, "padlen": P}
 
 
+def f_rows_measurements(torch, capi, L, dev, st):
+    """SURVEY.md 8(f) rows built next to the hot path, each at the C2 batch (65536 ragged protein sequences, P = 1024)
+    unless stated: K5 one-hot straight into the CNN's (B,C,L) float layout, K6 tokenize -> embedding rows, K7 BLOSUM62
+    point mutations on the packed residues, and the FlatFile feeder (file -> GPU tokens, no per-sequence host work)."""
+    import ctypes as C
+    import tempfile
+    import bioseq_b200
+    from bioseq_b200.synth import gen, AA20
+    peak, _ = measured_peak()
+    res = {}
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    tk = capi.tokenizer(KEY, **FLAGS)
+    ncols = tk.alphabet_size
+    bufs = [gen(102 + r, NSEQ, LO, HI, AA20) for r in range(2)]
+    dev_sets = [(torch.from_numpy(b).cuda(), torch.from_numpy(o).cuda(), int(o[-1])) for b, o in bufs]
+    it = [0]
+
+    def rot():
+        it[0] += 1
+        return dev_sets[it[0] % 2]
+
+    # K5: (B, C, L) float32 one-hot, 16384 x 23 x 1024 x 4 B = 1.54 GB per call (write-bound)
+    n5 = NSEQ // 4
+    out5 = torch.empty((n5, ncols, PADLEN), dtype=torch.float32, device="cuda")
+    def k5():
+        d_b, d_o, _ = rot()
+        capi.onehot_bcl(dev, st, d_b, d_o, None, n5, PADLEN, tk, capi.F32, out5)
+    ms = timed(k5, 5)
+    nb5 = int(bufs[0][1][n5])
+    by = nb5 + 8 * (n5 + 1) + n5 * ncols * PADLEN * 4
+    res["f4_onehot_bcl_f32_16384x23x1024"] = {"Gbases/s": nb5 / ms / 1e6, "GB/s": by / ms / 1e6, "frac_of_measured_hbm": by / ms / 1e6 / peak,
+                                                "us_per_call": ms * 1e3}
+    del out5
+    # K6: tokenize -> embedding gather, D = 64 float32 (256 B rows), batch-first: 16384 x 1024 x 256 B = 4.3 GB per call
+    D = 64
+    w = torch.randn((ncols, D), dtype=torch.float32, device="cuda")
+    out6 = torch.empty((n5, PADLEN, D), dtype=torch.float32, device="cuda")
+    def k6():
+        d_b, d_o, _ = rot()
+        capi.embed(dev, st, d_b, d_o, n5, PADLEN, tk, True, w, ncols, D * 4, out6)
+    ms = timed(k6, 5)
+    by = nb5 + 8 * (n5 + 1) + n5 * PADLEN * D * 4
+    res["f4_embed_f32_D64_16384x1024"] = {"Gbases/s": nb5 / ms / 1e6, "GB/s": by / ms / 1e6, "frac_of_measured_hbm": by / ms / 1e6 / peak,
+                                           "us_per_call": ms * 1e3}
+    del out6, w
+    # K7: BLOSUM62 augmentation in place, one substitution per sequence (chain_len 1) and eight: touches one
+    # 32-byte sector per substitution, so it is latency/launch-bound, not bandwidth-bound -- reported per sequence
+    for chain in (1, 8):
+        def k7():
+            d_b, d_o, _ = rot()
+            capi.augment_blosum62(dev, st, d_b, d_o, NSEQ, chain, 1.0, 1234, 0)
+        ms = timed(k7, 20)
+        res[f"f3_augment_blosum62_chain{chain}_65536_seqs"] = {"Gseqs/s": NSEQ / ms / 1e6, "us_per_call": ms * 1e3}
+    # f1: FlatFile feeder.  The file is written once (FASTA -> flat file, the reference's FlatFile::make), then a whole
+    # file goes file -> pinned copy / page cache -> GPU tokens through Tokenizer.batch_tokenize(FlatFile)
+    ptok = bioseq_b200.Tokenizer(KEY, **FLAGS)
+    buf, offs = bufs[0]
+    with tempfile.TemporaryDirectory() as td:
+        fa = os.path.join(td, "c2.fa")
+        with open(fa, "wb") as f:
+            for i in range(NSEQ):
+                f.write(b">s\n")
+                f.write(buf[offs[i]:offs[i + 1]].tobytes())
+                f.write(b"\n")
+        t0 = time.perf_counter()
+        bioseq_b200.FlatFile(fa, fa + ".ff")
+        make_s = time.perf_counter() - t0
+        want = None
+        for mode, kw in (("pinned", {"pinned": True}), ("mapped", {})):
+            ff = bioseq_b200.FlatFile(fa + ".ff", **kw)
+            for _ in range(2):
+                o = ptok.batch_tokenize(ff, padlen=PADLEN, batch_first=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            reps = 10
+            for _ in range(reps):
+                o = ptok.batch_tokenize(ff, padlen=PADLEN, batch_first=True)
+            torch.cuda.synchronize()
+            dt = (time.perf_counter() - t0) / reps
+            if want is None:
+                want = ptok.batch_tokenize_packed(torch.from_numpy(buf).cuda(), torch.from_numpy(offs).cuda(), padlen=PADLEN, batch_first=True)  # (dev_sets were mutated by K7)
+            res[f"f1_flatfile_{mode}_to_tokens_65536_seqs"] = {"Gbases/s": int(offs[-1]) / dt / 1e9, "ms_per_call": dt * 1e3,
+                                                              "matches_device_resident": bool(torch.equal(o, want))}
+            del ff
+        res["f1_flatfile_make_from_fasta"] = {"s": make_s, "MB/s": (int(offs[-1]) + 4 * NSEQ) / make_s / 1e6}
+    return res
+
+
 def measure_host_link(torch, nbytes=256 << 20, reps=5):
     """Pinned host->device copy rate of this rank's link (the roofline of the e2e number)."""
     h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
@@ -681,7 +783,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--smi", default="value", choices=["value", "all", "off"],
                     help="nvidia-smi clock sampler: over the device-timed region only (default), the whole run, or off")
-    ap.add_argument("--sections", default="value,e2e,extra,cpu,c4,c5",
+    ap.add_argument("--sections", default="value,e2e,extra,frows,cpu,c4,c5",
                     help="comma list of measurement sections to run (profiling runs use --sections value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
