@@ -1099,7 +1099,69 @@ scan_add_kernel(int64_t *__restrict__ data, int64_t n, const int64_t *__restrict
 // a per-warp shared-memory stage that carries the same 16-byte misalignment as the row's place in
 // the output buffer: whole 16-byte vectors then leave with st.global.v4, only the row's first and
 // last partial vectors (shared with the neighbouring rows) are written byte-wise.
-constexpr int kDecStage = 16 + 128 * 5 + 16;
+constexpr int kDecStage = 16 + 512 * 5 + 48;  // carry + the longest step (512 specials) + slack, a multiple of 16
+
+// One decode step as a stream of whole 32-bit words.  A lane's TPL (4 or 16) tokens expand to TPL + 4 * (#specials)
+// bytes -- whole words -- so the text moves as words: token k sits at byte k & 3 of the lane's current word; a special
+// closes that word with its first 4 - (k & 3) characters and opens the next one with the remaining (k & 3) + 1; a
+// plain character at byte 3 closes the word.  Word offsets come from one warp scan; the stream is shifted by the
+// carry (fill & 3 bytes) with one funnel shift per word.  Returns the number of bytes appended to the stage.
+template <int TPL>
+__device__ __forceinline__ int decode_word_step(const uint32_t (&ee)[TPL], const uint32_t (*patw)[8], uint32_t *stage_w, int fill,
+                                                int lane) {
+    int nw = TPL / 4;
+#pragma unroll
+    for (int k = 0; k < TPL; ++k) nw += (ee[k] >> 8) & 1;
+    int incl = nw;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+    }
+    const int nwords = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t last = 0;  // this lane's final word: decided by its last four tokens
+#pragma unroll
+    for (int k = TPL - 4; k < TPL; ++k) {
+        const uint32_t P = patw[ee[k] & 3u][0];  // "<BOS" / "<EOS" / "<PAD" (meaningful for specials only)
+        last = (ee[k] & 0x100u) ? __funnelshift_rc(P, 0x3eu, 32 - 8 * (k & 3)) : (last | ((ee[k] & 0xffu) << (8 * (k & 3))));
+    }
+    const int r8 = (fill & 3) * 8, kw = fill >> 2;
+    uint32_t pw = __shfl_up_sync(0xffffffffu, last, 1);
+    if (lane == 0) pw = r8 ? stage_w[kw] << (32 - r8) : 0u;
+    uint32_t *d = stage_w + kw + incl - nw;
+    uint32_t cur = 0;
+#pragma unroll
+    for (int k = 0; k < TPL; ++k) {
+        const int b = k & 3;
+        const bool sp = (ee[k] & 0x100u) != 0;
+        const uint32_t P = patw[ee[k] & 3u][0];
+        cur |= (sp ? P : (ee[k] & 0xffu)) << (8 * b);
+        if (sp) {
+            *d++ = __funnelshift_l(pw, cur, r8);
+            pw = cur;
+            cur = __funnelshift_rc(P, 0x3eu, 32 - 8 * b);
+        }
+        if (b == 3) {
+            *d++ = __funnelshift_l(pw, cur, r8);
+            pw = cur;
+            cur = 0;
+        }
+    }
+    if (lane == 31 && r8) *d = pw >> (32 - r8);
+    return 4 * nwords;
+}
+
+// `n` tokens of special k appended to the stage: bytes fill .. fill + 5 n repeat its five characters.
+__device__ __forceinline__ void decode_fill_special(int k, int n, const uint32_t (*patw)[8], uint8_t *stage, int fill, int lane) {
+    uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage);
+    const int k0 = (fill + 3) >> 2, kend = (fill + 5 * n) >> 2;
+    if (lane < 4 * k0 - fill) stage[fill + lane] = special_char(k, lane);
+    int ph = (4 * (k0 + lane) - fill) % 5;  // the phase advances by 128 % 5 = 3 from one of a lane's words to the next
+    for (int q = k0 + lane; q < kend; q += 32) {
+        stage_w[q] = patw[k][ph];
+        ph = ph >= 2 ? ph - 2 : ph + 3;
+    }
+    if (lane < ((fill + 5 * n) & 3)) stage[4 * kend + lane] = special_char(k, (4 * kend + lane - fill) % 5);
+}
 
 __global__ void __launch_bounds__(kDecWarps * 32)
 decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t rows, int64_t cols, int64_t row_stride,
@@ -1107,8 +1169,9 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
                     uint8_t *__restrict__ chars) {
     __shared__ uint16_t inv[512];
     __shared__ __align__(16) uint8_t stage_all[kDecWarps][kDecStage];
-    __shared__ uint32_t patw[3][8];  // patw[k][ph]: four bytes of special k's text repeated, starting at phase ph
+    __shared__ uint32_t patw[4][8];  // patw[k][ph]: four bytes of special k's text repeated, starting at phase ph
     for (int i = threadIdx.x; i < 512; i += kDecWarps * 32) inv[i] = invp.e[i];
+    if (threadIdx.x >= 32 && threadIdx.x < 40) patw[3][threadIdx.x - 32] = 0u;  // (kind 3 does not exist; keeps stray look-ups defined)
     if (threadIdx.x < 15) {
         const int k = threadIdx.x / 5, ph = threadIdx.x % 5;
         uint32_t w = 0;
@@ -1139,15 +1202,21 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
             if (rows16 && c0 + 512 <= cols) {
                 const uint4 x = *reinterpret_cast<const uint4 *>(rp + c0 + 16 * lane);
                 const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-                uint32_t w[4], any = 0;
+                uint32_t ee[16], any = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    const uint32_t e0 = inv[(xs[k] & 0xffu) + 128], e1 = inv[__byte_perm(xs[k], 0, 0x4441) + 128],
-                                   e2 = inv[__byte_perm(xs[k], 0, 0x4442) + 128], e3 = inv[(xs[k] >> 24) + 128];
-                    any |= e0 | e1 | e2 | e3;
-                    w[k] = __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
+                    ee[4 * k + 0] = inv[(xs[k] & 0xffu) + 128];
+                    ee[4 * k + 1] = inv[__byte_perm(xs[k], 0, 0x4441) + 128];
+                    ee[4 * k + 2] = inv[__byte_perm(xs[k], 0, 0x4442) + 128];
+                    ee[4 * k + 3] = inv[(xs[k] >> 24) + 128];
+                    any |= ee[4 * k] | ee[4 * k + 1] | ee[4 * k + 2] | ee[4 * k + 3];
                 }
+                const uint32_t x0 = __shfl_sync(0xffffffffu, x.x, 0);
                 if (!__any_sync(0xffffffffu, (any & 0x100u) != 0)) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        w[k] = __byte_perm(__byte_perm(ee[4 * k], ee[4 * k + 1], 0x0040), __byte_perm(ee[4 * k + 2], ee[4 * k + 3], 0x0040), 0x5410);
                     const int r8 = (fill & 3) * 8, kw = fill >> 2;
                     uint32_t lo = __shfl_up_sync(0xffffffffu, w[3], 1);
                     if (lane == 0) lo = r8 ? stage_w[kw] << (32 - r8) : 0u;
@@ -1158,9 +1227,14 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
                     d[3] = __funnelshift_l(w[2], w[3], r8);
                     if (lane == 31 && r8) d[4] = w[3] >> (32 - r8);
                     total = 512;
-                    step = 512;
-                    done = true;
+                } else if (__all_sync(0xffffffffu, x.x == x0 && x.x == __byte_perm(x.x, 0, 0x0000) && x.y == x.x && x.z == x.x && x.w == x.x)) {
+                    decode_fill_special(static_cast<int>(ee[0] & 3u), 512, patw, stage, fill, lane);
+                    total = 2560;
+                } else {
+                    total = decode_word_step<16>(ee, patw, stage_w, fill, lane);
                 }
+                step = 512;
+                done = true;
             }
             if (!done && fast && c0 + 128 <= cols) {
                 const uint32_t x = *reinterpret_cast<const uint32_t *>(rp + c0 + 4 * lane);
@@ -1178,13 +1252,12 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
                     total = 128;
                     done = true;
                 } else if (__all_sync(0xffffffffu, x == x0 && x == __byte_perm(x, 0, 0x0000))) {
-                    // 128 x the same special: bytes fill .. fill+640 of the stage repeat its five characters
-                    const int k = static_cast<int>(e0 & 3u);
-                    const int k0 = (fill + 3) >> 2, kend = (fill + 640) >> 2;
-                    if (lane < 4 * k0 - fill) stage[fill + lane] = special_char(k, lane);
-                    for (int q = k0 + lane; q < kend; q += 32) stage_w[q] = patw[k][(4 * q - fill) % 5];
-                    if (lane < ((fill + 640) & 3)) stage[4 * kend + lane] = special_char(k, (4 * kend + lane - fill) % 5);
+                    decode_fill_special(static_cast<int>(e0 & 3u), 128, patw, stage, fill, lane);
                     total = 640;
+                    done = true;
+                } else {
+                    const uint32_t ee[4] = {e0, e1, e2, e3};
+                    total = decode_word_step<4>(ee, patw, stage_w, fill, lane);
                     done = true;
                 }
             }
@@ -1217,13 +1290,13 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
             __syncwarp();
             fill += total;
             const int nfull = fill >> 4;
-            for (int vv = lane; vv < nfull; vv += 32) {
-                if (vv == 0 && head > 0) {  // first vector of the row: bytes [0, head) belong to the previous row
-                    for (int i = head; i < 16; ++i) gal[i] = stage[i];
-                } else {
-                    *reinterpret_cast<uint4 *>(gal + 16 * vv) = *reinterpret_cast<const uint4 *>(stage + 16 * vv);
-                }
+            int vfirst = lane;
+            if (head > 0 && nfull > 0) {  // first vector of the row: bytes [0, head) belong to the previous row
+                if (lane >= head && lane < 16) gal[lane] = stage[lane];
+                if (lane == 0) vfirst = 32;
             }
+            for (int vv = vfirst; vv < nfull; vv += 32)
+                *reinterpret_cast<uint4 *>(gal + 16 * vv) = *reinterpret_cast<const uint4 *>(stage + 16 * vv);
             if (nfull > 0) head = 0;
             const int rest = fill & 15;
             uint8_t keep = 0;
