@@ -15,6 +15,7 @@
 #include <cstring>
 #include <functional>
 #include <mutex>
+#include <pthread.h>
 #include <string>
 #include <thread>
 #include <vector>
@@ -48,8 +49,15 @@ namespace {
 class Pool {
 public:
     static Pool &get() {
-        static Pool *p = new Pool();  // leaked: worker threads must not be torn down under a running job at exit
-        return *p;
+        // leaked: worker threads must not be torn down under a running job at exit.  After fork() the child has
+        // none of the parent's threads, so it starts over with an empty pool (a forked DataLoader worker that only
+        // walks items would otherwise wait for workers that do not exist).
+        static std::once_flag once;
+        std::call_once(once, [] {
+            instance() = new Pool();
+            pthread_atfork(nullptr, nullptr, [] { instance() = new Pool(); });
+        });
+        return *instance();
     }
     // run fn(t) for t in [0, nt) on pool threads; returns at once.  Pair with wait().
     void start(int nt, std::function<void(int)> fn) {
@@ -76,6 +84,10 @@ public:
     }
 
 private:
+    static Pool *&instance() {
+        static Pool *p = nullptr;
+        return p;
+    }
     void loop(int id) {
         uint64_t seen = 0;
         for (;;) {

@@ -192,3 +192,27 @@ def test_parallel_for_runs_every_share_once():
             assert 1 <= nt <= nthreads           # capped at half the hardware threads
             assert sorted(seen) == [(t, nt) for t in range(nt)]
     assert L.bsq_parallel_for(2, None, None) == capi.ERR_ARG
+
+
+@pytest.mark.filterwarnings("ignore::DeprecationWarning")
+def test_parallel_for_after_fork():
+    # a forked child has none of the parent's pool threads: it must start its own instead of waiting for them
+    import os
+    L = capi.lib()
+    CB = C.CFUNCTYPE(None, C.c_int, C.c_int, C.c_void_p)
+    hits = []
+    cb = CB(lambda t, nt, ctx: hits.append(t))
+    assert L.bsq_parallel_for(4, C.cast(cb, C.c_void_p), None) == 0      # parent's pool exists now
+    pid = os.fork()
+    if pid == 0:
+        ok = 1
+        try:
+            import signal
+            signal.alarm(20)                                            # a deadlock ends the child, not the test run
+            hits.clear()
+            if L.bsq_parallel_for(4, C.cast(cb, C.c_void_p), None) == 0 and sorted(hits) == list(range(len(hits))) and hits:
+                ok = 0
+        finally:
+            os._exit(ok)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
