@@ -986,11 +986,15 @@ decode_len_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t rows
     }
 }
 
-// pass 1, lean form for one-byte tokens in 16-byte aligned rows whose length is a multiple of 16 (what
-// batch_tokenize itself produces): 16 tokens per lane and load, a 256-entry class table (0 = one character,
-// 1 = five-character special, 0x100 = no entry) summed per vector -- 2.5 instructions per token instead of 31
-// (profiles/r01e: the general kernel was issue-bound at 0.78 TB/s).  A row that holds a token without an
-// entry (the error path) is rescanned for the exact position.
+// pass 1, lean form for one-byte tokens that are contiguous along the row (any row alignment, any length): 16
+// tokens per lane and load over the aligned 16-byte vectors that cover the row, a 256-entry class table (0 = one
+// character, 1 = five-character special, 0x100 = no entry) summed per vector -- 2.5 instructions per token instead
+// of 31 (profiles/r01e: the general kernel was issue-bound at 0.78 TB/s).  Bytes of the first / last vector that lie
+// outside the row are replaced by token 0, which is a plain character in every alphabet.  A row that holds a token
+// without an entry (the error path) is rescanned for the exact position.
+// ANYALIGN = false: rows are 16-byte aligned and a multiple of 16 long (what batch_tokenize produces for such padlens):
+// the shifts and masks fold away.
+template <bool ANYALIGN>
 __global__ void __launch_bounds__(kDecWarps * 32)
 decode_len16_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t cols, int64_t row_stride, InvParam invp,
                     int64_t *__restrict__ row_len, unsigned long long *first_bad) {
@@ -1003,14 +1007,25 @@ decode_len16_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t co
     const int lane = threadIdx.x & 31;
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * kDecWarps + (threadIdx.x >> 5);
     const int64_t GW = static_cast<int64_t>(gridDim.x) * kDecWarps;
-    const int64_t nvec = cols >> 4;
     for (int64_t r = gw; r < rows; r += GW) {
-        const uint4 *rp = reinterpret_cast<const uint4 *>(tokens + r * row_stride);
+        const uint8_t *rb = tokens + r * row_stride;
+        const int a = ANYALIGN ? static_cast<int>(reinterpret_cast<uintptr_t>(rb) & 15u) : 0;
+        const uint4 *rp = reinterpret_cast<const uint4 *>(rb - a);
+        const int64_t nvec = (a + cols + 15) >> 4;
+        const int ktail = ANYALIGN ? static_cast<int>(a + cols - 16 * (nvec - 1)) : 16;  // bytes of the last vector that belong to the row
         uint32_t specials = 0, bad = 0;
 #pragma unroll 2
         for (int64_t v = lane; v < nvec; v += 32) {
             const uint4 x = __ldcs(rp + v);
-            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+            uint32_t w[4] = {x.x, x.y, x.z, x.w};
+            if (v == 0 && a != 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[k] &= ~lt_mask(a, k);
+            }
+            if (v == nvec - 1 && ktail != 16) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) w[k] &= lt_mask(ktail, k);
+            }
             uint32_t sum = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -1020,7 +1035,6 @@ decode_len16_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t co
         }
         for (int o = 16; o > 0; o >>= 1) specials += __shfl_xor_sync(0xffffffffu, specials, o);
         if (__any_sync(0xffffffffu, bad != 0)) {
-            const uint8_t *rb = tokens + r * row_stride;
             unsigned long long b = ~0ull;
             for (int64_t c = lane; c < cols; c += 32)
                 if (cls[rb[c]] & 0x100) {
@@ -1106,6 +1120,17 @@ constexpr int kDecStage = 16 + 512 * 5 + 48;  // carry + the longest step (512 s
 // closes that word with its first 4 - (k & 3) characters and opens the next one with the remaining (k & 3) + 1; a
 // plain character at byte 3 closes the word.  Word offsets come from one warp scan; the stream is shifted by the
 // carry (fill & 3 bytes) with one funnel shift per word.  Returns the number of bytes appended to the stage.
+// bytes [a, a + 16) of the 32 bytes v:n (a = 1..15, warp-uniform)
+__device__ __forceinline__ uint4 shift16(const uint4 &v, const uint4 &n, int a) {
+    const uint32_t sh = static_cast<uint32_t>(a & 3) * 8u;
+    switch (a >> 2) {
+        case 0: return make_uint4(__funnelshift_r(v.x, v.y, sh), __funnelshift_r(v.y, v.z, sh), __funnelshift_r(v.z, v.w, sh), __funnelshift_r(v.w, n.x, sh));
+        case 1: return make_uint4(__funnelshift_r(v.y, v.z, sh), __funnelshift_r(v.z, v.w, sh), __funnelshift_r(v.w, n.x, sh), __funnelshift_r(n.x, n.y, sh));
+        case 2: return make_uint4(__funnelshift_r(v.z, v.w, sh), __funnelshift_r(v.w, n.x, sh), __funnelshift_r(n.x, n.y, sh), __funnelshift_r(n.y, n.z, sh));
+        default: return make_uint4(__funnelshift_r(v.w, n.x, sh), __funnelshift_r(n.x, n.y, sh), __funnelshift_r(n.y, n.z, sh), __funnelshift_r(n.z, n.w, sh));
+    }
+}
+
 // "<BOS" / "<EOS" / "<PAD" as a little-endian word (registers, no table look-up)
 __device__ __forceinline__ uint32_t special_word(uint32_t entry) {
     const uint32_t k = entry & 3u;
@@ -1186,6 +1211,7 @@ __device__ __forceinline__ void decode_fill_special(int k, int n, const uint32_t
     if (lane < ((fill + 5 * n) & 3)) stage[4 * kend + lane] = special_char(k, (4 * kend + lane - fill) % 5);
 }
 
+template <bool ANYALIGN>  // false: every row is 16-byte aligned (the realignment folds away)
 __global__ void __launch_bounds__(kDecWarps * 32)
 decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t rows, int64_t cols, int64_t row_stride,
                     int64_t col_stride, int fast, InvParam invp, const int64_t *__restrict__ row_offs,
@@ -1205,11 +1231,11 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *stage = stage_all[warp];
     uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage);
-    const bool rows16 = fast == 2;  // rows are 16-byte aligned: 16 tokens per lane where a whole 512-token step is plain text
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * kDecWarps + warp;
     const int64_t GW = static_cast<int64_t>(gridDim.x) * kDecWarps;
     for (int64_t r = gw; r < rows; r += GW) {
         const uint8_t *rp = tokens + r * row_stride;
+        const int ra = ANYALIGN ? static_cast<int>(reinterpret_cast<uintptr_t>(rp) & 15u) : 0;  // the row's misalignment: loads are aligned, tokens are shifted into place
         uint8_t *dst = chars + row_offs[r];
         int fill = static_cast<int>(reinterpret_cast<uintptr_t>(dst) & 15u);  // bytes of the stage in front of the data
         uint8_t *gal = dst - fill;                                             // aligned address of stage[0]
@@ -1222,8 +1248,15 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
             // Steps of plain text or of one repeated special (the <PAD> run behind a sequence) -- nearly all of
             // them -- are laid into the stage as whole 32-bit words shifted by the carry (fill & 3 bytes):
             // one shuffle and one funnel shift per word instead of a scan and a byte store per character.
-            if (rows16 && c0 + 512 <= cols) {
-                const uint4 x = *reinterpret_cast<const uint4 *>(rp + c0 + 16 * lane);
+            if (fast && c0 + 512 <= cols) {
+                uint4 x = *reinterpret_cast<const uint4 *>(rp - ra + c0 + 16 * lane);
+                if (ra != 0) {  // (warp-uniform) tokens of this lane: bytes [ra, ra + 16) of its vector and the next one
+                    uint4 nx;
+                    nx.x = __shfl_down_sync(0xffffffffu, x.x, 1); nx.y = __shfl_down_sync(0xffffffffu, x.y, 1);
+                    nx.z = __shfl_down_sync(0xffffffffu, x.z, 1); nx.w = __shfl_down_sync(0xffffffffu, x.w, 1);
+                    if (lane == 31) nx = *reinterpret_cast<const uint4 *>(rp - ra + c0 + 512);
+                    x = shift16(x, nx, ra);
+                }
                 const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
                 uint32_t ee[16], any = 0;
 #pragma unroll
@@ -1260,7 +1293,12 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
                 done = true;
             }
             if (!done && fast && c0 + 128 <= cols) {
-                const uint32_t x = *reinterpret_cast<const uint32_t *>(rp + c0 + 4 * lane);
+                uint32_t x = *reinterpret_cast<const uint32_t *>(rp - (ra & 3) + c0 + 4 * lane);
+                if (ra & 3) {
+                    uint32_t nx = __shfl_down_sync(0xffffffffu, x, 1);
+                    if (lane == 31) nx = *reinterpret_cast<const uint32_t *>(rp - (ra & 3) + c0 + 128);
+                    x = __funnelshift_r(x, nx, 8 * (ra & 3));
+                }
                 const uint32_t e0 = inv[(x & 0xffu) + 128], e1 = inv[__byte_perm(x, 0, 0x4441) + 128],
                                e2 = inv[__byte_perm(x, 0, 0x4442) + 128], e3 = inv[(x >> 24) + 128];
                 const bool sp_here = ((e0 | e1 | e2 | e3) & 0x100u) != 0;
@@ -1286,7 +1324,7 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
             }
             if (!done) {
                 uint32_t e[4];
-                decode_fetch4(rp, itemsize, col_stride, c0 + 4 * lane, cols, inv, fast != 0, e);
+                decode_fetch4(rp, itemsize, col_stride, c0 + 4 * lane, cols, inv, fast != 0 && (ra & 3) == 0, e);
                 int mylen = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) mylen += e[k] >= 0xFFFEu ? 0 : ((e[k] & 0x100u) ? 5 : 1);
@@ -1541,13 +1579,9 @@ int launch_sf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t ld, int64
     return BSQ_OK;
 }
 
-// one-byte tokens, contiguous along the row: 1 = every row 4-byte aligned (four tokens per 32-bit load),
-// 2 = every row 16-byte aligned (sixteen tokens per 128-bit load where a step allows it)
-int decode_fast_path(const void *d_tokens, int itemsize, int64_t row_stride, int64_t col_stride) {
-    if (itemsize != 1 || col_stride != 1) return 0;
-    const uintptr_t a = reinterpret_cast<uintptr_t>(d_tokens);
-    if (row_stride % 16 == 0 && (a & 15u) == 0) return 2;
-    return row_stride % 4 == 0 && (a & 3u) == 0;
+// one-byte tokens, contiguous along the row (any alignment: the kernels load aligned words and shift)
+int decode_fast_path(const void * /*d_tokens*/, int itemsize, int64_t /*row_stride*/, int64_t col_stride) {
+    return itemsize == 1 && col_stride == 1;
 }
 unsigned decode_grid(int64_t rows, int ctas_per_sm = 8) {  // persistent: one warp per row, rows dealt round-robin
     return static_cast<unsigned>(std::min<int64_t>((rows + kDecWarps - 1) / kDecWarps, 148 * ctas_per_sm));
@@ -1702,8 +1736,12 @@ int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int items
     BSQ_CUDA_TRY(cudaMemsetAsync(d_work, 0xff, sizeof(int64_t), st));
     const InvParam inv = make_inv(*tok);
     const int fast = decode_fast_path(d_tokens, itemsize, row_stride, col_stride);
-    if (fast == 2 && cols % 16 == 0)
-        decode_len16_kernel<<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
+    const bool rows16 = (reinterpret_cast<uintptr_t>(d_tokens) & 15u) == 0 && row_stride % 16 == 0;
+    if (fast && rows16 && cols % 16 == 0)
+        decode_len16_kernel<false><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
+            static_cast<const uint8_t *>(d_tokens), rows, cols, row_stride, inv, d_row_offsets, reinterpret_cast<unsigned long long *>(d_work));
+    else if (fast)
+        decode_len16_kernel<true><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
             static_cast<const uint8_t *>(d_tokens), rows, cols, row_stride, inv, d_row_offsets, reinterpret_cast<unsigned long long *>(d_work));
     else
         decode_len_kernel<<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
@@ -1740,9 +1778,15 @@ int bsq_decode_chars(int device, void *stream, const void *d_tokens, int itemsiz
     BSQ_CUDA_TRY(cudaSetDevice(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const InvParam inv = make_inv(*tok);
-    decode_chars_kernel<<<decode_grid(rows), kDecWarps * 32, 0, st>>>(  // (a grid of only the 4 resident CTAs per SM measured slower: 470 vs 442 us)
-        static_cast<const uint8_t *>(d_tokens), itemsize, rows, cols, row_stride, col_stride,
-        decode_fast_path(d_tokens, itemsize, row_stride, col_stride), inv, d_row_offsets, d_chars);
+    const int fast = decode_fast_path(d_tokens, itemsize, row_stride, col_stride);
+    const bool rows16 = (reinterpret_cast<uintptr_t>(d_tokens) & 15u) == 0 && row_stride % 16 == 0;
+    // (a grid of only the 4 resident CTAs per SM measured slower: 470 vs 442 us)
+    if (fast && rows16)
+        decode_chars_kernel<false><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
+            static_cast<const uint8_t *>(d_tokens), itemsize, rows, cols, row_stride, col_stride, fast, inv, d_row_offsets, d_chars);
+    else
+        decode_chars_kernel<true><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
+            static_cast<const uint8_t *>(d_tokens), itemsize, rows, cols, row_stride, col_stride, fast, inv, d_row_offsets, d_chars);
     count_launch();
     BSQ_CUDA_TRY(cudaGetLastError());
     return BSQ_OK;
