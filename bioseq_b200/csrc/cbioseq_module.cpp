@@ -57,6 +57,13 @@ py::ssize_t get_num_threads() {
 void set_num_threads(py::ssize_t n) {
     if (n > 0) g_num_threads = static_cast<int>(n);
 }
+// Host threads for the pack / walk of a batch call.  The reference's `nthreads` sizes its OpenMP team and defaults to 1
+// (src/tokenize.cpp:65,82); here the GPU does the work the team did, and the argument only sizes the host-side gather.
+// An explicit value > 1 is honoured; the default (1, or anything <= 1) means "not specified" and uses the module-wide
+// setting (set_num_threads / Threading, src/omp.cpp:43-49; all hardware threads when unset).  libbsq caps its pool at
+// half the hardware threads either way.  Results do not depend on it.
+int host_threads(int nthreads) { return nthreads > 1 ? nthreads : static_cast<int>(get_num_threads()); }
+
 struct Threading {
     explicit Threading(py::ssize_t n = -1) { set_num_threads(n); }
     py::ssize_t get() const { return get_num_threads(); }
@@ -423,6 +430,7 @@ public:
             return run_flatfile(batch.cast<const FlatFile &>(), 0, py::none(), py::none(), padlen, dc, kind, false, batch_first, device);
         if (padlen <= 0) throw py::value_error("batch tokenize requires padlen is provded.");
         Unpacked u;
+        nthreads = host_threads(nthreads);
         unpack_items(batch, u, nthreads);
         return run_host(u.ptrs.data(), u.lens.data(), static_cast<int64_t>(u.lens.size()), nullptr, padlen, dc, kind,
                         /*onehot=*/false, batch_first, nthreads, device);
@@ -438,6 +446,7 @@ public:
             return run_flatfile(batch.cast<const FlatFile &>(), 0, py::none(), mask, padlen, dc, kind, true, false, device);
         if (padlen <= 0) throw py::value_error("batch tokenize requires padlen is provded.");
         Unpacked u;
+        nthreads = host_threads(nthreads);
         unpack_items(batch, u, nthreads);
         // mask: a list with one uint8 array per sequence; entries that are not arrays mean
         // "no mask for this sequence" (getmaskptr, src/tokenize.h:372-380).
