@@ -772,7 +772,10 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads)
+// TPC: position tiles per CTA (1, or 2 neighbouring ones): the second tile reuses the LUT, the tail table and the
+// resolved sequences (its windows start 128 bytes further), so the prologue and its offsets round trip are paid once.
+template <int TPC>
+__global__ void __launch_bounds__(kThreads, 6)
 seqfirst_tok8_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, FastDiv div_ptiles, LutParam lutp, Specials sp,
                      uint8_t *__restrict__ out) {
     __shared__ __align__(16) uint8_t lut[256];
@@ -785,7 +788,7 @@ seqfirst_tok8_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, FastDiv di
     // 32-byte sectors that two neighbouring windows share are still in L2 when the second one asks
     const uint32_t st = fd_div(blockIdx.x, div_ptiles);
     const int64_t i0 = static_cast<int64_t>(st) * kTileSeqs;
-    const int p0 = static_cast<int>(blockIdx.x - st * div_ptiles.d) * kTilePos;
+    const int p00 = static_cast<int>(blockIdx.x - st * div_ptiles.d) * (TPC * kTilePos);  // div_ptiles: groups of TPC position tiles
     const int nseq_tile = static_cast<int>(min(static_cast<int64_t>(kTileSeqs), nseq - i0));
     load_lut(lut, lutp);
     init_tailtab(tab, sp);
@@ -796,17 +799,21 @@ seqfirst_tok8_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, FastDiv di
         if (il < nseq_tile) {
             const int64_t start = __ldg(v.offs + i0 + il);
             n = sp.bos + static_cast<int>(__ldg(v.offs + i0 + il + 1) - start);
-            a = reinterpret_cast<uintptr_t>(v.bytes + (start - sp.bos + p0));
+            a = reinterpret_cast<uintptr_t>(v.bytes + (start - sp.bos + p00));
         }
         rinfo[il] = make_int4(n, static_cast<int>(a & 15u), static_cast<int>(static_cast<uint32_t>(a & ~static_cast<uintptr_t>(15))),
                               static_cast<int>(static_cast<uint32_t>(a >> 32)));
     }
     __syncthreads();
 
-    // ---- phase 0: lane (il, q) copies 16-byte word q (and lane q == 0 word 8) of sequence il's window ----
     const int q = tid & 7;
-    const int c0 = p0 + 16 * q;  // first column of this thread's chunks
     const uint32_t stage_s = smem_u32(stage) + static_cast<uint32_t>(tid >> 3) * kStagePitch;
+#pragma unroll 1
+    for (int tp = 0; tp < TPC; ++tp) {
+    const int p0 = p00 + tp * kTilePos;
+    if (TPC > 1 && p0 >= padlen) break;
+    // ---- phase 0: lane (il, q) copies 16-byte word q (and lane q == 0 word 8) of sequence il's window ----
+    const int c0 = p0 + 16 * q;  // first column of this thread's chunks
     int nn[4], sh[4];
     int4 ris[4];
 #pragma unroll
@@ -819,7 +826,7 @@ seqfirst_tok8_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, FastDiv di
         // stage offsets [olo, ohi) hold the residues under this tile (columns max(bos, p0) .. min(n, p0 + 128))
         const int olo = ri.y + max(sp.bos - p0, 0), ohi = ri.y + min(ri.x - p0, kTilePos);
         const uint8_t *src = reinterpret_cast<const uint8_t *>((static_cast<uint64_t>(static_cast<uint32_t>(ri.w)) << 32) |
-                                                               static_cast<uint32_t>(ri.z));
+                                                               static_cast<uint32_t>(ri.z)) + tp * kTilePos;
         const uint32_t dst = stage_s + static_cast<uint32_t>(32 * u) * kStagePitch + 16u * q;
         if (16 * q < ohi && 16 * q + 16 > olo) cp_async16(dst, src + 16 * q);
         if (q == 0 && ohi > kTilePos) cp_async16(dst + kTilePos, src + kTilePos);
@@ -888,6 +895,8 @@ seqfirst_tok8_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, FastDiv di
                     if (k < nvalid) o[k] = static_cast<uint8_t>(y[k >> 2][j] >> (8 * (k & 3)));
             }
         }
+    }
+    if (TPC > 1 && tp + 1 < TPC) __syncthreads();  // the tile is rewritten by the next position tile
     }
 }
 
@@ -1560,7 +1569,10 @@ int launch_sf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t ld, int64
         if (sizeof(T) == 1 && aligned && ld % 16 == 0 && tok.pad_id < 0x80) {
             if (env_int("BSQ_SF_OLD", 0)) BSQ_SF(kTokFast);
             else if (gx * gy > 0x7fffffffll) return fail(BSQ_ERR_ARG, "batch too large for one launch");
-            else seqfirst_tok8_kernel<<<static_cast<unsigned>(gx * gy), kThreads, 0, st>>>(
+            else if (env_int("BSQ_SF_TPC", 2) == 2 && gy % 2 == 0 && gx * gy / 2 >= 8ll * 148 * 6)  // enough CTAs left to balance 888 resident slots
+                seqfirst_tok8_kernel<2><<<static_cast<unsigned>(gx * gy / 2), kThreads, 0, st>>>(
+                    v, nseq, ld, pl, make_fastdiv(static_cast<uint32_t>(gy / 2)), p.lut, p.sp, reinterpret_cast<uint8_t *>(o));
+            else seqfirst_tok8_kernel<1><<<static_cast<unsigned>(gx * gy), kThreads, 0, st>>>(
                     v, nseq, ld, pl, make_fastdiv(static_cast<uint32_t>(gy)), p.lut, p.sp, reinterpret_cast<uint8_t *>(o));
         }
         else BSQ_SF(kTokGeneric);
