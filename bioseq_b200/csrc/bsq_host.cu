@@ -391,8 +391,8 @@ int stage_begin(bsq_stager *s, const RunArgs &a) {
 }
 
 // End of the staged range that starts at sequence i0: whole 128-sequence groups holding ~kChunkBytes of residues.
-int64_t range_end(const int64_t *h_offs, int64_t nseq, int64_t i0) {
-    const int64_t want = h_offs[i0] + static_cast<int64_t>(kChunkBytes);
+int64_t range_end(const int64_t *h_offs, int64_t nseq, int64_t i0, size_t chunk = kChunkBytes) {
+    const int64_t want = h_offs[i0] + static_cast<int64_t>(chunk);
     int64_t i1 = std::upper_bound(h_offs + i0, h_offs + nseq + 1, want) - h_offs - 1;
     i1 = std::max(i1, i0 + 1);
     return std::min(nseq, (i1 + kSeqAlign - 1) / kSeqAlign * kSeqAlign);
@@ -449,9 +449,16 @@ int staged_run(bsq_stager *s, cudaStream_t st, const uint8_t *h_bytes, const int
     a.pin_b = is_pinned(h_bytes);
     a.pin_m = h_mask && is_pinned(h_mask);
     if (int rc = stage_begin(s, a)) return rc;
+    // Range size.  The call costs copy time + the kernel of the last range + a few microseconds per copy: small
+    // outputs (narrow tokens: the whole batch's kernel is a few % of its copy) do best with few large ranges from a
+    // pinned source, expanding outputs (one-hot, wide types) and bounced pageable sources with 4 MiB ones.
+    static const long env_mib = std::getenv("BSQ_CHUNK_MIB") ? std::atol(std::getenv("BSQ_CHUNK_MIB")) : 0;
+    size_t chunk = kChunkBytes;
+    if (a.pin_b && !h_mask && !onehot && bsq_kind_size(kind) <= 2) chunk = size_t(32) << 20;  // 35 MB batch, pipelined calls: 4 MiB 0.707 ms, 16 MiB 0.689, 32 MiB 0.674, one range 0.681 (raw copy 0.650)
+    if (env_mib > 0) chunk = static_cast<size_t>(env_mib) << 20;
     size_t nchunk = 0;
     for (int64_t i0 = 0; i0 < nseq;) {
-        const int64_t i1 = range_end(h_offs, nseq, i0);
+        const int64_t i1 = range_end(h_offs, nseq, i0, chunk);
         if (int rc = stage_range(s, a, i0, i1, nchunk++)) return rc;
         i0 = i1;
     }
