@@ -16,6 +16,7 @@
 #include <functional>
 #include <mutex>
 #include <pthread.h>
+#include <sched.h>
 #include <string>
 #include <thread>
 #include <vector>
@@ -116,7 +117,12 @@ private:
 // threads (measured on the 16-core B200 host: 8 workers 1.31 ms per 65536-sequence batch, 16 workers 1.93 ms --
 // the submitting thread needs a core of its own and the copies saturate the memory system well before that).
 inline int pool_threads(int wanted) {
-    static const int cap = std::max(1u, std::thread::hardware_concurrency() / 2);
+    static const int cap = [] {
+        cpu_set_t set;  // the CPUs this process may run on (a container's cpuset), not the machine's
+        CPU_ZERO(&set);
+        const int n = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : static_cast<int>(std::thread::hardware_concurrency());
+        return std::max(1, n / 2);
+    }();
     return std::max(1, std::min(std::min(wanted, cap), 64));
 }
 
