@@ -1277,21 +1277,36 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
                     any |= ee[4 * k] | ee[4 * k + 1] | ee[4 * k + 2] | ee[4 * k + 3];
                 }
                 const uint32_t x0 = __shfl_sync(0xffffffffu, x.x, 0);
-                if (!__any_sync(0xffffffffu, (any & 0x100u) != 0)) {
+                // plain text, possibly behind ONE special in the very first position (the BOS that opens a row): that
+                // special is one extra word in front ("<BOS") and its '>' takes the first byte of lane 0's first word
+                uint32_t any_rest = any;
+                if (lane == 0)
+                    any_rest = ee[1] | ee[2] | ee[3] | ee[4] | ee[5] | ee[6] | ee[7] | ee[8] | ee[9] | ee[10] | ee[11] | ee[12] | ee[13] | ee[14] | ee[15];
+                if (!__any_sync(0xffffffffu, (any_rest & 0x100u) != 0)) {
+                    const uint32_t e00 = __shfl_sync(0xffffffffu, ee[0], 0);
+                    const int lead = (e00 & 0x100u) ? 1 : 0;  // warp-uniform
                     uint32_t w[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         w[k] = pack4(ee[4 * k], ee[4 * k + 1], ee[4 * k + 2], ee[4 * k + 3]);
                     const int r8 = (fill & 3) * 8, kw = fill >> 2;
                     uint32_t lo = __shfl_up_sync(0xffffffffu, w[3], 1);
-                    if (lane == 0) lo = r8 ? stage_w[kw] << (32 - r8) : 0u;
-                    uint32_t *d = stage_w + kw + 4 * lane;
+                    if (lane == 0) {
+                        lo = r8 ? stage_w[kw] << (32 - r8) : 0u;
+                        if (lead) {
+                            const uint32_t P = special_word(e00);
+                            stage_w[kw] = __funnelshift_l(lo, P, r8);
+                            lo = P;
+                            w[0] = (w[0] & 0xffffff00u) | 0x3eu;
+                        }
+                    }
+                    uint32_t *d = stage_w + kw + lead + 4 * lane;
                     d[0] = __funnelshift_l(lo, w[0], r8);
                     d[1] = __funnelshift_l(w[0], w[1], r8);
                     d[2] = __funnelshift_l(w[1], w[2], r8);
                     d[3] = __funnelshift_l(w[2], w[3], r8);
                     if (lane == 31 && r8) d[4] = w[3] >> (32 - r8);
-                    total = 512;
+                    total = 512 + 4 * lead;
                 } else if (__all_sync(0xffffffffu, x.x == x0 && x.x == __byte_perm(x.x, 0, 0x0000) && x.y == x.x && x.z == x.x && x.w == x.x)) {
                     decode_fill_special(static_cast<int>(ee[0] & 3u), 512, patw, stage, fill, lane);
                     total = 2560;

@@ -538,6 +538,14 @@ def test_decode_fast_steps_every_alignment(cols, row_pad, shift):
     a[0] = 22
     a[1] = 3
     a[2, :] = np.arange(cols) % 20
+    a[3, :] = (np.arange(cols) * 7) % 20            # one special in the very first position, then plain text
+    a[3, 0] = 20
+    a[4, :] = (np.arange(cols) * 3) % 20            # ... then text, EOS and a PAD run
+    a[4, 0] = 20
+    a[4, cols // 2] = 21
+    a[4, cols // 2 + 1:] = 22
+    a[5, :] = 22                                    # specials only, two kinds
+    a[5, ::2] = 21
     want = orc.decode_tokens(a)
     assert want[0] == "<PAD>" * cols and want[1] == "E" * cols
     flat = torch.zeros(rows * (cols + row_pad) + 64, dtype=torch.uint8, device="cuda")
