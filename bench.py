@@ -262,7 +262,7 @@ def run_ours(args):
 
     sections = set(args.sections.split(","))
     e2e_steps = max(3, min(args.steps, 50)) if "e2e" in sections else 1
-    for i in range(3 if "e2e" in sections else 0):
+    for i in range(2 * ROT if "e2e" in sections else 0):   # every pinned set goes through the link once before timing
         e2e_step(i)
     # three back-to-back repeats of the same K-step region; the median repeat is reported (a host hiccup --
     # page-locking, another tenant of the box -- inside one repeat would otherwise decide the number)
