@@ -6,6 +6,10 @@
 // src/tokenize.h:386-419 (transencode) / :289-322 (one-hot); the caller-side
 // `torch.from_numpy(arr).to(device)` (bioseq/loaders.py:84) is what the staging replaces.
 #include <cuda_runtime.h>
+#if defined(__x86_64__)
+#include <cpuid.h>
+#include <immintrin.h>  // _mm_sfence
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -124,6 +128,35 @@ inline int pool_threads(int wanted) {
         return std::max(1, n / 2);
     }();
     return std::max(1, std::min(std::min(wanted, cap), 64));
+}
+
+// Write the cache lines of [p, p + n) back to memory (clwb keeps them valid in the cache); no-op without clwb.
+// The gathered bytes are read next by the DMA engine, and lines still dirty in the cores' caches slow that read
+// down: without the write-back the last copy of a gathered 35 MB batch finished ~1 ms after it was issued (device done
+// 2.0 ms after the call started, vs 1.45 ms with it; non-temporal stores also fix the lag but make the gather 2x slower).
+inline bool have_clwb() {
+#if defined(__x86_64__)
+    static const bool ok = [] {
+        unsigned a, b, c, d;
+        if (!__get_cpuid_count(7, 0, &a, &b, &c, &d)) return false;
+        return ((b >> 24) & 1u) != 0 && std::getenv("BSQ_NO_CLWB") == nullptr;
+    }();
+    return ok;
+#else
+    return false;
+#endif
+}
+inline void writeback_lines(const uint8_t *p, size_t n) {
+#if defined(__x86_64__)
+    if (n == 0 || !have_clwb()) return;
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p) & ~uintptr_t(63), hi = reinterpret_cast<uintptr_t>(p) + n;
+    for (uintptr_t a = lo; a < hi; a += 64) asm volatile("clwb (%0)" ::"r"(a) : "memory");
+#endif
+}
+inline void copy_fence() {
+#if defined(__x86_64__)
+    _mm_sfence();
+#endif
 }
 
 inline void spin_until(const std::function<bool()> &ready) {
@@ -359,10 +392,14 @@ int stage_copy(bsq_stager *s, void *dst, const void *src, size_t n, bool src_pin
             pool.start(nt, [=](int t) {
                 const size_t lo = m * static_cast<size_t>(t) / nt, hi = m * static_cast<size_t>(t + 1) / nt;
                 std::memcpy(to + lo, from + lo, hi - lo);
+                writeback_lines(to + lo, hi - lo);  // the DMA engine reads these lines next
+                copy_fence();
             });
             pool.wait();
         } else {
             std::memcpy(to, from, m);
+            writeback_lines(to, m);
+            copy_fence();
         }
         BSQ_CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(dst) + done, s->ring[k], m, cudaMemcpyHostToDevice, s->copy_stream));
         BSQ_CUDA_TRY(cudaEventRecord(s->ring_free[k], s->copy_stream));
@@ -512,8 +549,11 @@ int items_run(bsq_stager *s, bsq_pack *p, cudaStream_t st, const void *const *pt
     const size_t nranges = bounds.size() - 1;
 
     auto copy_seqs = [&](int64_t lo, int64_t hi) {
+        if (hi <= lo) return;
         for (int64_t i = lo; i < hi; ++i)
             if (lens[i] > 0) std::memcpy(p->bytes + p->offs[i], ptrs[i], static_cast<size_t>(lens[i]));
+        writeback_lines(p->bytes + p->offs[lo], static_cast<size_t>(p->offs[hi] - p->offs[lo]));
+        copy_fence();
     };
     int nt = pool_threads(nthreads);
     nt = static_cast<int>(std::min<int64_t>(nt, std::max<int64_t>(1, total >> 19)));  // >= 512 KiB per thread
