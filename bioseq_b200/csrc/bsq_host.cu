@@ -256,27 +256,32 @@ int bsq_pack_gather(bsq_pack *p, const void *const *ptrs, const int64_t *lens, i
     p->nbytes = total;
     p->maxlen = maxlen;
 
+    const bool pinned = p->pinned != 0;
     auto copy_range = [&](int64_t lo, int64_t hi) {
+        if (hi <= lo) return;
         for (int64_t i = lo; i < hi; ++i)
             if (lens[i] > 0) std::memcpy(p->bytes + p->offs[i], ptrs[i], static_cast<size_t>(lens[i]));
+        if (pinned) {  // read next by the DMA engine: see writeback_lines
+            writeback_lines(p->bytes + p->offs[lo], static_cast<size_t>(p->offs[hi] - p->offs[lo]));
+            copy_fence();
+        }
     };
-    int nt = std::max(1, nthreads);
+    int nt = pool_threads(nthreads);
     nt = static_cast<int>(std::min<int64_t>(nt, std::max<int64_t>(1, total >> 20)));  // >= 1 MiB per thread
     if (nt <= 1) {
         copy_range(0, n);
     } else {
-        // split by bytes, not by count, so ragged batches stay balanced
-        std::vector<std::thread> workers;
-        int64_t lo = 0;
-        for (int t = 0; t < nt; ++t) {
-            const int64_t target = total * (t + 1) / nt;
-            const int64_t hi = t == nt - 1 ? n : std::upper_bound(p->offs, p->offs + n + 1, target) - p->offs - 1;
-            const int64_t hi_c = std::max(lo, std::min(hi, n));
-            if (t == nt - 1) copy_range(lo, n);
-            else workers.emplace_back(copy_range, lo, hi_c);
-            lo = hi_c;
-        }
-        for (auto &w : workers) w.join();
+        // shares split by bytes, not by count, so ragged batches stay balanced
+        Pool &pool = Pool::get();
+        pool.start(nt, [&, nt](int t) {
+            auto cut = [&](int u) {
+                if (u <= 0) return int64_t(0);
+                if (u >= nt) return n;
+                return static_cast<int64_t>(std::lower_bound(p->offs, p->offs + n, total * u / nt) - p->offs);
+            };
+            copy_range(cut(t), cut(t + 1));
+        });
+        pool.wait();
     }
     std::memset(p->bytes + total, 0, 32);
     return BSQ_OK;
