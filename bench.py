@@ -48,9 +48,32 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_SYNTH = None
+
+
+def synth():
+    """bioseq_b200/synth.py (pure numpy) loaded by path: the reference arm must not import the product package
+    (that would map libbsq.so / the cbioseq extension into the process that times the reference)."""
+    global _SYNTH
+    if _SYNTH is None:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("_bsq_synth", os.path.join(ROOT, "bioseq_b200", "synth.py"))
+        _SYNTH = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(_SYNTH)
+    return _SYNTH
+
+
 def make_batch(seed):
-    from bioseq_b200.synth import gen, AA20
-    return gen(seed, NSEQ, LO, HI, AA20)
+    sy = synth()
+    return sy.gen(seed, NSEQ, LO, HI, sy.AA20)
+
+
+def bench_config(world):
+    """The one `config` object both arms print (the driver compares them field by field)."""
+    return {"workload": WORKLOAD, "seqs_per_gpu": NSEQ, "padlen": PADLEN, "len_range": [LO, HI], "alphabet": "AA20 uniform",
+            "tokenizer": "PROTEIN bos+eos+padchar", "batch_first": True, "dtype": "u8", "seed": 102,
+            "l2": f"inputs+outputs rotate through {ROT} distinct 103 MB sets (> 126 MB L2)",
+            "parallelism": f"{world} ranks, sequences sharded by index (byte-balanced ranges), no collective"}
 
 
 def algorithmic_bytes(nbases, nseq, padlen, itemsize=1, ncols=1):
@@ -114,19 +137,20 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
-def cpu_arm(buf, offs, steps, warmup, budget_s=20.0):
+def cpu_arm(buf, offs, steps, warmup, budget_s=20.0, opt="O3", nthreads=None):
     """The reference's CPU implementation on the host cores (oracle/_ref), else the C port."""
-    from bioseq_b200.synth import as_list
+    as_list = synth().as_list
     from oracle.oracle import load_ref, OracleTokenizer
     nbases = int(offs[-1])
-    R = load_ref()
-    cores = os.cpu_count() or 1
+    R = load_ref(opt=opt)
+    cores = nthreads or os.cpu_count() or 1
     if R is not None:
         tok = R.Tokenizer(KEY, **FLAGS)
         seqs = as_list(buf, offs)
         fn = lambda: tok.batch_tokenize(seqs, padlen=PADLEN, destchar="B", batch_first=True, nthreads=cores)  # noqa: E731
         kind, used = "reference", cores
-        how = f"oracle/_ref (reference src/tokenize.cpp, g++ -O3 -march=x86-64-v3 -fopenmp), nthreads={cores}, list[bytes] input"
+        flags = "-O3 -march=x86-64-v3 -fopenmp" if opt == "O3" else "-O0 -fopenmp (the flags the reference ships with, setup.py:50-55)"
+        how = f"oracle/_ref (reference src/tokenize.cpp, g++ {flags}), nthreads={cores}, list[bytes] input"
     else:
         tok = OracleTokenizer(KEY, **FLAGS)
         fn = lambda: tok.batch_tokenize((buf, offs), padlen=PADLEN, destchar="B", batch_first=True)  # noqa: E731
@@ -158,7 +182,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "tokenize_throughput", "value": res["value"], "unit": "Gbases/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "note": "CPU arm: one host, all threads; not sharded over GPUs"},
+            "config": bench_config(args.gpus), "note": "CPU arm: one host, all threads; not sharded over GPUs",
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}

@@ -86,6 +86,11 @@ def lib():
         "bsq_flatfile_is_pinned": (i32, [vp]),
         "bsq_fastx_lengths": (i32, [C.c_char_p, C.POINTER(C.POINTER(i64)), C.POINTER(i64)]),
         "bsq_free": (None, [vp]),
+        "bsq_tokenize_stream_items": (i32, [vp, vp, i64, vp, vp, vp, i64, tokp, i32, i32, vp, i32]),
+        "bsq_onehot_stream_items": (i32, [vp, vp, i64, vp, vp, vp, i64, tokp, i32, vp, i32]),
+        "bsq_shard_bounds": (i32, [vp, i64, i32, vp]),
+        "bsq_tokenize_host_sharded": (i32, [vp, vp, i32, vp, vp, i64, i64, tokp, i32, i32, i32, vp, vp]),
+        "bsq_memcpy_d2d": (i32, [i32, vp, vp, vp, C.c_size_t]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -102,7 +107,8 @@ EXPORTS = ("bsq_abi_version bsq_last_error bsq_launch_count bsq_launch_count_res
            "bsq_flatfile_make bsq_flatfile_open bsq_flatfile_close bsq_flatfile_nseqs bsq_flatfile_seq_offset "
            "bsq_flatfile_max_seq_len bsq_flatfile_offsets bsq_flatfile_bytes bsq_flatfile_is_pinned bsq_fastx_lengths "
            "bsq_free bsq_stage_host bsq_stage_release bsq_stager_set_augment bsq_onehot_bcl bsq_embed bsq_augment_blosum62 "
-           "bsq_blosum62_thresholds bsq_tokenize_items bsq_onehot_items bsq_fetch_rows bsq_parallel_for").split()
+           "bsq_blosum62_thresholds bsq_tokenize_items bsq_onehot_items bsq_fetch_rows bsq_parallel_for "
+           "bsq_tokenize_stream_items bsq_onehot_stream_items bsq_shard_bounds bsq_tokenize_host_sharded bsq_memcpy_d2d").split()
 
 
 def last_error():

@@ -51,6 +51,8 @@ using bsq::fail;
 // ---------------------------------------------------------------------------------------
 namespace {
 
+thread_local bool t_in_pool_worker = false;  // set on pool threads: a nested parallel section runs inline instead
+
 class Pool {
 public:
     static Pool &get() {
@@ -104,7 +106,9 @@ private:
                 if (id >= nt_) continue;
                 fn = fn_;
             }
+            t_in_pool_worker = true;
             fn(id);
+            t_in_pool_worker = false;
             std::lock_guard<std::mutex> lk(mu_);
             if (--pending_ == 0) done_cv_.notify_all();
         }
@@ -125,8 +129,10 @@ inline int pool_threads(int wanted) {
         cpu_set_t set;  // the CPUs this process may run on (a container's cpuset), not the machine's
         CPU_ZERO(&set);
         const int n = sched_getaffinity(0, sizeof(set), &set) == 0 ? CPU_COUNT(&set) : static_cast<int>(std::thread::hardware_concurrency());
+        if (const char *e = std::getenv("BSQ_POOL_CAP")) return std::max(1, std::atoi(e));
         return std::max(1, n / 2);
     }();
+    if (t_in_pool_worker) return 1;  // the pool runs one job at a time: a worker must not wait for it
     return std::max(1, std::min(std::min(wanted, cap), 64));
 }
 
@@ -324,14 +330,23 @@ constexpr int64_t kSeqAlign = 128;               // chunk boundaries: whole tile
 constexpr size_t kFetchBytes = size_t(8) << 20;  // decoded characters per device -> host stage
 }  // namespace
 
-struct bsq_stager {
-    int device = 0;
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t done = nullptr;  // completion of the previous call's kernels
-    bool busy = false;
+// Device-side staging of one batch in flight: residues (+ mask) and offsets, and the event that says the kernels
+// reading them have finished.  Two slots alternate call by call, so the copies of call k+1 never wait for the
+// kernels of call k (they used to: one buffer, stream-wait on `done` before the first copy).
+struct DevSlot {
     uint8_t *d_bytes = nullptr, *d_mask = nullptr;
     int64_t *d_offs = nullptr;
     size_t cap_bytes = 0, cap_mask = 0, cap_offs = 0;
+    cudaEvent_t done = nullptr;  // completion of the kernels of the call that used this slot last
+    bool busy = false;
+};
+constexpr int kDevSlots = 2;
+
+struct bsq_stager {
+    int device = 0;
+    cudaStream_t copy_stream = nullptr;
+    DevSlot slot[kDevSlots];
+    int cur = 0;  // slot of the call in progress / of the last call
     uint8_t *ring[kRingSlots] = {nullptr, nullptr, nullptr};
     cudaEvent_t ring_free[kRingSlots] = {nullptr, nullptr, nullptr};
     bool ring_used[kRingSlots] = {false, false, false};
@@ -345,6 +360,21 @@ struct bsq_stager {
     double aug_frac = 0.0;
     uint64_t aug_seed = 0;
     int64_t aug_base = 0;
+    // pinned-ness of host buffers seen before (cudaPointerGetAttributes is a driver call; callers hand the same
+    // pinned buffers over again and again)
+    const void *pin_key[8] = {};
+    size_t pin_len[8] = {};
+    bool pin_val[8] = {};
+    int pin_next = 0;
+    // streamed item batches (bsq_*_stream_items): two pinned packs alternate call by call, each with the event of
+    // the last copy that read it, plus the per-item scratch arrays
+    bsq_pack ipack[2];
+    cudaEvent_t ipack_ev[2] = {nullptr, nullptr};
+    bool ipack_used[2] = {false, false};
+    int ipack_next = 0;
+    std::vector<const void *> it_ptrs;
+    std::vector<int64_t> it_lens;
+    int64_t avg_len_hint = 512;
 };
 
 namespace {
@@ -367,6 +397,23 @@ bool is_pinned(const void *p) {
         return false;
     }
     return attr.type == cudaMemoryTypeHost;
+}
+// Cached form for the [p, p + n) ranges a stager is handed: a hit needs the same start and a length the earlier
+// answer covered (a pinned registration covers whole allocations, so a shorter range of one is pinned too; a buffer
+// that was freed and re-allocated pageable at the same address with a larger size is asked about again).
+bool is_pinned_cached(bsq_stager *s, const void *p, size_t n) {
+    if (p == nullptr) return false;
+    for (int i = 0; i < 8; ++i)
+        if (s->pin_key[i] == p && n <= s->pin_len[i] && s->pin_val[i]) return true;
+    const bool v = is_pinned(p);
+    if (v) {  // only positive answers are cached: "pageable" must stay safe if the caller pins the buffer later
+        const int k = s->pin_next;
+        s->pin_next = (k + 1) % 8;
+        s->pin_key[k] = p;
+        s->pin_len[k] = n;
+        s->pin_val[k] = true;
+    }
+    return v;
 }
 
 // host -> device copy of n bytes on the copy stream; pageable sources bounce through the
@@ -426,16 +473,25 @@ struct RunArgs {
     bool pin_b, pin_m;
 };
 
+// Takes the next device slot, reserves its staging buffers for `nbytes` residues and nseq + 1 offsets.
+int slot_begin(bsq_stager *s, int64_t nbytes, int64_t nseq, bool with_mask) {
+    s->cur = (s->cur + 1) % kDevSlots;
+    DevSlot &d = s->slot[s->cur];
+    if (d.busy) BSQ_CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, d.done, 0));  // the kernels that read this slot two calls ago
+    if (int rc = dev_reserve(reinterpret_cast<void **>(&d.d_bytes), &d.cap_bytes, static_cast<size_t>(nbytes) + 32)) return rc;
+    if (int rc = dev_reserve(reinterpret_cast<void **>(&d.d_offs), &d.cap_offs, sizeof(int64_t) * (nseq + 1))) return rc;
+    if (with_mask)
+        if (int rc = dev_reserve(reinterpret_cast<void **>(&d.d_mask), &d.cap_mask, static_cast<size_t>(nbytes) + 32)) return rc;
+    return BSQ_OK;
+}
+
 // Reserves the device-side staging buffers of a batch and copies its offsets.
 int stage_begin(bsq_stager *s, const RunArgs &a) {
     const int64_t nbytes = a.h_offs[a.nseq] - a.base;
-    if (s->busy) BSQ_CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->done, 0));  // staging buffers still in use
-    if (int rc = dev_reserve(reinterpret_cast<void **>(&s->d_bytes), &s->cap_bytes, static_cast<size_t>(nbytes) + 32)) return rc;
-    if (int rc = dev_reserve(reinterpret_cast<void **>(&s->d_offs), &s->cap_offs, sizeof(int64_t) * (a.nseq + 1))) return rc;
-    if (a.h_mask != nullptr)
-        if (int rc = dev_reserve(reinterpret_cast<void **>(&s->d_mask), &s->cap_mask, static_cast<size_t>(nbytes) + 32)) return rc;
+    if (int rc = slot_begin(s, nbytes, a.nseq, a.h_mask != nullptr)) return rc;
     // offsets first (small); the kernels index d_bytes with (offset - base) via a shifted pointer
-    return stage_copy(s, s->d_offs, a.h_offs, sizeof(int64_t) * (a.nseq + 1), is_pinned(a.h_offs));
+    return stage_copy(s, s->slot[s->cur].d_offs, a.h_offs, sizeof(int64_t) * (a.nseq + 1),
+                      is_pinned_cached(s, a.h_offs, sizeof(int64_t) * (a.nseq + 1)));
 }
 
 // End of the staged range that starts at sequence i0: whole 128-sequence groups holding ~kChunkBytes of residues.
@@ -448,11 +504,12 @@ int64_t range_end(const int64_t *h_offs, int64_t nseq, int64_t i0, size_t chunk 
 
 // Copies the residues (and mask) of sequences [i0, i1) and launches their kernel behind the copy.
 int stage_range(bsq_stager *s, const RunArgs &a, int64_t i0, int64_t i1, size_t nchunk) {
+    DevSlot &d = s->slot[s->cur];
     const int64_t base = a.base;
     const int64_t b0 = a.h_offs[i0] - base, b1 = a.h_offs[i1] - base;
-    if (int rc = stage_copy(s, s->d_bytes + b0, a.h_bytes + base + b0, static_cast<size_t>(b1 - b0), a.pin_b)) return rc;
+    if (int rc = stage_copy(s, d.d_bytes + b0, a.h_bytes + base + b0, static_cast<size_t>(b1 - b0), a.pin_b)) return rc;
     if (a.h_mask)
-        if (int rc = stage_copy(s, s->d_mask + b0, a.h_mask + base + b0, static_cast<size_t>(b1 - b0), a.pin_m)) return rc;
+        if (int rc = stage_copy(s, d.d_mask + b0, a.h_mask + base + b0, static_cast<size_t>(b1 - b0), a.pin_m)) return rc;
     while (nchunk >= s->events.size()) {
         cudaEvent_t e;
         BSQ_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -460,25 +517,28 @@ int stage_range(bsq_stager *s, const RunArgs &a, int64_t i0, int64_t i1, size_t 
     }
     BSQ_CUDA_TRY(cudaEventRecord(s->events[nchunk], s->copy_stream));
     BSQ_CUDA_TRY(cudaStreamWaitEvent(a.st, s->events[nchunk], 0));
-    const uint8_t *d_bytes_shifted = s->d_bytes - base;
-    const uint8_t *d_mask_shifted = a.h_mask ? s->d_mask - base : nullptr;
+    const uint8_t *d_bytes_shifted = d.d_bytes - base;
+    const uint8_t *d_mask_shifted = a.h_mask ? d.d_mask - base : nullptr;
     const size_t esize = bsq_kind_size(a.kind);
     const int64_t ncols = a.onehot ? a.tok->alphabet_size : 1;
     if (s->aug_chain > 0)
-        if (int rc = bsq_augment_blosum62(s->device, a.st, s->d_bytes - base, s->d_offs + i0, i1 - i0, s->aug_chain, s->aug_frac,
+        if (int rc = bsq_augment_blosum62(s->device, a.st, d.d_bytes - base, d.d_offs + i0, i1 - i0, s->aug_chain, s->aug_frac,
                                           s->aug_seed, s->aug_base + i0))
             return rc;
     if (a.onehot)
-        return bsq::launch_onehot(a.st, d_bytes_shifted, s->d_offs + i0, d_mask_shifted, i1 - i0, a.nseq, a.padlen, *a.tok, a.kind,
+        return bsq::launch_onehot(a.st, d_bytes_shifted, d.d_offs + i0, d_mask_shifted, i1 - i0, a.nseq, a.padlen, *a.tok, a.kind,
                                   static_cast<uint8_t *>(a.d_out) + static_cast<size_t>(i0) * ncols * esize);
     const size_t off = a.batch_first ? static_cast<size_t>(i0) * a.padlen * esize : static_cast<size_t>(i0) * esize;
-    return bsq::launch_tokenize(a.st, d_bytes_shifted, s->d_offs + i0, i1 - i0, a.nseq, a.padlen, *a.tok, a.batch_first, a.kind,
+    return bsq::launch_tokenize(a.st, d_bytes_shifted, d.d_offs + i0, i1 - i0, a.nseq, a.padlen, *a.tok, a.batch_first, a.kind,
                                 static_cast<uint8_t *>(a.d_out) + off, /*first_off=*/a.h_offs[i0]);
 }
 
-int stage_end(bsq_stager *s, const RunArgs &a) {
-    BSQ_CUDA_TRY(cudaEventRecord(s->done, a.st));
-    s->busy = true;
+// Marks the current slot as in use by whatever `st` holds now.  Also called on the error paths: kernels of earlier
+// ranges may already be reading the slot.
+int stage_end(bsq_stager *s, cudaStream_t st) {
+    DevSlot &d = s->slot[s->cur];
+    BSQ_CUDA_TRY(cudaEventRecord(d.done, st));
+    d.busy = true;
     return BSQ_OK;
 }
 
@@ -493,9 +553,10 @@ int staged_run(bsq_stager *s, cudaStream_t st, const uint8_t *h_bytes, const int
     }
     if (nseq == 0) return BSQ_OK;
     RunArgs a{st, h_bytes, h_offs, h_mask, nseq, padlen, h_offs[0], tok, onehot, batch_first, kind, d_out, false, false};
-    if (h_offs[nseq] - a.base > 0 && h_bytes == nullptr) return fail(BSQ_ERR_ARG, "null residue buffer");
-    a.pin_b = is_pinned(h_bytes);
-    a.pin_m = h_mask && is_pinned(h_mask);
+    const int64_t nbytes = h_offs[nseq] - a.base;
+    if (nbytes > 0 && h_bytes == nullptr) return fail(BSQ_ERR_ARG, "null residue buffer");
+    a.pin_b = nbytes > 0 && is_pinned_cached(s, h_bytes + a.base, static_cast<size_t>(nbytes));
+    a.pin_m = h_mask && nbytes > 0 && is_pinned_cached(s, h_mask + a.base, static_cast<size_t>(nbytes));
     if (int rc = stage_begin(s, a)) return rc;
     // Range size.  The call costs copy time + the kernel of the last range + a few microseconds per copy: small
     // outputs (narrow tokens: the whole batch's kernel is a few % of its copy) do best with few large ranges from a
@@ -505,95 +566,257 @@ int staged_run(bsq_stager *s, cudaStream_t st, const uint8_t *h_bytes, const int
     if (a.pin_b && !h_mask && !onehot && bsq_kind_size(kind) <= 2) chunk = size_t(32) << 20;  // 35 MB batch, pipelined calls: 4 MiB 0.707 ms, 16 MiB 0.689, 32 MiB 0.674, one range 0.681 (raw copy 0.650)
     if (env_mib > 0) chunk = static_cast<size_t>(env_mib) << 20;
     size_t nchunk = 0;
-    for (int64_t i0 = 0; i0 < nseq;) {
+    int rc = BSQ_OK;
+    for (int64_t i0 = 0; i0 < nseq && rc == BSQ_OK;) {
         const int64_t i1 = range_end(h_offs, nseq, i0, chunk);
-        if (int rc = stage_range(s, a, i0, i1, nchunk++)) return rc;
+        rc = stage_range(s, a, i0, i1, nchunk++);
         i0 = i1;
     }
-    return stage_end(s, a);
+    const int rc2 = stage_end(s, st);  // also after a failure: earlier ranges' kernels may be reading the slot
+    return rc ? rc : rc2;
 }
 
-// Items (borrowed host pointers, the reference's unpacked batch: src/tokenize.h:389-419) -> pinned pack ->
-// device -> kernels, range by range: while the DMA engine moves range k the host threads are already
-// gathering range k+1, so that the call costs max(gather, copy) rather than their sum.
-int items_run(bsq_stager *s, bsq_pack *p, cudaStream_t st, const void *const *ptrs, const int64_t *lens, int64_t n,
-              int64_t padlen, const bsq_tokenizer *tok, int onehot, int batch_first, int kind, void *d_out, int nthreads) {
-    if (s == nullptr || p == nullptr) return fail(BSQ_ERR_ARG, "null stager / pack");
-    if (!p->pinned) return fail(BSQ_ERR_ARG, "bsq_*_items needs a pinned pack");
-    if (n < 0 || (n > 0 && (ptrs == nullptr || lens == nullptr))) return fail(BSQ_ERR_ARG, "bad pack arguments");
-    if (int rc = bsq::check_launch_args(s->device, n, padlen, tok, kind, d_out)) return rc;
-    int64_t total = 0, maxlen = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        if (lens[i] < 0) return fail(BSQ_ERR_ARG, "negative sequence length");
-        total += lens[i];
-        maxlen = std::max(maxlen, lens[i]);
-    }
-    const int64_t extra = (tok->bos_id >= 0) + (tok->eos_id >= 0);
-    if (maxlen + extra > padlen)  // src/tokenize.h:456-459
-        return fail(BSQ_ERR_TOO_LONG, "seq len + bos + eos > padlen: " + std::to_string(maxlen + extra) + ", vs padlen " +
-                                          std::to_string(padlen));
-    // the pinned pack of the previous call may still be feeding the DMA engine
-    BSQ_CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
-    if (int rc = pack_reserve(p, total, n)) return rc;
-    int64_t acc = 0;
-    for (int64_t i = 0; i < n; ++i) {
-        p->offs[i] = acc;
-        acc += lens[i];
-    }
-    p->offs[n] = acc;
-    p->nseq = n;
-    p->nbytes = total;
-    p->maxlen = maxlen;
-    std::memset(p->bytes + total, 0, 32);
-    if (n == 0) return BSQ_OK;
+// ------------------------------------------------------------------------------------------------------------------
+// Streamed item batches: the reference's unpacked batch (src/tokenize.h:389-419: a Python list of str / bytes /
+// bytearray) -> pinned pack -> device -> kernels in ONE pass over the items, range by range.
+//
+// The items stay with their owner; `resolve(ctx, lo, hi, ptrs, lens)` is called from pool threads and fills pointer
+// and length of items [lo, hi) (length -1 = "needs the owner's thread", e.g. a Python str whose UTF-8 form has to be
+// created), `fixup(ctx, i, &ptr, &len)` is then called on the calling thread for those.
+//
+// Per range of R items (a multiple of 128, ~4 MiB of residues going by the previous call's mean length):
+//   workers   walk their share of the range (prefetching the item headers ahead), publish its byte sum / maximum,
+//             walk their share of the NEXT range, wait for the range's base offsets, then copy exactly the items they
+//             walked (their header lines are still in that core's cache) into the pinned pack, writing the offsets as
+//             they go, and write the lines back (clwb) for the DMA engine;
+//   caller    as soon as a range is walked: fixes up what the workers could not resolve, checks the lengths, turns the
+//             byte sums into base offsets; as soon as the previous range is gathered: enqueues its two copies (offsets,
+//             residues) on the copy stream and its kernel behind them.
+// The DMA of range k overlaps the gather of range k+1 and the walk of range k+2; nothing is walked twice and the
+// call returns when the last range has been enqueued.  Two pinned packs alternate call by call (each with the event
+// of the last copy that read it), so back-to-back calls do not synchronise with the copy stream.
+// ------------------------------------------------------------------------------------------------------------------
+struct ItemsShared {
+    int nt = 1;
+    int64_t n = 0, R = 0, nranges = 0;
+    const void **ptrs = nullptr;
+    int64_t *lens = nullptr;
+    bsq_resolve_fn resolve = nullptr;
+    void *ctx = nullptr;
+    bsq_pack *pack = nullptr;
+    std::vector<int64_t> sum, mx, special, base;  // [range * nt + thread]
+    std::vector<std::atomic<int>> walked, gathered, go;  // per range
+    std::atomic<bool> abort{false};
+    int64_t lo(int64_t k) const { return k * R; }
+    int64_t hi(int64_t k) const { return std::min(n, (k + 1) * R); }
+    // thread t's share of range k: items [cut(k, t), cut(k, t + 1))
+    int64_t cut(int64_t k, int t) const { return lo(k) + (hi(k) - lo(k)) * t / nt; }
+};
 
-    RunArgs a{st, p->bytes, p->offs, nullptr, n, padlen, 0, tok, onehot, batch_first, kind, d_out, true, false};
-    if (int rc = stage_begin(s, a)) return rc;
-    std::vector<int64_t> bounds{0};
-    while (bounds.back() < n) bounds.push_back(range_end(p->offs, n, bounds.back()));
-    const size_t nranges = bounds.size() - 1;
+void items_walk(ItemsShared &sh, int64_t k, int t) {
+    const int64_t a = sh.cut(k, t), b = sh.cut(k, t + 1);
+    if (b > a) sh.resolve(sh.ctx, a, b, sh.ptrs, sh.lens);
+    int64_t sum = 0, mx = 0, special = 0;
+    for (int64_t i = a; i < b; ++i) {
+        const int64_t l = sh.lens[i];
+        if (l < 0) ++special;
+        else { sum += l; mx = std::max(mx, l); }
+    }
+    const size_t j = static_cast<size_t>(k) * sh.nt + t;
+    sh.sum[j] = sum; sh.mx[j] = mx; sh.special[j] = special;
+    sh.walked[static_cast<size_t>(k)].fetch_add(1, std::memory_order_release);
+}
 
-    auto copy_seqs = [&](int64_t lo, int64_t hi) {
-        if (hi <= lo) return;
-        for (int64_t i = lo; i < hi; ++i)
-            if (lens[i] > 0) std::memcpy(p->bytes + p->offs[i], ptrs[i], static_cast<size_t>(lens[i]));
-        writeback_lines(p->bytes + p->offs[lo], static_cast<size_t>(p->offs[hi] - p->offs[lo]));
-        copy_fence();
+void items_gather(ItemsShared &sh, int64_t k, int t) {
+    const int64_t a = sh.cut(k, t), b = sh.cut(k, t + 1);
+    uint8_t *bytes = sh.pack->bytes;
+    int64_t *offs = sh.pack->offs;
+    int64_t pos = sh.base[static_cast<size_t>(k) * sh.nt + t];
+    const int64_t pos0 = pos;
+    // the items are separate heap objects: every one starts with a miss that the hardware prefetcher cannot
+    // anticipate.  Requesting the bodies a few items ahead turns the loop from latency-bound into bandwidth-bound.
+    constexpr int64_t kAhead = 4;
+    auto prefetch_body = [&](int64_t j) {
+        const char *p = static_cast<const char *>(sh.ptrs[j]);
+        const int64_t l = std::min<int64_t>(sh.lens[j], 2048);
+        for (int64_t o = 0; o < l; o += 64) __builtin_prefetch(p + o, 0, 0);
     };
+    for (int64_t j = a; j < std::min(b, a + kAhead); ++j) prefetch_body(j);
+    for (int64_t i = a; i < b; ++i) {
+        if (i + kAhead < b) prefetch_body(i + kAhead);
+        if (i != sh.lo(k)) offs[i] = pos;  // (the range's first offset was written by the caller)
+        const int64_t l = sh.lens[i];
+        if (l > 0) std::memcpy(bytes + pos, sh.ptrs[i], static_cast<size_t>(l));
+        pos += l;
+    }
+    writeback_lines(bytes + pos0, static_cast<size_t>(pos - pos0));
+    writeback_lines(reinterpret_cast<const uint8_t *>(offs + a), static_cast<size_t>(b - a) * sizeof(int64_t));
+    copy_fence();
+    sh.gathered[static_cast<size_t>(k)].fetch_add(1, std::memory_order_release);
+}
+
+void items_worker(ItemsShared &sh, int t) {
+    items_walk(sh, 0, t);
+    for (int64_t k = 0; k < sh.nranges; ++k) {
+        if (k + 1 < sh.nranges) items_walk(sh, k + 1, t);
+        spin_until([&] { return sh.go[static_cast<size_t>(k)].load(std::memory_order_acquire) != 0 || sh.abort.load(std::memory_order_relaxed); });
+        if (sh.abort.load(std::memory_order_relaxed)) return;
+        items_gather(sh, k, t);
+    }
+}
+
+int pack_event(bsq_stager *s, int k) {
+    if (s->ipack_ev[k] == nullptr) BSQ_CUDA_TRY(cudaEventCreateWithFlags(&s->ipack_ev[k], cudaEventDisableTiming));
+    return BSQ_OK;
+}
+
+int items_stream_run(bsq_stager *s, cudaStream_t st, int64_t n, bsq_resolve_fn resolve, bsq_fixup_fn fixup, void *ctx, int64_t padlen,
+                     const bsq_tokenizer *tok, int onehot, int batch_first, int kind, void *d_out, int nthreads) {
+    if (s == nullptr) return fail(BSQ_ERR_ARG, "null stager");
+    if (n < 0 || (n > 0 && resolve == nullptr)) return fail(BSQ_ERR_ARG, "bad item arguments");
+    if (int rc = bsq::check_launch_args(s->device, n, padlen, tok, kind, d_out)) return rc;
+    if (n == 0) return BSQ_OK;
+    const int64_t extra = (tok->bos_id >= 0) + (tok->eos_id >= 0);
+
+    // the pack this call gathers into: wait for the last copy that read it (two calls ago: long done in steady state)
+    const int pk = s->ipack_next;
+    s->ipack_next ^= 1;
+    bsq_pack *pack = &s->ipack[pk];
+    pack->pinned = 1;
+    if (int rc = pack_event(s, pk)) return rc;
+    if (s->ipack_used[pk]) BSQ_CUDA_TRY(cudaEventSynchronize(s->ipack_ev[pk]));
+
+    ItemsShared sh;
+    sh.n = n;
+    const int64_t want_items = std::max<int64_t>(1, static_cast<int64_t>(kChunkBytes) / std::max<int64_t>(s->avg_len_hint, 1));
+    sh.R = std::max<int64_t>(kSeqAlign, std::min<int64_t>(int64_t(1) << 20, (want_items + kSeqAlign - 1) / kSeqAlign * kSeqAlign));
+    sh.nranges = (n + sh.R - 1) / sh.R;
     int nt = pool_threads(nthreads);
-    nt = static_cast<int>(std::min<int64_t>(nt, std::max<int64_t>(1, total >> 19)));  // >= 512 KiB per thread
-    if (nt <= 1) {
-        for (size_t k = 0; k < nranges; ++k) {
-            copy_seqs(bounds[k], bounds[k + 1]);
-            if (int rc = stage_range(s, a, bounds[k], bounds[k + 1], k)) return rc;
-        }
-        return stage_end(s, a);
-    }
-    // every worker copies its byte-balanced share of range 0, then of range 1, ...: ranges complete in order
-    std::vector<std::atomic<int>> done(nranges);
-    for (auto &d : done) d.store(0, std::memory_order_relaxed);
+    nt = static_cast<int>(std::min<int64_t>(nt, std::max<int64_t>(1, std::min(n, sh.R) / 256)));  // >= 256 items per share
+    sh.nt = nt;
+    s->it_ptrs.resize(static_cast<size_t>(n));
+    s->it_lens.resize(static_cast<size_t>(n));
+    sh.ptrs = s->it_ptrs.data();
+    sh.lens = s->it_lens.data();
+    sh.resolve = resolve;
+    sh.ctx = ctx;
+    sh.pack = pack;
+    const size_t cells = static_cast<size_t>(sh.nranges) * nt;
+    sh.sum.assign(cells, 0); sh.mx.assign(cells, 0); sh.special.assign(cells, 0); sh.base.assign(cells, 0);
+    sh.walked = std::vector<std::atomic<int>>(static_cast<size_t>(sh.nranges));
+    sh.gathered = std::vector<std::atomic<int>>(static_cast<size_t>(sh.nranges));
+    sh.go = std::vector<std::atomic<int>>(static_cast<size_t>(sh.nranges));
+    for (int64_t k = 0; k < sh.nranges; ++k) { sh.walked[k].store(0); sh.gathered[k].store(0); sh.go[k].store(0); }
+
+    if (int rc = pack_reserve(pack, 0, n)) return rc;  // offsets: n + 1 entries, known up front
+    if (int rc = slot_begin(s, static_cast<int64_t>(pack->cap_bytes), n, false)) return rc;  // device buffers follow the pack's capacity
+    RunArgs a{st, pack->bytes, pack->offs, nullptr, n, padlen, 0, tok, onehot, batch_first, kind, d_out, true, false};
+
     Pool &pool = Pool::get();
-    pool.start(nt, [&, nt](int t) {
-        for (size_t k = 0; k < nranges; ++k) {
-            const int64_t i0 = bounds[k], i1 = bounds[k + 1];
-            const int64_t b0 = p->offs[i0], nb = p->offs[i1] - b0;
-            auto cut = [&](int u) {  // first sequence of share u
-                if (u <= 0) return i0;
-                if (u >= nt) return i1;
-                return static_cast<int64_t>(std::lower_bound(p->offs + i0, p->offs + i1, b0 + nb * u / nt) - p->offs);
-            };
-            copy_seqs(cut(t), cut(t + 1));
-            done[k].fetch_add(1, std::memory_order_release);
-        }
-    });
+    const bool pooled = nt > 1;
+    if (pooled) pool.start(nt, [&sh](int t) { items_worker(sh, t); });
+
     int rc = BSQ_OK;
-    for (size_t k = 0; k < nranges && rc == BSQ_OK; ++k) {
-        spin_until([&] { return done[k].load(std::memory_order_acquire) == nt; });
-        rc = stage_range(s, a, bounds[k], bounds[k + 1], k);
+    int64_t running = 0, issued = 0;  // bytes placed so far; ranges enqueued so far
+    auto issue = [&](int64_t k) -> int {  // copies + kernel of range k (gathered)
+        DevSlot &d = s->slot[s->cur];
+        const int64_t i0 = sh.lo(k), i1 = sh.hi(k);
+        BSQ_CUDA_TRY(cudaMemcpyAsync(d.d_offs + i0, pack->offs + i0, sizeof(int64_t) * static_cast<size_t>(i1 - i0 + 1), cudaMemcpyHostToDevice,
+                                     s->copy_stream));
+        a.h_bytes = pack->bytes;
+        return stage_range(s, a, i0, i1, static_cast<size_t>(k));
+    };
+    auto wait_gathered = [&](int64_t k) {
+        if (pooled) spin_until([&] { return sh.gathered[static_cast<size_t>(k)].load(std::memory_order_acquire) == nt; });
+    };
+    for (int64_t k = 0; k < sh.nranges && rc == BSQ_OK; ++k) {
+        if (pooled) spin_until([&] { return sh.walked[static_cast<size_t>(k)].load(std::memory_order_acquire) == nt; });
+        else items_walk(sh, k, 0);
+        // items the workers could not resolve (Python str) or that are of no accepted type
+        int64_t special = 0;
+        for (int t = 0; t < nt; ++t) special += sh.special[static_cast<size_t>(k) * nt + t];
+        if (special > 0) {
+            for (int t = 0; t < nt && rc == BSQ_OK; ++t) {
+                const size_t j = static_cast<size_t>(k) * nt + t;
+                if (sh.special[j] == 0) continue;
+                int64_t sum = 0, mx = 0;
+                for (int64_t i = sh.cut(k, t); i < sh.cut(k, t + 1); ++i) {
+                    if (sh.lens[i] < 0 && (fixup == nullptr || fixup(ctx, i, &sh.ptrs[i], &sh.lens[i]) != 0 || sh.lens[i] < 0)) {
+                        rc = fail(BSQ_ERR_ARG, "item was none of string, bytes, or numpy array of 8-bit integers. ");  // src/tokenize.h:412
+                        break;
+                    }
+                    sum += sh.lens[i];
+                    mx = std::max(mx, sh.lens[i]);
+                }
+                sh.sum[j] = sum; sh.mx[j] = mx;
+            }
+            if (rc) break;
+        }
+        int64_t total_k = 0, mx = 0;
+        for (int t = 0; t < nt; ++t) {
+            const size_t j = static_cast<size_t>(k) * nt + t;
+            sh.base[j] = running + total_k;
+            total_k += sh.sum[j];
+            mx = std::max(mx, sh.mx[j]);
+        }
+        if (mx + extra > padlen) {  // src/tokenize.h:456-459
+            rc = fail(BSQ_ERR_TOO_LONG, "seq len + bos + eos > padlen: " + std::to_string(mx + extra) + ", vs padlen " + std::to_string(padlen));
+            break;
+        }
+        // capacity: the pinned pack and the device slot grow together (rare after the first calls: both keep their size)
+        if (static_cast<size_t>(running + total_k) + 32 > pack->cap_bytes) {
+            // everything gathered so far has to leave the old buffers first
+            while (issued < k && rc == BSQ_OK) { wait_gathered(issued); rc = issue(issued++); }
+            if (rc) break;
+            BSQ_CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+            const int64_t seen = sh.hi(k);
+            const int64_t est = static_cast<int64_t>(static_cast<double>(running + total_k) * static_cast<double>(n) / static_cast<double>(seen) * 1.15) + 4096;
+            if ((rc = pack_reserve(pack, est, n)) != BSQ_OK) break;  // (offsets keep their buffer: capacity n + 1 already)
+            DevSlot &d = s->slot[s->cur];
+            if ((rc = dev_reserve(reinterpret_cast<void **>(&d.d_bytes), &d.cap_bytes, pack->cap_bytes)) != BSQ_OK) break;
+        }
+        pack->offs[sh.lo(k)] = running;
+        running += total_k;
+        pack->offs[sh.hi(k)] = running;
+        if (pooled) sh.go[static_cast<size_t>(k)].store(1, std::memory_order_release);
+        else items_gather(sh, k, 0);
+        // enqueue whatever is gathered by now, but never wait for the range that was only just released
+        while (issued < k && rc == BSQ_OK) { wait_gathered(issued); rc = issue(issued++); }
     }
-    pool.wait();  // also on error: the workers borrow this frame
-    if (rc) return rc;
-    return stage_end(s, a);
+    while (issued < sh.nranges && rc == BSQ_OK) { wait_gathered(issued); rc = issue(issued++); }
+    if (rc) {
+        sh.abort.store(true);
+        for (auto &g : sh.go) g.store(1, std::memory_order_release);
+    }
+    if (pooled) pool.wait();  // also on error: the workers borrow this frame
+    pack->nseq = n;
+    pack->nbytes = running;
+    if (rc == BSQ_OK && n > 0) s->avg_len_hint = std::max<int64_t>(1, running / n);
+    // the pack is free again when the copies enqueued so far have been made
+    if (cudaEventRecord(s->ipack_ev[pk], s->copy_stream) == cudaSuccess) s->ipack_used[pk] = true;
+    const int rc2 = stage_end(s, st);
+    return rc ? rc : rc2;
+}
+
+// Items given as pointer / length arrays (already walked): the streamed pipeline with a resolver that copies from them.
+struct ArrayItems {
+    const void *const *ptrs;
+    const int64_t *lens;
+};
+void array_resolve(void *ctx, int64_t lo, int64_t hi, const void **ptrs, int64_t *lens) {
+    const ArrayItems &it = *static_cast<const ArrayItems *>(ctx);
+    for (int64_t i = lo; i < hi; ++i) {
+        ptrs[i] = it.ptrs[i];
+        lens[i] = it.lens[i];
+    }
+}
+int items_run(bsq_stager *s, bsq_pack * /*unused: the stager owns the pinned packs*/, cudaStream_t st, const void *const *ptrs, const int64_t *lens,
+              int64_t n, int64_t padlen, const bsq_tokenizer *tok, int onehot, int batch_first, int kind, void *d_out, int nthreads) {
+    if (n < 0 || (n > 0 && (ptrs == nullptr || lens == nullptr))) return fail(BSQ_ERR_ARG, "bad pack arguments");
+    for (int64_t i = 0; i < n; ++i)
+        if (lens[i] < 0) return fail(BSQ_ERR_ARG, "negative sequence length");
+    ArrayItems it{ptrs, lens};
+    return items_stream_run(s, st, n, array_resolve, nullptr, &it, padlen, tok, onehot, batch_first, kind, d_out, nthreads);
 }
 
 // Rows of a device byte buffer -> separate host destinations (the bodies of the Python strings that
@@ -688,7 +911,7 @@ int bsq_stager_create(bsq_stager **out, int device) {
     bsq_stager *s = new bsq_stager();
     s->device = device;
     cudaError_t e = cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming);
+    for (int k = 0; k < kDevSlots && e == cudaSuccess; ++k) e = cudaEventCreateWithFlags(&s->slot[k].done, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete s;
         return fail(BSQ_ERR_CUDA, std::string("bsq_stager_create: ") + cudaGetErrorString(e));
@@ -701,9 +924,17 @@ void bsq_stager_destroy(bsq_stager *s) {
     if (s == nullptr) return;
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
-    cudaFree(s->d_bytes);
-    cudaFree(s->d_mask);
-    cudaFree(s->d_offs);
+    for (int k = 0; k < kDevSlots; ++k) {
+        cudaFree(s->slot[k].d_bytes);
+        cudaFree(s->slot[k].d_mask);
+        cudaFree(s->slot[k].d_offs);
+        if (s->slot[k].done) cudaEventDestroy(s->slot[k].done);
+    }
+    for (int k = 0; k < 2; ++k) {
+        host_free(s->ipack[k].bytes, 1);
+        host_free(s->ipack[k].offs, 1);
+        if (s->ipack_ev[k]) cudaEventDestroy(s->ipack_ev[k]);
+    }
     for (int k = 0; k < kRingSlots; ++k) {
         if (s->ring[k]) cudaFreeHost(s->ring[k]);
         if (s->ring_free[k]) cudaEventDestroy(s->ring_free[k]);
@@ -713,7 +944,6 @@ void bsq_stager_destroy(bsq_stager *s) {
         if (s->fetch_ring[k]) cudaFreeHost(s->fetch_ring[k]);
         if (s->fetch_ev[k]) cudaEventDestroy(s->fetch_ev[k]);
     }
-    if (s->done) cudaEventDestroy(s->done);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
 }
@@ -743,11 +973,12 @@ int bsq_stage_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const in
     const int64_t base = h_offsets[0], nbytes = h_offsets[nseq] - base;
     if (nbytes < 0) return fail(BSQ_ERR_ARG, "offsets must be non-decreasing");
     if (nbytes > 0 && h_bytes == nullptr) return fail(BSQ_ERR_ARG, "null residue buffer");
-    if (s->busy) BSQ_CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->done, 0));
-    if (int rc = dev_reserve(reinterpret_cast<void **>(&s->d_bytes), &s->cap_bytes, static_cast<size_t>(nbytes) + 32)) return rc;
-    if (int rc = dev_reserve(reinterpret_cast<void **>(&s->d_offs), &s->cap_offs, sizeof(int64_t) * (nseq + 1))) return rc;
-    if (int rc = stage_copy(s, s->d_offs, h_offsets, sizeof(int64_t) * (nseq + 1), is_pinned(h_offsets))) return rc;
-    if (int rc = stage_copy(s, s->d_bytes, h_bytes + base, static_cast<size_t>(nbytes), nbytes > 0 && is_pinned(h_bytes))) return rc;
+    if (int rc = slot_begin(s, nbytes, nseq, false)) return rc;
+    DevSlot &d = s->slot[s->cur];
+    if (int rc = stage_copy(s, d.d_offs, h_offsets, sizeof(int64_t) * (nseq + 1), is_pinned_cached(s, h_offsets, sizeof(int64_t) * (nseq + 1)))) return rc;
+    if (int rc = stage_copy(s, d.d_bytes, h_bytes + base, static_cast<size_t>(nbytes),
+                            nbytes > 0 && is_pinned_cached(s, h_bytes + base, static_cast<size_t>(nbytes))))
+        return rc;
     if (s->events.empty()) {
         cudaEvent_t e;
         BSQ_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -756,23 +987,20 @@ int bsq_stage_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const in
     BSQ_CUDA_TRY(cudaEventRecord(s->events[0], s->copy_stream));
     BSQ_CUDA_TRY(cudaStreamWaitEvent(st, s->events[0], 0));
     if (s->aug_chain > 0 && nseq > 0)
-        if (int rc = bsq_augment_blosum62(s->device, st, s->d_bytes - base, s->d_offs, nseq, s->aug_chain, s->aug_frac, s->aug_seed,
+        if (int rc = bsq_augment_blosum62(s->device, st, d.d_bytes - base, d.d_offs, nseq, s->aug_chain, s->aug_frac, s->aug_seed,
                                           s->aug_base))
             return rc;
     // until bsq_stage_release the buffers count as in use by `stream`
-    BSQ_CUDA_TRY(cudaEventRecord(s->done, st));
-    s->busy = true;
-    *d_bytes = s->d_bytes - base;
-    *d_offsets = s->d_offs;
+    if (int rc = stage_end(s, st)) return rc;
+    *d_bytes = d.d_bytes - base;
+    *d_offsets = d.d_offs;
     return BSQ_OK;
 }
 
 int bsq_stage_release(bsq_stager *s, void *stream) {
     if (s == nullptr) return fail(BSQ_ERR_ARG, "null stager");
     BSQ_CUDA_TRY(cudaSetDevice(s->device));
-    BSQ_CUDA_TRY(cudaEventRecord(s->done, static_cast<cudaStream_t>(stream)));
-    s->busy = true;
-    return BSQ_OK;
+    return stage_end(s, static_cast<cudaStream_t>(stream));
 }
 
 int bsq_tokenize_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const int64_t *h_offsets, int64_t nseq,
@@ -794,6 +1022,67 @@ int bsq_tokenize_items(bsq_stager *s, bsq_pack *p, void *stream, const void *con
 int bsq_onehot_items(bsq_stager *s, bsq_pack *p, void *stream, const void *const *ptrs, const int64_t *lens, int64_t n,
                      int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out, int nthreads) {
     return items_run(s, p, static_cast<cudaStream_t>(stream), ptrs, lens, n, padlen, tok, 1, 0, kind, d_out, nthreads);
+}
+
+int bsq_tokenize_stream_items(bsq_stager *s, void *stream, int64_t n, bsq_resolve_fn resolve, bsq_fixup_fn fixup, void *ctx,
+                              int64_t padlen, const bsq_tokenizer *tok, int batch_first, int kind, void *d_out, int nthreads) {
+    return items_stream_run(s, static_cast<cudaStream_t>(stream), n, resolve, fixup, ctx, padlen, tok, 0, batch_first, kind, d_out, nthreads);
+}
+
+int bsq_onehot_stream_items(bsq_stager *s, void *stream, int64_t n, bsq_resolve_fn resolve, bsq_fixup_fn fixup, void *ctx,
+                            int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out, int nthreads) {
+    return items_stream_run(s, static_cast<cudaStream_t>(stream), n, resolve, fixup, ctx, padlen, tok, 1, 0, kind, d_out, nthreads);
+}
+
+int bsq_shard_bounds(const int64_t *h_offsets, int64_t nseq, int nshards, int64_t *bounds) {
+    if (nseq < 0 || nshards <= 0 || bounds == nullptr || (nseq > 0 && h_offsets == nullptr)) return fail(BSQ_ERR_ARG, "bad shard arguments");
+    bounds[0] = 0;
+    bounds[nshards] = nseq;
+    if (nseq == 0) {
+        for (int g = 1; g < nshards; ++g) bounds[g] = 0;
+        return BSQ_OK;
+    }
+    const int64_t base = h_offsets[0], total = h_offsets[nseq] - base;
+    for (int g = 1; g < nshards; ++g) {
+        // first sequence whose start is at or beyond g/nshards of the residues (ties and empty batches: by count)
+        int64_t i = total > 0 ? static_cast<int64_t>(std::lower_bound(h_offsets, h_offsets + nseq, base + static_cast<int64_t>((static_cast<__int128>(total) * g) / nshards)) - h_offsets)
+                              : nseq * g / nshards;
+        bounds[g] = std::max(bounds[g - 1], std::min(i, nseq));
+    }
+    return BSQ_OK;
+}
+
+int bsq_tokenize_host_sharded(bsq_stager *const *stagers, void *const *streams, int ndev, const uint8_t *h_bytes, const int64_t *h_offsets,
+                              int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int onehot, int batch_first, int kind,
+                              void *const *d_outs, const int64_t *bounds) {
+    if (stagers == nullptr || streams == nullptr || d_outs == nullptr || bounds == nullptr || ndev <= 0) return fail(BSQ_ERR_ARG, "bad shard arguments");
+    if (int rc = bsq_check_lengths_host(h_offsets, nseq, padlen, tok)) return rc;
+    std::vector<int> rcs(static_cast<size_t>(ndev), BSQ_OK);
+    std::vector<std::string> msgs(static_cast<size_t>(ndev));
+    auto run = [&](int g) {
+        const int64_t i0 = bounds[g], i1 = bounds[g + 1];
+        if (i1 <= i0) return;
+        rcs[g] = staged_run(stagers[g], static_cast<cudaStream_t>(streams[g]), h_bytes, h_offsets + i0, nullptr, i1 - i0, padlen, tok, onehot,
+                            batch_first, kind, d_outs[g]);
+        if (rcs[g] != BSQ_OK) msgs[g] = bsq_last_error();
+    };
+    if (ndev == 1 || t_in_pool_worker) {
+        for (int g = 0; g < ndev; ++g) run(g);
+    } else {
+        // one host thread per device (each keeps its own current device and enqueues its shard's copies and kernels)
+        Pool &pool = Pool::get();
+        pool.start(ndev, run);
+        pool.wait();
+    }
+    for (int g = 0; g < ndev; ++g)
+        if (rcs[g] != BSQ_OK) return fail(rcs[g], msgs[g]);
+    return BSQ_OK;
+}
+
+int bsq_memcpy_d2d(int device, void *stream, void *d_dst, const void *d_src, size_t nbytes) {
+    BSQ_CUDA_TRY(cudaSetDevice(device));
+    BSQ_CUDA_TRY(cudaMemcpyAsync(d_dst, d_src, nbytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    return BSQ_OK;
 }
 
 int bsq_parallel_for(int nthreads, void (*fn)(int, int, void *), void *ctx) {

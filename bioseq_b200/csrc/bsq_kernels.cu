@@ -1416,7 +1416,9 @@ bool ring_enabled() {
     return on;
 }
 bool pdl_enabled() {
-    static const bool on = env_int("BSQ_PDL", 1) != 0;
+    static const bool tune = env_int("BSQ_TUNE", 0) != 0;
+    static bool on = env_int("BSQ_PDL", 1) != 0;
+    if (tune) on = env_int("BSQ_PDL", 1) != 0;
     return on;
 }
 int ring_ctas_per_sm() {
@@ -1483,6 +1485,11 @@ int launch_bf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t /*ld*/, i
     // one-byte tokens: the codes are the output bytes (ids wrap to 8 bits like the reference's
     // int -> int8 store); wider types expand codes through Expand.
     const Prepared p = prepare(tok, sizeof(T) == 1 ? 0 : 1);
+    if (sizeof(T) == 1 && span_kernel_applicable(padlen)) {
+        int dev = 0;
+        BSQ_CUDA_TRY(cudaGetDevice(&dev));
+        return launch_tokenize_span(dev, st, v, nseq, padlen, p, static_cast<uint8_t *>(d_out), pdl_enabled());
+    }
     if (sizeof(T) == 1 && padlen > 256 && ring_enabled()) {
         // K1r: persistent, bulk-copy fed, per-row specialised realignment; any padlen that fits the ring
         constexpr int WARPS = kThreads / 32, NB = 2;

@@ -70,6 +70,11 @@ struct Prepared {
 };
 Prepared prepare(const bsq_tokenizer &tok, int mode);
 
+// K1s (bsq_span.cu): batch-first one-byte tokens, tile-staged and warp-specialised.
+bool span_kernel_applicable(int64_t padlen);
+int launch_tokenize_span(int device, cudaStream_t st, const SeqView &v, int64_t nseq, int64_t padlen, const Prepared &p,
+                         uint8_t *out, bool pdl_allowed);
+
 #ifdef __CUDACC__
 
 __device__ __forceinline__ uint4 ldg16(uintptr_t addr) {

@@ -1,0 +1,549 @@
+// K1s: batch-first one-byte tokens, tile-staged and warp-specialised (sm_100a).
+//
+// Reference semantics: Tokenizer::transencode<T>, batch_first branch (src/tokenize.h:430-434, :451-479).
+//
+// The (nseq, padlen) output is one flat byte array; a *tile* is a run of `vt` 16-byte output vectors of
+// it (whole rows when padlen divides the tile, otherwise it starts and ends inside rows).  The residues
+// that a tile needs are ONE contiguous span of the packed input (rows are consecutive sequences), so a
+// tile costs one 1-D bulk asynchronous copy (cp.async.bulk global -> shared, SASS UBLKCP, the TMA unit)
+// instead of one copy, one barrier wait and one slot computation per row:
+//
+//   producer warp   per tile: divides the tile's flat range into rows, loads the rows' offsets
+//                   (coalesced), issues the span copy into the next free stage of a ring of NSTAGE
+//                   shared-memory buffers (completion counted on the stage's `full` mbarrier) and
+//                   writes the per-row table {source position in the stage, length} next to it;
+//   8 consumer warps per tile: one 16-byte output vector per lane and step, vectors dealt flat
+//                   (consecutive lanes = consecutive vectors, a warp stores 512 contiguous bytes).
+//                   A lane finds its row with one multiply-shift division and one LDS.64 of the row
+//                   table, then: two LDS.128 of the staged residues, word select + four funnel
+//                   shifts (source-to-output byte shift), 16 LUT look-ups, BOS / EOS / PAD from the
+//                   17-entry mask tables on boundary vectors only, one st.global.cs.v4.  Vectors
+//                   beyond a row's EOS are the constant pad vector and skip all loads.
+//
+// Rows whose padlen is not a multiple of 16 use the same code: vectors stay aligned in the flat
+// output, a vector that straddles two rows is assembled from both and stored whole, and only the
+// batch's final partial vector (nseq * padlen % 16 != 0) is stored bytewise.
+//
+// Nothing per row is left in the instruction stream of the consumers except the row-table load: the
+// ring kernel it replaces (K1r, bsq_kernels.cu) spent 236 warp-instructions per 1 KiB row, 128 of them
+// on per-row bookkeeping (slot arithmetic, elect loops around each row's bulk copy, barrier waits,
+// uniform-datapath shuffling); see profiles/ r01x vs r02.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
+#include "bsq_internal.h"
+#include "bsq_kernels.cuh"
+
+namespace bsq {
+
+namespace {
+
+constexpr int kSpanConsumerWarps = 8;
+constexpr int kSpanConsumers = kSpanConsumerWarps * 32;
+constexpr int kSpanThreads = kSpanConsumers + 32;
+constexpr int kSpanSlack = 32;  // bytes in front of the staged span (two LDS.128 never leave the stage)
+constexpr int kSpanTail = 64;   // and behind it
+// MINB (launch bound, CTAs per SM) sets the register budget: 4 -> 56, 5 -> 40, 6 -> 32 registers per thread.
+
+__device__ __forceinline__ uint32_t s_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void bar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "BSQ_SPAN_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra BSQ_SPAN_WAIT_%=;\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+struct SpanParams {
+    const uint8_t *bytes;
+    const int64_t *offs;
+    uint8_t *out;
+    int64_t nseq;
+    int64_t total;    // nseq * padlen output bytes
+    int64_t ntiles;
+    int64_t step_rows;  // a CTA's next tile starts (gridDim.x * tile bytes) further on: that many whole rows ...
+    int step_cols;      // ... plus that many columns
+    int padlen;
+    int vt;           // 16-byte vectors per tile (a multiple of kSpanConsumers)
+    int stage_bytes;  // data area of a stage
+    int max_rows;     // row-table entries of a stage
+    uint32_t div_mul, div_shift;  // n / padlen = umulhi(n, div_mul) >> div_shift for 0 <= n < 2^31 (span_magic)
+};
+
+// Shared-memory loads by 32-bit shared address (the addresses are formed once per tile, outside the vector loop).
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ int4 lds128i(uint32_t a) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t ldsu8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+
+// Four LUT look-ups.  `lutb` is the LUT's shared address, 256-byte aligned: one PRMT per byte builds the
+// whole address (byte k of x under the upper three bytes of lutb), then LDS.U8; the codes are re-packed
+// with integer multiply-adds (FMA pipe; the PRMTs sit on the ALU pipe).
+__device__ __forceinline__ uint32_t span_translate4(uint32_t x, uint32_t lutb) {
+    const uint32_t b0 = ldsu8(__byte_perm(x, lutb, 0x7650));
+    const uint32_t b1 = ldsu8(__byte_perm(x, lutb, 0x7651));
+    const uint32_t b2 = ldsu8(__byte_perm(x, lutb, 0x7652));
+    const uint32_t b3 = ldsu8(__byte_perm(x, lutb, 0x7653));
+    return b0 + b1 * 0x100u + b2 * 0x10000u + b3 * 0x1000000u;
+}
+
+// 16 codes from the 32-byte window {v0, v1}: word shift Q (compile time), bit shift sh (taken mod 32).
+// PRE: the stage already holds codes (two-phase form: translated in place before the vectors are placed).
+template <int Q, bool PRE>
+__device__ __forceinline__ void span_translate16(const uint4 &v0, const uint4 &v1, uint32_t sh, uint32_t lutb, uint32_t t[4]) {
+    const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t x = __funnelshift_r(w[Q + k], w[Q + k + 1], sh);
+        t[k] = PRE ? x : span_translate4(x, lutb);
+    }
+}
+template <bool PRE>
+__device__ __forceinline__ void span_window16(uint32_t S, uint32_t lutb, uint32_t t[4]) {
+    const uint4 v0 = lds128(S & ~15u), v1 = lds128((S & ~15u) + 16u);
+    const uint32_t sh = S << 3;
+    // one whole specialised body per word shift: warp-uniform (no divergence) whenever the warp's vectors lie
+    // in one row, which is the case for every padlen >= 512
+    switch (S & 12u) {
+        case 0: span_translate16<0, PRE>(v0, v1, sh, lutb, t); break;
+        case 4: span_translate16<1, PRE>(v0, v1, sh, lutb, t); break;
+        case 8: span_translate16<2, PRE>(v0, v1, sh, lutb, t); break;
+        default: span_translate16<3, PRE>(v0, v1, sh, lutb, t); break;
+    }
+}
+
+// Loop invariants of the consumers, kept in registers.  They are read back from shared memory (cst[]) rather than
+// taken from the kernel parameters: ptxas re-materialises parameter values with constant-bank loads (and shared
+// addresses with window arithmetic) inside the vector loop -- 6 to 10 extra instructions per vector -- which it
+// cannot do with the result of a shared-memory load.
+struct SpanRegs {
+    uint32_t lutb;   // shared address of the LUT (256-byte aligned)
+    uint32_t tab_m;  // shared address of TailTab::m[0]; TailTab::f[k] is 17 * 16 bytes further on
+    uint32_t bos_w, bos_sel;  // BOS byte and the PRMT selector that puts it into byte 0 (identity without BOS)
+    uint4 padq;               // the constant pad vector
+    int bos, eos, padlen, neg_padlen;
+    uint32_t mul, shift;  // multiply-shift division by padlen
+};
+constexpr int kCstWords = 16;
+
+// Codes of columns c0 .. c0+15 of one row (src/tokenize.h:460-478), for c0 < n + eos: `srow` is the shared
+// address of the byte that column 0 would come from (first residue - bos), n = bos + len.  Columns >= padlen are
+// don't-care.  The residue window is loaded and translated unconditionally: whatever lies left of the first
+// residue or right of the last is replaced by the BOS / tail fix-ups (for c0 == n the whole vector is).
+template <bool PRE>
+__device__ __forceinline__ uint4 span_row_codes(uint32_t srow, int n, int c0, const SpanRegs &g) {
+    uint32_t t[4];
+    span_window16<PRE>(srow + static_cast<uint32_t>(c0), g.lutb, t);
+    if (c0 == 0) t[0] = __byte_perm(t[0], g.bos_w, g.bos_sel);
+    if (c0 + 16 > n) {  // the row's residues end inside this vector: keep n - c0 bytes, then EOS / pad
+        const uint32_t a = g.tab_m + 16u * static_cast<uint32_t>(n - c0);
+        const uint4 m = lds128(a), f = lds128(a + 17u * 16u);
+        t[0] = (t[0] & m.x) | f.x; t[1] = (t[1] & m.y) | f.y;
+        t[2] = (t[2] & m.z) | f.z; t[3] = (t[3] & m.w) | f.w;
+    }
+    return make_uint4(t[0], t[1], t[2], t[3]);
+}
+
+// Same for -16 < c0 < 0: the second half of a vector that straddles two rows (padlen % 16 != 0); bytes left of
+// column 0 are don't-care.
+template <bool PRE>
+__device__ __forceinline__ uint4 span_row_codes_neg(uint32_t srow, int n, int c0, const SpanRegs &g) {
+    uint32_t t[4] = {0u, 0u, 0u, 0u};
+    if (c0 < n && c0 + 16 > g.bos) span_window16<PRE>(srow + static_cast<uint32_t>(c0), g.lutb, t);
+    if (g.bos) {  // BOS sits at byte -c0 of the vector
+        const uint4 ma = lds128(g.tab_m - 16u * static_cast<uint32_t>(c0)), mb = lds128(g.tab_m + 16u - 16u * static_cast<uint32_t>(c0));
+        t[0] = (t[0] & ~(mb.x & ~ma.x)) | (g.bos_w & mb.x & ~ma.x);
+        t[1] = (t[1] & ~(mb.y & ~ma.y)) | (g.bos_w & mb.y & ~ma.y);
+        t[2] = (t[2] & ~(mb.z & ~ma.z)) | (g.bos_w & mb.z & ~ma.z);
+        t[3] = (t[3] & ~(mb.w & ~ma.w)) | (g.bos_w & mb.w & ~ma.w);
+    }
+    if (c0 + 16 > n) {
+        const uint32_t a = g.tab_m + 16u * static_cast<uint32_t>(n - c0);
+        const uint4 m = lds128(a), f = lds128(a + 17u * 16u);
+        t[0] = (t[0] & m.x) | f.x; t[1] = (t[1] & m.y) | f.y;
+        t[2] = (t[2] & m.z) | f.z; t[3] = (t[3] & m.w) | f.w;
+    }
+    return make_uint4(t[0], t[1], t[2], t[3]);
+}
+
+// The four offsets that delimit a tile's span: rows r0 and r1 (first and last row the tile touches).
+struct SpanEdges {
+    int64_t a0, a1, b0, b1;
+};
+
+template <int NSTAGE, bool ALIGNED, bool PRE, int MINB>
+__global__ void __launch_bounds__(kSpanThreads, MINB)
+tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp) {
+    extern __shared__ __align__(128) uint8_t dyn[];  // NSTAGE x { data[stage_bytes], rows[max_rows] x 16 B }
+    __shared__ __align__(256) uint8_t lut[256];
+    __shared__ TailTab tab;
+    __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE];
+    __shared__ __align__(16) int4 hdr[NSTAGE];           // c_first, nrows, nvec, -
+    __shared__ __align__(16) uint32_t cst[kCstWords];    // loop invariants of the consumers (see SpanRegs)
+
+    // Programmatic dependent launch: the next kernel of the stream may start its prologue now; ours (LUT, mask
+    // tables, barriers: no global memory) runs before the previous kernel of the stream has finished.
+    asm volatile("griddepcontrol.launch_dependents;");
+    load_lut(lut, lutp);
+    init_tailtab(tab, sp);
+    if (threadIdx.x == 96) {
+        cst[0] = static_cast<uint32_t>(q.padlen); cst[1] = q.div_mul; cst[2] = q.div_shift;
+        cst[3] = static_cast<uint32_t>(sp.eos); cst[4] = sp.bos ? sp.bos_w : 0u; cst[5] = sp.bos ? 0x3214u : 0x3210u;
+        cst[6] = static_cast<uint32_t>(-q.padlen); cst[7] = static_cast<uint32_t>(sp.bos);
+        cst[8] = s_u32(lut); cst[9] = s_u32(&tab.m[0]);
+        cst[12] = cst[13] = cst[14] = cst[15] = sp.pad_w;
+    }
+    if (threadIdx.x == 128) {
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) {
+            bar_init(full + s, 1);
+            bar_init(empty + s, kSpanConsumerWarps);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int stage_stride = q.stage_bytes + 16 * q.max_rows;
+    const int tile_bytes = q.vt * 16;
+
+    if (warp == kSpanConsumerWarps) {
+        // ------------------------------- producer -------------------------------
+        int64_t t = blockIdx.x;
+        if (t >= q.ntiles) return;
+        // first tile: one 64-bit division; later tiles advance by (step_rows, step_cols)
+        int64_t r0 = (t * tile_bytes) / q.padlen;
+        int c_first = static_cast<int>(t * tile_bytes - r0 * q.padlen);
+        // offsets of this CTA's first tile: into L2 while the previous kernel drains (a prefetch is only a hint,
+        // the real loads come after the wait)
+        if (16 * lane <= tile_bytes / q.padlen + 2 && r0 + 16 * lane <= q.nseq) asm volatile("prefetch.global.L2 [%0];" ::"l"(q.offs + r0 + 16 * lane));
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        const int maxlen = max(q.padlen - sp.bos - sp.eos, 0);
+        auto last_row = [&](int64_t tt, int64_t rr0, int cc, int &c_last) {  // r1 and c_last of tile tt
+            const int64_t f0 = tt * tile_bytes;
+            const uint32_t e = static_cast<uint32_t>(cc) + static_cast<uint32_t>(min(static_cast<int64_t>(tile_bytes), q.total - f0)) - 1u;
+            const uint32_t dr = __umulhi(e, q.div_mul) >> q.div_shift;
+            c_last = static_cast<int>(e - dr * static_cast<uint32_t>(q.padlen));
+            return rr0 + dr;
+        };
+        auto load_edges = [&](int64_t rr0, int64_t rr1) {
+            SpanEdges e;
+            e.a0 = __ldg(q.offs + rr0); e.a1 = __ldg(q.offs + rr0 + 1);
+            e.b0 = __ldg(q.offs + rr1); e.b1 = __ldg(q.offs + rr1 + 1);
+            return e;
+        };
+        int c_last;
+        int64_t r1 = last_row(t, r0, c_first, c_last);
+        SpanEdges cur = load_edges(r0, r1);
+        uint32_t it = 0;
+        for (;; ++it) {
+            // the next tile's edge offsets are requested now and consumed one iteration later: their latency hides
+            // behind this tile's barrier wait, copy issue and row table
+            const int64_t tn = t + gridDim.x;
+            int64_t r0n = r0 + q.step_rows;
+            int cn = c_first + q.step_cols;
+            if (cn >= q.padlen) { cn -= q.padlen; ++r0n; }
+            int c_lastn = 0;
+            int64_t r1n = 0;
+            SpanEdges nxt = cur;
+            if (tn < q.ntiles) {
+                r1n = last_row(tn, r0n, cn, c_lastn);
+                nxt = load_edges(r0n, r1n);
+            }
+            const int s = static_cast<int>(it % NSTAGE);
+            const uint32_t ph = (it / NSTAGE) & 1u;
+            const int64_t f0 = t * tile_bytes, f1 = min(f0 + tile_bytes, q.total);
+            const int nrows = static_cast<int>(r1 - r0) + 1;
+            // the span: residues of columns [c_first, padlen) of row r0 ... [0, c_last] of row r1
+            const int len0 = static_cast<int>(min(max(cur.a1 - cur.a0, int64_t(0)), static_cast<int64_t>(maxlen)));
+            const int len1 = static_cast<int>(min(max(cur.b1 - cur.b0, int64_t(0)), static_cast<int64_t>(maxlen)));
+            const int64_t lo = cur.a0 + min(max(c_first - sp.bos, 0), len0);
+            const int64_t hi = cur.b0 + min(max(c_last + 1 - sp.bos, 0), len1);
+            const uintptr_t A_lo = reinterpret_cast<uintptr_t>(q.bytes + lo) & ~uintptr_t(15);
+            const uintptr_t A_hi = (reinterpret_cast<uintptr_t>(q.bytes + hi) + 15) & ~uintptr_t(15);
+            const uint32_t nbytes = hi > lo ? static_cast<uint32_t>(min(static_cast<int64_t>(A_hi - A_lo),
+                                                                         static_cast<int64_t>(q.stage_bytes - kSpanSlack - kSpanTail)))
+                                            : 0u;
+            uint8_t *stage = dyn + static_cast<size_t>(s) * stage_stride;
+            int4 *rows = reinterpret_cast<int4 *>(stage + q.stage_bytes);
+            if (it >= NSTAGE) bar_wait(s_u32(empty + s), ph ^ 1u);  // the consumers are done with this stage
+            if (lane == 0) {
+                if (nbytes) {
+                    bar_expect_tx(s_u32(full + s), nbytes);
+                    bulk_load(s_u32(stage + kSpanSlack), reinterpret_cast<const void *>(A_lo), nbytes, s_u32(full + s));
+                }
+                hdr[s] = make_int4(c_first, nrows, static_cast<int>((f1 - f0 + 15) >> 4), static_cast<int>(nbytes));
+            }
+            // shared address of the byte that column 0 of row r0 + i comes from
+            const int64_t base = static_cast<int64_t>(reinterpret_cast<uintptr_t>(q.bytes)) - static_cast<int64_t>(A_lo) + kSpanSlack - sp.bos +
+                                 static_cast<int64_t>(s_u32(stage));
+            for (int i = lane; i < nrows; i += 32) {
+                const int64_t o0 = __ldg(q.offs + r0 + i), o1 = __ldg(q.offs + r0 + i + 1);
+                const int n = sp.bos + static_cast<int>(min(max(o1 - o0, int64_t(0)), static_cast<int64_t>(maxlen)));
+                rows[i] = make_int4(static_cast<int>(o0 + base), n, n + sp.eos, 0);
+            }
+            __syncwarp();
+            if (lane == 0) bar_arrive(s_u32(full + s));  // release: row table + header visible to whoever sees the phase flip
+            if (tn >= q.ntiles) break;
+            t = tn; r0 = r0n; c_first = cn; r1 = r1n; c_last = c_lastn; cur = nxt;
+        }
+        return;
+    }
+
+    // ------------------------------- consumers -------------------------------
+    const int ctid = threadIdx.x;  // 0 .. kSpanConsumers-1
+    SpanRegs g;
+    const uint32_t cst_a = s_u32(cst);
+    g.padlen = static_cast<int>(lds32(cst_a));
+    g.mul = lds32(cst_a + 4u);
+    g.shift = lds32(cst_a + 8u);
+    g.eos = static_cast<int>(lds32(cst_a + 12u));
+    g.bos_w = lds32(cst_a + 16u);
+    g.bos_sel = lds32(cst_a + 20u);
+    g.neg_padlen = static_cast<int>(lds32(cst_a + 24u));
+    g.bos = static_cast<int>(lds32(cst_a + 28u));
+    g.lutb = lds32(cst_a + 32u);
+    g.tab_m = lds32(cst_a + 36u);
+    g.padq = lds128(cst_a + 48u);
+    const uint32_t dyn_a = s_u32(dyn);
+    uint32_t it = 0;
+    for (int64_t t = blockIdx.x; t < q.ntiles; t += gridDim.x, ++it) {
+        const int s = static_cast<int>(it % NSTAGE);
+        const uint32_t ph = (it / NSTAGE) & 1u;
+        const uint32_t rows_a = dyn_a + static_cast<uint32_t>(s * stage_stride + q.stage_bytes);
+        bar_wait(s_u32(full + s), ph);
+        const int4 h = hdr[s];
+        const int nrows = h.y;
+        const int64_t tile0 = t * tile_bytes;
+        if (PRE) {
+            // phase 1: the staged residues become codes in place -- dense (every lane busy, no row logic, no
+            // realignment): LDS.128, 16 look-ups, STS.128 per 16 bytes of the span
+            const uint32_t d0 = dyn_a + static_cast<uint32_t>(s * stage_stride + kSpanSlack);
+            for (uint32_t b = 16u * static_cast<uint32_t>(ctid); b < static_cast<uint32_t>(h.w); b += 16u * kSpanConsumers) {
+                const uint4 v = lds128(d0 + b);
+                const uint32_t c0 = span_translate4(v.x, g.lutb), c1 = span_translate4(v.y, g.lutb);
+                const uint32_t c2 = span_translate4(v.z, g.lutb), c3 = span_translate4(v.w, g.lutb);
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(d0 + b), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(kSpanConsumers) : "memory");  // consumers only
+        }
+        // F: column-space offset of the lane's vector from column 0 of the tile's first row
+        uint32_t F = static_cast<uint32_t>(h.x) + 16u * static_cast<uint32_t>(ctid);
+        const uint32_t Fend = static_cast<uint32_t>(h.x) + 16u * static_cast<uint32_t>(h.z);
+        uint8_t *dst = q.out + tile0 + 16 * ctid;
+        for (; F < Fend; F += 16u * kSpanConsumers, dst += 16 * kSpanConsumers) {
+            const uint32_t rl = __umulhi(F, g.mul) >> g.shift;
+            const int col = static_cast<int>(rl * static_cast<uint32_t>(g.neg_padlen) + F);
+            const int4 ri = lds128i(rows_a + 16u * rl);  // {shared address of column 0's source byte, bos + len, bos + len + eos, -}
+            if (ALIGNED) {
+                if (col >= ri.z) {
+                    __stcs(reinterpret_cast<uint4 *>(dst), g.padq);
+                } else {
+                    __stcs(reinterpret_cast<uint4 *>(dst), span_row_codes<PRE>(static_cast<uint32_t>(ri.x), ri.y, col, g));
+                }
+                continue;
+            }
+            uint4 codes = g.padq;
+            if (col < ri.z) codes = span_row_codes<PRE>(static_cast<uint32_t>(ri.x), ri.y, col, g);
+            if (col + 16 > g.padlen && static_cast<int>(rl) + 1 < nrows) {  // the vector straddles into the next row
+                const int4 rj = lds128i(rows_a + 16u * rl + 16u);
+                const int c2 = col - g.padlen;
+                uint4 nxt = g.padq;
+                if (c2 < rj.z) nxt = span_row_codes_neg<PRE>(static_cast<uint32_t>(rj.x), rj.y, c2, g);
+                const uint4 m = lds128(g.tab_m + 16u * static_cast<uint32_t>(g.padlen - col));
+                codes.x = (codes.x & m.x) | (nxt.x & ~m.x); codes.y = (codes.y & m.y) | (nxt.y & ~m.y);
+                codes.z = (codes.z & m.z) | (nxt.z & ~m.z); codes.w = (codes.w & m.w) | (nxt.w & ~m.w);
+            }
+            const int64_t pos = tile0 + static_cast<int64_t>(F - static_cast<uint32_t>(h.x));
+            if (pos + 16 <= q.total) {
+                __stcs(reinterpret_cast<uint4 *>(dst), codes);
+            } else {  // the batch's final partial vector
+                const int keep = static_cast<int>(q.total - pos);
+                const uint32_t w[4] = {codes.x, codes.y, codes.z, codes.w};
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (j < keep) dst[j] = static_cast<uint8_t>(w[j >> 2] >> (8 * (j & 3)));
+            }
+        }
+        // the stage was written through the generic proxy (phase 1); the next thing to touch it is the async proxy
+        if (PRE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) bar_arrive(s_u32(empty + s));
+    }
+}
+
+// n / d = umulhi(n, mul) >> shift for every 0 <= n < 2^31 and 2 <= d <= 2^30 (round-up magic number with one
+// bit of headroom: no add-back step, two instructions per division).
+void span_magic(uint32_t d, uint32_t *mul, uint32_t *shift) {
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;
+    *mul = static_cast<uint32_t>((1ull << (31 + s)) / d + 1);
+    *shift = s - 1;
+}
+
+int span_env(const char *name, int dflt) {
+    const char *e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+
+struct DevInfo {
+    int sms = 0;
+    bool attr_set[4][2][2][3] = {};
+};
+DevInfo &dev_info(int dev) {
+    static DevInfo info[64];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> g(mu);
+    DevInfo &d = info[dev & 63];
+    if (d.sms == 0) cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    return d;
+}
+
+}  // namespace
+
+bool span_kernel_applicable(int64_t padlen) {
+    static const bool tune = span_env("BSQ_TUNE", 0) != 0;
+    static bool on = span_env("BSQ_SPAN", 1) != 0;
+    static int minp = span_env("BSQ_SPAN_MINPAD", 257);
+    if (tune) {
+        on = span_env("BSQ_SPAN", 1) != 0;
+        minp = span_env("BSQ_SPAN_MINPAD", 257);
+    }
+    return on && padlen >= minp && padlen <= (1ll << 30);
+}
+
+// Launches K1s over `nseq` rows; `device` is the current device.  Returns BSQ_OK or an error code.
+int launch_tokenize_span(int device, cudaStream_t st, const SeqView &v, int64_t nseq, int64_t padlen, const Prepared &p, uint8_t *out,
+                         bool pdl_allowed) {
+    // A/B knobs (read once; BSQ_TUNE=1 re-reads them at every launch for in-process sweeps)
+    static const bool tune = span_env("BSQ_TUNE", 0) != 0;
+    static int vt_max = 0, nstage = 0, ctas_env = 0, two_phase = 1, minb = 5;
+    if (vt_max == 0 || tune) {
+        vt_max = std::max(256, span_env("BSQ_SPAN_VT", 1024) / 256 * 256);
+        nstage = std::min(4, std::max(2, span_env("BSQ_SPAN_STAGES", 3)));
+        ctas_env = span_env("BSQ_SPAN_CTAS", 0);
+        two_phase = span_env("BSQ_SPAN_2P", 0);
+        minb = std::min(6, std::max(4, span_env("BSQ_SPAN_MINB", 5)));
+    }
+    DevInfo &di = dev_info(device);
+    const int sms = di.sms > 0 ? di.sms : 148;
+    const int64_t total = nseq * padlen;
+    const int64_t V = (total + 15) / 16;
+    // stage: slack + span (<= tile bytes + 32) + tail, plus the row table
+    auto smem_for = [&](int vt) {
+        const int stage_bytes = (kSpanSlack + vt * 16 + 32 + kSpanTail + 127) / 128 * 128;
+        const int max_rows = static_cast<int>(std::min<int64_t>(vt * 16 / padlen + 3, nseq + 1));
+        return static_cast<size_t>(nstage) * (stage_bytes + 16 * ((max_rows + 7) / 8 * 8));
+    };
+    const size_t static_smem = 256 + sizeof(TailTab) + 16 * nstage * 2 + 1024;
+    int per_sm = static_cast<int>((227 * 1024) / (smem_for(vt_max) + static_smem));
+    per_sm = std::max(1, std::min(std::min(per_sm, 2048 / kSpanThreads), minb));
+    if (ctas_env > 0) per_sm = std::min(per_sm, ctas_env);
+    const int64_t grid_full = static_cast<int64_t>(sms) * per_sm;
+    // tiles: as large as vt_max allows, and a count that fills whole rounds of the persistent grid
+    const int64_t rounds = std::max<int64_t>(1, (V + grid_full * vt_max - 1) / (grid_full * vt_max));
+    int64_t vt = (V + grid_full * rounds - 1) / (grid_full * rounds);
+    vt = std::min<int64_t>(vt_max, (vt + kSpanConsumers - 1) / kSpanConsumers * kSpanConsumers);
+    const int64_t ntiles = (V + vt - 1) / vt;
+    SpanParams q;
+    q.bytes = v.bytes;
+    q.offs = v.offs;
+    q.out = out;
+    q.nseq = nseq;
+    q.total = total;
+    q.ntiles = ntiles;
+    q.padlen = static_cast<int>(padlen);
+    q.vt = static_cast<int>(vt);
+    q.stage_bytes = (kSpanSlack + static_cast<int>(vt) * 16 + 32 + kSpanTail + 127) / 128 * 128;
+    q.max_rows = (static_cast<int>(std::min<int64_t>(vt * 16 / padlen + 3, nseq + 1)) + 7) / 8 * 8;
+    span_magic(static_cast<uint32_t>(padlen), &q.div_mul, &q.div_shift);
+    const size_t smem = static_cast<size_t>(nstage) * (q.stage_bytes + 16 * q.max_rows);
+    const bool aligned = padlen % 16 == 0;
+
+    const int64_t blocks = std::min<int64_t>(ntiles, grid_full);
+    const int64_t step = blocks * vt * 16;
+    q.step_rows = step / padlen;
+    q.step_cols = static_cast<int>(step % padlen);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned>(blocks));
+    cfg.blockDim = dim3(kSpanThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    // two whole persistent grids must fit on the SMs at once (see launch_bf in bsq_kernels.cu)
+    const bool pdl = pdl_allowed && 2 * per_sm * (smem + static_smem) <= 227 * 1024 && 2 * per_sm * kSpanThreads <= 2048;
+    cfg.numAttrs = pdl ? 1 : 0;
+
+#define BSQ_SPAN_LAUNCH(NS, AL, PR, MB)                                                                                           \
+    do {                                                                                                                          \
+        auto kern = tokenize_span_kernel<NS, AL, PR, MB>;                                                                         \
+        if (!di.attr_set[NS - 1][AL][PR][MB - 4]) {                                                                               \
+            BSQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                    \
+            di.attr_set[NS - 1][AL][PR][MB - 4] = true;                                                                           \
+        }                                                                                                                         \
+        BSQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, q, p.lut, p.sp));                                                             \
+    } while (0)
+#define BSQ_SPAN_LAUNCH3(NS, MB)                                                                                                  \
+    do {                                                                                                                          \
+        if (aligned && two_phase) BSQ_SPAN_LAUNCH(NS, true, true, MB);                                                            \
+        else if (aligned) BSQ_SPAN_LAUNCH(NS, true, false, MB);                                                                   \
+        else if (two_phase) BSQ_SPAN_LAUNCH(NS, false, true, MB);                                                                 \
+        else BSQ_SPAN_LAUNCH(NS, false, false, MB);                                                                               \
+    } while (0)
+#define BSQ_SPAN_LAUNCH2(NS)                                                                                                      \
+    do {                                                                                                                          \
+        if (minb == 4) BSQ_SPAN_LAUNCH3(NS, 4);                                                                                   \
+        else if (minb == 5) BSQ_SPAN_LAUNCH3(NS, 5);                                                                              \
+        else BSQ_SPAN_LAUNCH3(NS, 6);                                                                                             \
+    } while (0)
+    if (nstage == 2) BSQ_SPAN_LAUNCH2(2);
+    else if (nstage == 3) BSQ_SPAN_LAUNCH2(3);
+    else BSQ_SPAN_LAUNCH2(4);
+#undef BSQ_SPAN_LAUNCH3
+#undef BSQ_SPAN_LAUNCH2
+#undef BSQ_SPAN_LAUNCH
+    count_launch();
+    return BSQ_OK;
+}
+
+}  // namespace bsq

@@ -20,6 +20,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -141,13 +142,20 @@ DeviceCtx &device_ctx(int device) {
     static std::mutex map_mu;
     static std::map<int, DeviceCtx *> *ctxs = new std::map<int, DeviceCtx *>();  // leaked: CUDA teardown order
     std::lock_guard<std::mutex> g(map_mu);
-    DeviceCtx *&c = (*ctxs)[device];
-    if (c == nullptr) {
-        c = new DeviceCtx();
-        check(bsq_stager_create(&c->stager, device));
-        check(bsq_pack_create(&c->pack, /*pinned=*/1));
+    auto it = ctxs->find(device);
+    if (it != ctxs->end()) return *it->second;
+    // built completely before it is published: a failed create (transient CUDA error, no pinned memory left)
+    // must not leave a half-made context behind for every later call on this device
+    std::unique_ptr<DeviceCtx> c(new DeviceCtx());
+    check(bsq_stager_create(&c->stager, device));
+    const int rc = bsq_pack_create(&c->pack, /*pinned=*/1);
+    if (rc != BSQ_OK) {
+        bsq_stager_destroy(c->stager);
+        check(rc);
     }
-    return *c;
+    DeviceCtx *raw = c.release();
+    (*ctxs)[device] = raw;
+    return *raw;
 }
 
 // ------------------------------------------------------------------ item unpacking (src/tokenize.h:389-419)
@@ -177,32 +185,58 @@ inline bool unpack_one(PyObject *it, const void *&ptr, int64_t &len) {
     return true;
 }
 
-struct WalkCtx {
+// Resolver callbacks of bsq_*_stream_items (include/bsq.h).  The calling thread keeps the GIL for the whole
+// call, like the reference does (src/tokenize.h:389-419 runs under it): nothing can resize a bytearray item or
+// replace a list element while the pool threads read the items' headers and copy their bodies.
+struct PyItems {
     PyObject **items;
-    const void **ptrs;
-    int64_t *lens;
     Py_ssize_t n;
 };
-// Pool-thread share of the walk: bytes / bytearray items only (plain field reads of objects that the
-// calling thread keeps alive and, holding the GIL, unchanged); anything else is left to the caller (-1).
-void walk_share(int t, int nt, void *vctx) {
-    const WalkCtx &c = *static_cast<const WalkCtx *>(vctx);
-    const Py_ssize_t lo = c.n * t / nt, hi = c.n * (t + 1) / nt;
-    for (Py_ssize_t i = lo; i < hi; ++i) {
+// pool threads: bytes / bytearray items only (plain field reads); anything else is left to the caller (-1)
+void py_resolve(void *vctx, int64_t lo, int64_t hi, const void **ptrs, int64_t *lens) {
+    const PyItems &c = *static_cast<const PyItems *>(vctx);
+    constexpr int64_t kAhead = 12;  // the walk is a chain of cache misses on object headers: keep a dozen in flight
+    for (int64_t i = lo; i < std::min(hi, lo + kAhead); ++i) __builtin_prefetch(c.items[i]);
+    for (int64_t i = lo; i < hi; ++i) {
+        if (i + kAhead < hi) __builtin_prefetch(c.items[i + kAhead]);
         PyObject *it = c.items[i];
         if (PyBytes_Check(it)) {
-            c.ptrs[i] = PyBytes_AS_STRING(it);
-            c.lens[i] = PyBytes_GET_SIZE(it);
+            ptrs[i] = PyBytes_AS_STRING(it);
+            lens[i] = PyBytes_GET_SIZE(it);
         } else if (PyByteArray_Check(it)) {
-            c.ptrs[i] = PyByteArray_AS_STRING(it);
-            c.lens[i] = PyByteArray_GET_SIZE(it);
+            ptrs[i] = PyByteArray_AS_STRING(it);
+            lens[i] = PyByteArray_GET_SIZE(it);
         } else {
-            c.lens[i] = -1;
+            lens[i] = -1;
         }
     }
 }
+// calling thread: str items (UTF-8 form via the C API); non-zero = a type the reference rejects, or a Python error
+int py_fixup(void *vctx, int64_t i, const void **ptr, int64_t *len) {
+    const PyItems &c = *static_cast<const PyItems *>(vctx);
+    PyObject *it = c.items[i];
+    if (PyUnicode_Check(it)) {
+        Py_ssize_t size;
+        const char *s = PyUnicode_AsUTF8AndSize(it, &size);
+        if (s == nullptr) return 2;  // Python error set
+        *ptr = s;
+        *len = size;
+        return 0;
+    }
+    if (PyBytes_Check(it)) {
+        *ptr = PyBytes_AS_STRING(it);
+        *len = PyBytes_GET_SIZE(it);
+        return 0;
+    }
+    if (PyByteArray_Check(it)) {
+        *ptr = PyByteArray_AS_STRING(it);
+        *len = PyByteArray_GET_SIZE(it);
+        return 0;
+    }
+    return 1;
+}
 
-void unpack_items(const py::sequence &batch, Unpacked &u, int nthreads = 1) {
+void unpack_items(const py::sequence &batch, Unpacked &u, int /*nthreads*/ = 1) {
     PyObject *fast = PySequence_Fast(batch.ptr(), "batch must be a sequence");
     if (fast == nullptr) throw py::error_already_set();
     u.keepalive = py::reinterpret_steal<py::object>(fast);
@@ -211,15 +245,6 @@ void unpack_items(const py::sequence &batch, Unpacked &u, int nthreads = 1) {
     u.ptrs.resize(static_cast<size_t>(n));
     u.lens.resize(static_cast<size_t>(n));
     const char *bad = "item was none of string, bytes, or numpy array of 8-bit integers. ";
-    if (nthreads > 1 && n >= 8192) {
-        // touching 10^5 object headers is a chain of cache misses: spread it over the pool (the GIL stays with
-        // this thread, so nothing can mutate the items meanwhile); str items need the C API and are done here
-        WalkCtx c{items, u.ptrs.data(), u.lens.data(), n};
-        check(bsq_parallel_for(static_cast<int>(std::min<Py_ssize_t>(nthreads, n / 4096)), walk_share, &c));
-        for (Py_ssize_t i = 0; i < n; ++i)
-            if (u.lens[i] < 0 && !unpack_one(items[i], u.ptrs[i], u.lens[i])) throw py::value_error(bad);
-        return;
-    }
     for (Py_ssize_t i = 0; i < n; ++i)
         if (!unpack_one(items[i], u.ptrs[i], u.lens[i])) throw py::value_error(bad);
 }
@@ -429,11 +454,7 @@ public:
         if (py::isinstance<FlatFile>(batch))  // additive: a whole FlatFile, no per-sequence objects
             return run_flatfile(batch.cast<const FlatFile &>(), 0, py::none(), py::none(), padlen, dc, kind, false, batch_first, device);
         if (padlen <= 0) throw py::value_error("batch tokenize requires padlen is provded.");
-        Unpacked u;
-        nthreads = host_threads(nthreads);
-        unpack_items(batch, u, nthreads);
-        return run_host(u.ptrs.data(), u.lens.data(), static_cast<int64_t>(u.lens.size()), nullptr, padlen, dc, kind,
-                        /*onehot=*/false, batch_first, nthreads, device);
+        return run_items(batch, padlen, dc, kind, /*onehot=*/false, batch_first, host_threads(nthreads), device);
     }
 
     // ---- batch_onehot_encode (src/tokenize.cpp:65-81); always (padlen, batch, alphabet_size)
@@ -445,8 +466,9 @@ public:
         if (py::isinstance<FlatFile>(batch))
             return run_flatfile(batch.cast<const FlatFile &>(), 0, py::none(), mask, padlen, dc, kind, true, false, device);
         if (padlen <= 0) throw py::value_error("batch tokenize requires padlen is provded.");
-        Unpacked u;
         nthreads = host_threads(nthreads);
+        if (!py::isinstance<py::list>(mask)) return run_items(batch, padlen, dc, kind, /*onehot=*/true, false, nthreads, device);
+        Unpacked u;
         unpack_items(batch, u, nthreads);
         // mask: a list with one uint8 array per sequence; entries that are not arrays mean
         // "no mask for this sequence" (getmaskptr, src/tokenize.h:372-380).
@@ -482,6 +504,71 @@ public:
     py::object onehot_packed(const py::object &bytes, const py::object &offsets, py::ssize_t padlen, const std::string &destchar,
                              const py::object &mask, const py::object &device, bool check_len) const {
         return run_packed(bytes, offsets, mask, padlen, destchar, true, false, device, check_len);
+    }
+
+    // ---- additive: one packed host batch -> one shard per device (one process, one host thread per
+    // GPU).  Shards are contiguous sequence ranges holding equal shares of the residues; shard g lives on devices[g]
+    // as that device's own (n_g, padlen) / (padlen, n_g) tensor -- the per-device batches a DataParallel model
+    // consumes (training/cnnpretrain.py:86).  Returns (list of tensors, bounds).
+    py::tuple tokenize_sharded(const py::object &bytes, const py::object &offsets, py::ssize_t padlen, const std::string &destchar,
+                               bool batch_first, const py::object &devices) const {
+        Torch &t = Torch::get();
+        const char dc = destchar.empty() ? '\0' : destchar[0];
+        const int kind = bsq_kind_of_destchar(dc);
+        if (kind < 0) raise_status(kind);
+        if (padlen <= 0) throw py::value_error("batch tokenize requires padlen is provded.");
+        ArrayArg b = array_arg(bytes, "bytes", 1, "uint8", t.uint8);
+        ArrayArg o = array_arg(offsets, "offsets", 8, "int64", t.int64);
+        if (b.on_device || o.on_device) throw py::value_error("batch_tokenize_sharded takes host arrays (numpy / torch CPU, pinned or pageable)");
+        if (o.count < 1) throw py::value_error("offsets needs at least one entry");
+        const int64_t n = o.count - 1;
+        const int64_t *ho = static_cast<const int64_t *>(o.ptr);
+        if (n > 0 && (ho[0] < 0 || ho[n] > b.count)) throw py::value_error("offsets run past the end of bytes");
+        check(bsq_check_lengths_host(ho, n, padlen, &tok_));
+        std::vector<int> devs;
+        if (devices.is_none()) {
+            resolve_device(py::none());
+            const int cnt = t.cuda.attr("device_count")().cast<int>();
+            for (int g = 0; g < cnt; ++g) devs.push_back(g);
+        } else {
+            for (const auto &d : devices) devs.push_back(resolve_device(py::reinterpret_borrow<py::object>(d)));
+        }
+        if (devs.empty()) throw py::value_error("no devices given");
+        const int G = static_cast<int>(devs.size());
+        std::vector<int64_t> bounds(static_cast<size_t>(G) + 1);
+        check(bsq_shard_bounds(ho, n, G, bounds.data()));
+        py::list outs;
+        std::vector<void *> optrs(G), streams(G);
+        std::vector<bsq_stager *> stagers(G);
+        std::vector<DeviceCtx *> ctxs(G);
+        for (int g = 0; g < G; ++g) {
+            const int64_t ng = bounds[g + 1] - bounds[g];
+            std::vector<int64_t> shape = batch_first ? std::vector<int64_t>{ng, padlen} : std::vector<int64_t>{padlen, ng};
+            py::object out = new_tensor(shape, t.dtype_of(dc, kind), devs[g]);
+            optrs[g] = ng > 0 ? data_ptr(out) : nullptr;
+            streams[g] = current_stream(devs[g]);
+            ctxs[g] = &device_ctx(devs[g]);
+            stagers[g] = ctxs[g]->stager;
+            outs.append(out);
+        }
+        int rc;
+        {
+            py::gil_scoped_release nogil;
+            std::vector<DeviceCtx *> order(ctxs);  // lock each device's context once, in address order
+            std::sort(order.begin(), order.end());
+            order.erase(std::unique(order.begin(), order.end()), order.end());
+            if (order.size() != ctxs.size()) {
+                rc = BSQ_ERR_ARG;
+            } else {
+                for (DeviceCtx *c : order) c->mu.lock();
+                rc = bsq_tokenize_host_sharded(stagers.data(), streams.data(), G, static_cast<const uint8_t *>(b.ptr), ho, n, padlen, &tok_, 0,
+                                               batch_first ? 1 : 0, kind, optrs.data(), bounds.data());
+                for (DeviceCtx *c : order) c->mu.unlock();
+            }
+        }
+        if (rc == BSQ_ERR_ARG && std::string(bsq_last_error()).empty()) throw py::value_error("devices must be distinct");
+        check(rc);
+        return py::make_tuple(outs, py::cast(bounds));
     }
 
     // ---- additive: sequences [start, stop) of a FlatFile; padlen <= 0 means the file's longest
@@ -537,7 +624,9 @@ public:
         if (rows == 0) return new_tensor({0, tok_.alphabet_size}, Torch::get().dtype_of(dc, bsq_kind_of_destchar(dc)), resolve_device(device));
         py::object out = run_host(&ptr, &len, 1, nullptr, rows, dc, bsq_kind_of_destchar(dc), true, false, 1, device);
         out = out.attr("reshape")(rows, tok_.alphabet_size);
-        if (padchar_ && padlen > len) out[py::slice(padlen, rows, 1)].attr("zero_")();
+        // the reference pads rows [len + bos + eos, padlen) only (src/tokenize.h:210-214); the kernel padded up to `rows`
+        const int64_t zero_from = std::max<int64_t>(padlen, len + bos_ + eos_);
+        if (padchar_ && zero_from < rows) out[py::slice(zero_from, rows, 1)].attr("zero_")();
         return out;
     }
 
@@ -616,6 +705,43 @@ public:
     }
 
 private:
+    // The reference's calling convention, streamed: walk -> pinned pack -> copy -> kernel in one pass over the items
+    // (bsq_*_stream_items).  The GIL stays with this thread for the whole call, as in the reference.
+    py::object run_items(const py::sequence &batch, int64_t padlen, char dc, int kind, bool onehot, bool batch_first, int nthreads,
+                         const py::object &device) const {
+        PyObject *fast = PySequence_Fast(batch.ptr(), "batch must be a sequence");
+        if (fast == nullptr) throw py::error_already_set();
+        py::object keepalive = py::reinterpret_steal<py::object>(fast);
+        PyItems items{PySequence_Fast_ITEMS(fast), PySequence_Fast_GET_SIZE(fast)};
+        const int64_t n = items.n;
+        // item types are checked while streaming; small batches are checked up front as well, so that their errors
+        // precede any device use like the reference's (src/tokenize.h:389-419 unpacks before it allocates)
+        if (n <= 4096)
+            for (int64_t i = 0; i < n; ++i)
+                if (!PyUnicode_Check(items.items[i]) && !PyBytes_Check(items.items[i]) && !PyByteArray_Check(items.items[i]))
+                    throw py::value_error("item was none of string, bytes, or numpy array of 8-bit integers. ");
+        const int dev = resolve_device(device);
+        std::vector<int64_t> shape;
+        if (onehot) shape = {padlen, n, tok_.alphabet_size};
+        else if (batch_first) shape = {n, padlen};
+        else shape = {padlen, n};
+        py::object out = new_tensor(shape, Torch::get().dtype_of(dc, kind), dev);
+        if (n == 0) return out;
+        void *st = current_stream(dev);
+        void *optr = data_ptr(out);
+        DeviceCtx &ctx = device_ctx(dev);
+        int rc;
+        {
+            std::lock_guard<std::mutex> g(ctx.mu);
+            const int nt = nthreads > 0 ? nthreads : 1;
+            if (onehot) rc = bsq_onehot_stream_items(ctx.stager, st, n, py_resolve, py_fixup, &items, padlen, &tok_, kind, optr, nt);
+            else rc = bsq_tokenize_stream_items(ctx.stager, st, n, py_resolve, py_fixup, &items, padlen, &tok_, batch_first, kind, optr, nt);
+        }
+        if (rc != BSQ_OK && PyErr_Occurred()) throw py::error_already_set();  // raised inside py_fixup
+        check(rc, onehot);
+        return out;
+    }
+
     // pack (pinned) -> stage -> launch.  ptrs/lens describe n host sequences.
     py::object run_host(const void *const *ptrs, const int64_t *lens, int64_t n, const uint8_t *mask, int64_t padlen, char dc,
                         int kind, bool onehot, bool batch_first, int nthreads, const py::object &device) const {
@@ -639,7 +765,7 @@ private:
         DeviceCtx &ctx = device_ctx(dev);
         int rc;
         {
-            py::gil_scoped_release nogil;
+            // the GIL stays with this thread: ptrs borrow the items' buffers, which only it keeps unchanged
             std::lock_guard<std::mutex> g(ctx.mu);
             const int nt = nthreads > 0 ? nthreads : 1;
             if (mask == nullptr) {
@@ -828,6 +954,8 @@ PYBIND11_MODULE(cbioseq, m) {
         .def("batch_onehot_encode_packed", &Tokenizer::onehot_packed, py::arg("bytes"), py::arg("offsets"), py::arg("padlen") = -1,
              py::arg("destchar") = "B", py::arg("mask") = py::none(), py::arg("device") = py::none(),
              py::arg("check_lengths") = true)
+        .def("batch_tokenize_sharded", &Tokenizer::tokenize_sharded, py::arg("bytes"), py::arg("offsets"), py::arg("padlen") = -1,
+             py::arg("destchar") = "B", py::arg("batch_first") = false, py::arg("devices") = py::none())
         .def("batch_tokenize_flatfile", &Tokenizer::tokenize_flatfile, py::arg("flatfile"), py::arg("start") = 0,
              py::arg("stop") = py::none(), py::arg("padlen") = -1, py::arg("destchar") = "B", py::arg("batch_first") = false,
              py::arg("device") = py::none())

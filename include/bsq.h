@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BSQ_ABI_VERSION 3
+#define BSQ_ABI_VERSION 4
 
 /* ---- status codes ---------------------------------------------------------------- */
 #define BSQ_OK 0
@@ -164,8 +164,8 @@ int bsq_decode_chars(int device, void *stream, const void *d_tokens, int itemsiz
  * The calls return once all work is enqueued.  Pageable sources have been fully read when
  * the call returns; pinned sources are read asynchronously (cudaMemcpyAsync semantics: do
  * not overwrite them until `stream` reaches this point, or call bsq_stager_sync_copies).
- * The staging buffers stay owned by the stager and are reused by the next call on it
- * (which waits for the previous one on the device, not on the host). */
+ * The staging buffers stay owned by the stager; two sets alternate call by call, so the
+ * copies of a call never wait for the kernels of the call before it. */
 typedef struct bsq_stager bsq_stager;
 int bsq_stager_create(bsq_stager **out, int device);
 void bsq_stager_destroy(bsq_stager *s);
@@ -179,18 +179,53 @@ int bsq_onehot_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const i
                     const uint8_t *h_mask, int64_t nseq, int64_t padlen, const bsq_tokenizer *tok,
                     int kind, void *d_out);
 
-/* The reference's own calling convention: n borrowed host pointers + lengths (what its unpack loop collects
- * from the Python str/bytes/bytearray items, src/tokenize.h:389-419 / :289-322).  Gather into the pinned pack `p`
- * (created with pinned = 1), host->device copy and kernel run range by range (~4 MiB of residues each):
- * `nthreads` pool threads gather range k+1 while the DMA engine moves range k, so that the call costs
- * max(gather, copy) instead of their sum.  Lengths are checked before anything is copied.  Returns once all
- * work is enqueued; ptrs/lens are not referenced after the return.  `p` afterwards describes the batch
- * (bsq_pack_bytes/offsets) and must stay untouched until bsq_stager_sync_copies(s) or the next call on `s`. */
+/* The reference's own calling convention (src/tokenize.h:389-419 / :289-322: a sequence of str / bytes / bytearray
+ * items, unpacked into borrowed pointers + lengths) as ONE pass over the items, range by range (~4 MiB of
+ * residues each): pool threads walk a range's items, gather exactly the items they walked into a pinned pack
+ * and write the offsets as they go; the caller's thread enqueues the range's host->device copies and its kernel
+ * as soon as it is gathered.  The DMA of range k overlaps the gather of range k+1 and the walk of range k+2;
+ * nothing is walked twice, and back-to-back calls do not synchronise with the copy stream (two pinned packs,
+ * owned by the stager, alternate).
+ *
+ * The items stay with their owner:
+ *   resolve(ctx, lo, hi, ptrs, lens)   called from pool threads; fills ptrs[i], lens[i] for lo <= i < hi.  It must
+ *                                      only read (no allocation, no interpreter calls); lens[i] = -1 defers item i to
+ *   fixup(ctx, i, &ptr, &len)          called on the calling thread (may use the interpreter: the caller holds its
+ *                                      lock for the whole call, which is also what keeps the items unchanged while the
+ *                                      pool reads them -- the reference holds the GIL throughout as well); non-zero =
+ *                                      not an accepted item -> BSQ_ERR_ARG "item was none of string, bytes, ..." (:412).
+ * Over-long items -> BSQ_ERR_TOO_LONG with the reference's text (:458), found while streaming: ranges enqueued before
+ * the offending one have run, the output is to be discarded.  Returns once all work is enqueued; the items are not
+ * referenced after the return. */
+typedef void (*bsq_resolve_fn)(void *ctx, int64_t lo, int64_t hi, const void **ptrs, int64_t *lens);
+typedef int (*bsq_fixup_fn)(void *ctx, int64_t i, const void **ptr, int64_t *len);
+int bsq_tokenize_stream_items(bsq_stager *s, void *stream, int64_t n, bsq_resolve_fn resolve, bsq_fixup_fn fixup, void *ctx,
+                              int64_t padlen, const bsq_tokenizer *tok, int batch_first, int kind, void *d_out, int nthreads);
+int bsq_onehot_stream_items(bsq_stager *s, void *stream, int64_t n, bsq_resolve_fn resolve, bsq_fixup_fn fixup, void *ctx,
+                            int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out, int nthreads);
+
+/* Same pipeline for items that have already been unpacked into pointer / length arrays.  `p` is not used any more
+ * (the stager owns its pinned packs) and may be NULL; ptrs/lens are not referenced after the return. */
 int bsq_tokenize_items(bsq_stager *s, bsq_pack *p, void *stream, const void *const *ptrs, const int64_t *lens,
                        int64_t n, int64_t padlen, const bsq_tokenizer *tok, int batch_first, int kind,
                        void *d_out, int nthreads);
 int bsq_onehot_items(bsq_stager *s, bsq_pack *p, void *stream, const void *const *ptrs, const int64_t *lens,
                      int64_t n, int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out, int nthreads);
+
+/* ---- one process, several devices ("one host thread per GPU") ------------------------ */
+/* The path shards by sequence index with no exchange step: every output row depends on one input sequence.
+ * bsq_shard_bounds splits a packed batch into `nshards` contiguous sequence ranges holding equal shares of the
+ * RESIDUES (ragged lengths: equal counts would not balance): bounds[0] = 0 <= ... <= bounds[nshards] = nseq.
+ * bsq_tokenize_host_sharded runs shard g (sequences bounds[g] .. bounds[g+1]) through stagers[g] / streams[g]
+ * into d_outs[g] -- that device's own (n_g, padlen) / (padlen, n_g) / (padlen, n_g, C) array -- with one pool
+ * thread per device enqueuing its copies and kernels concurrently; the host source is shared, nothing is
+ * gathered between devices.  onehot != 0 selects batch_onehot_encode (batch_first ignored).  The reference's
+ * only multi-GPU construct is nn.DataParallel around the model (training/cnnpretrain.py:86), fed by exactly
+ * such per-device batches. */
+int bsq_shard_bounds(const int64_t *h_offsets, int64_t nseq, int nshards, int64_t *bounds);
+int bsq_tokenize_host_sharded(bsq_stager *const *stagers, void *const *streams, int ndev, const uint8_t *h_bytes,
+                              const int64_t *h_offsets, int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int onehot,
+                              int batch_first, int kind, void *const *d_outs, const int64_t *bounds);
 
 /* Run fn(t, nthreads, ctx) for t = 0 .. nthreads-1 on the library's persistent host worker pool (the one the
  * gather / scatter loops above use) and return when all have finished.  The reference's counterpart is its
@@ -210,7 +245,7 @@ int bsq_fetch_rows(bsq_stager *s, void *stream, const uint8_t *d_chars, const in
  * device entry points that have no *_host twin (bsq_embed, bsq_onehot_bcl, ...).  `stream` is made
  * to wait for the copy.  *d_bytes is biased so that residue k of h_bytes is (*d_bytes)[k], i.e. it
  * pairs with the unrebased *d_offsets exactly like h_bytes pairs with h_offsets.  The buffers stay
- * valid until the next *_host / bsq_stage_host call on this stager; call bsq_stage_release after
+ * valid until the next *_host / *_items / bsq_stage_host call on this stager; call bsq_stage_release after
  * enqueuing the kernels that read them so that the next staging waits for those kernels. */
 int bsq_stage_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const int64_t *h_offsets, int64_t nseq,
                    const uint8_t **d_bytes, const int64_t **d_offsets);
@@ -287,6 +322,9 @@ int bsq_fastx_lengths(const char *path, int64_t **lens, int64_t *n);
 void bsq_free(void *p);
 
 /* ---- misc -------------------------------------------------------------------------- */
+/* Measurement aid: a plain cudaMemcpyAsync device->device on `stream` (bench.py times it on the same rotating
+ * buffers as the tokeniser to put a copy of the same HBM traffic next to the kernel's number). */
+int bsq_memcpy_d2d(int device, void *stream, void *d_dst, const void *d_src, size_t nbytes);
 int bsq_abi_version(void);
 const char *bsq_last_error(void);
 /* number of kernel launches issued by this library on the calling thread since the last

@@ -340,7 +340,8 @@ def test_single_sequence_onehot_encode():
     for key, flags in (("DNA", {}), ("DNA", dict(bos=True, eos=True, padchar=True)), ("PROTEIN", dict(eos=True, padchar=True))):
         ref_t, t = R.Tokenizer(key, **flags), bioseq_b200.Tokenizer(key, **flags)
         for seq in ("ACGT", "", "ACGTACGTAC", b"GATTACA", bytearray(b"CCGG")):
-            for padlen in (0, 3, 12):
+            # len + 1: with BOS + EOS + padchar the EOS row lies at `padlen` itself (it must not be zeroed)
+            for padlen in (0, 3, 12, len(seq) + 1, len(seq)):
                 if padlen and len(seq) > padlen:
                     with pytest.raises(RuntimeError, match="padlen is too short"):
                         t.onehot_encode(seq, padlen)

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/bsq.h but not exported by libbsq.so"
     assert sorted(capi.EXPORTS) == names, "capi.py binding list out of sync with include/bsq.h"
-    assert capi.lib().bsq_abi_version() == 3
+    assert capi.lib().bsq_abi_version() == 4
 
 
 def test_alphabet_registry_and_luts(golden):
