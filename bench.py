@@ -178,7 +178,7 @@ def run_reference(args):
     if rank != 0:
         return
     buf, offs = make_batch(102)
-    res, _ = cpu_arm(buf, offs, args.steps, args.warmup, budget_s=120.0)
+    res, _ = cpu_arm(buf, offs, args.steps, args.warmup, budget_s=120.0, opt=args.ref_opt, nthreads=args.ref_threads or None)
     line = {"impl": "reference", "metric": "tokenize_throughput", "value": res["value"], "unit": "Gbases/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -189,17 +189,69 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def cpu_arm_subprocess(opt, nthreads, steps=3, warmup=1):
+    """Another build / thread count of the reference, timed in its own process (the -O3 and -O0 builds both register
+    the pybind11 type `Tokenizer`: only one of them can live in a process)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup),
+           "--ref-opt", opt, "--ref-threads", str(nthreads)]
+    env = dict(os.environ)
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env).stdout.strip().splitlines()
+        d = json.loads(out[-1])
+        return dict(d["cpu_baseline"], ms_per_step=d["ms_per_step"])
+    except Exception as e:   # a missing -O0 build etc.: reported, not fatal
+        return {"unavailable": repr(e)[:200]}
+
+
+def rank_batches(rank, world):
+    """This rank's ROT batches.  N = 1: BASELINE.json configs[1] as is (seed 102 + r).  N > 1: the N ranks' batches are
+    one global batch of N x 65536 sequences (chunk c = gen(102 + 1000 c + r)), partitioned the way DESIGN.md section 6
+    describes -- contiguous sequence ranges holding equal shares of the RESIDUES (bioseq_b200/shard.py, the same split
+    as the C ABI's bsq_shard_bounds) -- so the byte-balanced partition is the one that is timed."""
+    sy = synth()
+    if world == 1:
+        return [make_batch(102 + r) for r in range(ROT)], None
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_bsq_shard", os.path.join(ROOT, "bioseq_b200", "shard.py"))
+    sh = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sh)
+    sets, info = [], []
+    for r in range(ROT):
+        lens = np.concatenate([sy.gen_lens(102 + 1000 * c + r, NSEQ, LO, HI) for c in range(world)])
+        goffs = np.zeros(lens.size + 1, dtype=np.int64)
+        np.cumsum(lens, out=goffs[1:])
+        bounds = sh.shard_bounds(goffs, world)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        parts = []
+        for c in range(lo // NSEQ, (hi - 1) // NSEQ + 1):
+            cb, co = sy.gen(102 + 1000 * c + r, NSEQ, LO, HI, sy.AA20)
+            i0, i1 = max(lo - c * NSEQ, 0), min(hi - c * NSEQ, NSEQ)
+            parts.append(cb[co[i0]:co[i1]])
+        buf = np.ascontiguousarray(np.concatenate(parts))
+        offs = np.ascontiguousarray(goffs[lo:hi + 1] - goffs[lo])
+        assert offs[-1] == buf.size
+        sets.append((buf, offs))
+        info.append({"first_seq": lo, "nseq": hi - lo, "bases": int(buf.size)})
+    return sets, info
+
+
 def run_ours(args):
     import torch
     import ctypes as C
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpus = os.cpu_count() or 1
+    # host threads per rank for the pack / bounce loops: the ranks of one box share its cores
+    host_threads = max(1, (cpus * 3 // 4) // world)
+    os.environ.setdefault("BSQ_POOL_CAP", str(host_threads))
     from bioseq_b200 import capi
     import bioseq_b200
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -211,16 +263,17 @@ def run_ours(args):
     ptok = bioseq_b200.Tokenizer(KEY, **FLAGS)
 
     # ---- inputs: ROT distinct batches per rank, resident in HBM ---------------------------------
+    batches, shard_info = rank_batches(rank, world)
     sets = []
-    for r in range(ROT):
-        buf, offs = make_batch(102 + 1000 * rank + r)
-        sets.append({"buf": buf, "offs": offs, "nbases": int(offs[-1]),
+    for buf, offs in batches:
+        n = len(offs) - 1
+        sets.append({"buf": buf, "offs": offs, "n": n, "nbases": int(offs[-1]),
                      "d_bytes": torch.from_numpy(buf).cuda(), "d_offs": torch.from_numpy(offs).cuda(),
-                     "out": torch.empty((NSEQ, PADLEN), dtype=torch.uint8, device="cuda")})
+                     "out": torch.empty((n, PADLEN), dtype=torch.uint8, device="cuda")})
     st = torch.cuda.current_stream().cuda_stream
     for s in sets:
-        capi.check_lengths_device(dev, st, s["d_offs"], NSEQ, PADLEN, tok)
-    calls = [(dev, st, s["d_bytes"].data_ptr(), s["d_offs"].data_ptr(), NSEQ, PADLEN, C.byref(tok), 1, capi.I8,
+        capi.check_lengths_device(dev, st, s["d_offs"], s["n"], PADLEN, tok)
+    calls = [(dev, st, s["d_bytes"].data_ptr(), s["d_offs"].data_ptr(), s["n"], PADLEN, C.byref(tok), 1, capi.I8,
               s["out"].data_ptr()) for s in sets]
 
     def step(i):
@@ -256,6 +309,29 @@ def run_ours(args):
     barrier()
     launches = int(L.bsq_launch_count())
     ms_total = ev[0].elapsed_time(ev[1])
+    bases_timed = sum(sets[i % ROT]["nbases"] for i in range(args.steps))
+    alg_bytes = sum(algorithmic_bytes(sets[i % ROT]["nbases"], sets[i % ROT]["n"], PADLEN) for i in range(args.steps))
+
+    # ---- the same HBM traffic as a plain device-to-device copy, in the same run, rotated the same way -------------
+    # (cudaMemcpyAsync of half the step's algorithmic bytes: reads n and writes n.)  What a 103 MB launch can reach at
+    # all on this part -- launch ramp and tail included -- is this number, not the 2 GiB burst copy of MEASURED_PEAKS.
+    half = int(alg_bytes / args.steps / 2) // 256 * 256
+    half = min(half, min(s["out"].numel() for s in sets))
+    cdst = [torch.empty(half, dtype=torch.uint8, device="cuda") for _ in range(ROT)]
+
+    def copy_step(i):
+        L.bsq_memcpy_d2d(dev, st, cdst[i % ROT].data_ptr(), sets[i % ROT]["out"].data_ptr(), half)
+    for i in range(args.warmup):
+        copy_step(i)
+    barrier()
+    ev[0].record()
+    for i in range(args.steps):
+        copy_step(i)
+    ev[1].record()
+    barrier()
+    copy_us = ev[0].elapsed_time(ev[1]) / args.steps * 1e3
+    del cdst
+
     clocks_early = None
     if args.smi == "value":
         # K steps last a few ms, less than one nvidia-smi sampling period: keep the very same launches going
@@ -271,87 +347,102 @@ def run_ours(args):
             clocks_early = sampler.stop()
             clocks_early["sampled_over"] = "warm-up, the K timed launches and 1.2 s of the same launches back to back (untimed)"
         barrier()
-    bases_timed = sum(sets[i % ROT]["nbases"] for i in range(args.steps))
-    alg_bytes = sum(algorithmic_bytes(sets[i % ROT]["nbases"], NSEQ, PADLEN) for i in range(args.steps))
 
-    # ---- e2e: public Python API, pinned host buffers, H2D inside the timed region ----------------
+    # ---- e2e: the reference's own call -- Tokenizer.batch_tokenize(list[bytes]) -- with HOST items: item walk, pinned
+    # pack, host->device copies and kernels inside the timed region, plus a device->host read of the last output row ----
+    sections = set(args.sections.split(","))
+    as_list = synth().as_list
+    lists = [as_list(s["buf"], s["offs"]) for s in sets] if "e2e" in sections else None
     pinned = [(torch.from_numpy(s["buf"]).pin_memory(), torch.from_numpy(s["offs"]).pin_memory()) for s in sets]
     last = torch.empty(PADLEN, dtype=torch.uint8).pin_memory()
 
     def e2e_step(i):
-        hb, ho = pinned[i % ROT]
-        out = ptok.batch_tokenize_packed(hb, ho, padlen=PADLEN, destchar="B", batch_first=True)
-        last.copy_(out[NSEQ - 1], non_blocking=True)
+        out = ptok.batch_tokenize(lists[i % ROT], padlen=PADLEN, destchar="B", batch_first=True, nthreads=host_threads)
+        last.copy_(out[-1], non_blocking=True)
         return out
 
-    sections = set(args.sections.split(","))
+    def e2e_packed_step(i):
+        hb, ho = pinned[i % ROT]
+        out = ptok.batch_tokenize_packed(hb, ho, padlen=PADLEN, destchar="B", batch_first=True)
+        last.copy_(out[-1], non_blocking=True)
+        return out
+
+    def timed_region(fn, nsteps, repeats):
+        """`repeats` back-to-back repeats of the same nsteps-step region; the median repeat is reported (a host hiccup --
+        page-locking, another tenant of the box -- inside one repeat would otherwise decide the number)."""
+        reps, out = [], None
+        for _ in range(repeats):
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(nsteps):
+                out = fn(i)
+            torch.cuda.synchronize()
+            reps.append(time.perf_counter() - t0)
+        return sorted(reps)[len(reps) // 2], reps, out
+
     e2e_steps = max(3, min(args.steps, 50)) if "e2e" in sections else 1
-    for i in range(2 * ROT if "e2e" in sections else 0):   # every pinned set goes through the link once before timing
-        e2e_step(i)
-    # three back-to-back repeats of the same K-step region; the median repeat is reported (a host hiccup --
-    # page-locking, another tenant of the box -- inside one repeat would otherwise decide the number)
-    e2e_repeats = []
-    for _ in range(3 if "e2e" in sections else 1):
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(e2e_steps):
-            out = e2e_step(i)
-        torch.cuda.synchronize()
-        e2e_repeats.append(time.perf_counter() - t0)
-    e2e_s = sorted(e2e_repeats)[len(e2e_repeats) // 2]
+    e2e_s, e2e_repeats, e2e_ok, packed_s, packed_repeats, packed_ok = 1.0, [1.0], None, 1.0, [1.0], None
+    if "e2e" in sections:
+        for i in range(2 * ROT):   # every set goes through the link once before timing
+            e2e_step(i)
+        e2e_s, e2e_repeats, out = timed_region(e2e_step, e2e_steps, 3)
+        e2e_ok = bool(torch.equal(out, sets[(e2e_steps - 1) % ROT]["out"]))
+        for i in range(2 * ROT):
+            e2e_packed_step(i)
+        packed_s, packed_repeats, out = timed_region(e2e_packed_step, e2e_steps, 3)
+        packed_ok = bool(torch.equal(out, sets[(e2e_steps - 1) % ROT]["out"]))
+        del out
     barrier()
-    e2e_ok = bool(torch.equal(out, sets[(e2e_steps - 1) % ROT]["out"]))
-    # host link: every rank copies at the same moment (barrier-aligned), the way the e2e steps load the box;
-    # the sum over ranks is the roofline of the e2e number (at N=8 well below N x the single-GPU rate)
+    # host link: every rank copies at the same moment (barrier-aligned); the sum over ranks is the roofline of the
+    # e2e numbers (at N=8 well below N x the single-GPU rate)
     host_link = None
     if "e2e" in sections:
         barrier()
-        host_link = measure_host_link(torch)
-        hl = torch.tensor([host_link["h2d_gbs"], host_link["h2d_gbs_4MiB_copies"]], dtype=torch.float64, device="cuda")
+        host_link = measure_host_link(torch, barrier)
+        hl = torch.tensor([host_link["h2d_gbs"]], dtype=torch.float64, device="cuda")
         if dist is not None:
             dist.all_reduce(hl, op=dist.ReduceOp.SUM)
-        host_link["h2d_gbs_all_ranks_concurrent"], host_link["h2d_gbs_4MiB_copies_all_ranks_concurrent"] = hl.tolist()
+        host_link["h2d_gbs_all_ranks_concurrent"] = hl.tolist()[0]
         barrier()
-    # the reference's own calling convention: a Python list of bytes objects (walk + pinned pack + H2D + kernel)
-    e2e_list = None
-    if "e2e" in sections and rank == 0:
-        from bioseq_b200.synth import as_list
-        seqs = as_list(sets[0]["buf"], sets[0]["offs"])
-        nthreads = os.cpu_count() or 1   # libbsq caps its pool at half the hardware threads
-        for _ in range(2):
-            ptok.batch_tokenize(seqs, padlen=PADLEN, destchar="B", batch_first=True, nthreads=nthreads)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        nrep = 10
-        for _ in range(nrep):
-            o2 = ptok.batch_tokenize(seqs, padlen=PADLEN, destchar="B", batch_first=True, nthreads=nthreads)
-        torch.cuda.synchronize()
-        dt = (time.perf_counter() - t0) / nrep
-        e2e_list = {"value": sets[0]["nbases"] / dt / 1e9, "unit": "Gbases/s", "ms_per_call": dt * 1e3,
-                    "api": f"Tokenizer.batch_tokenize(list[bytes], nthreads={nthreads})",
-                    "matches_device_resident": bool(torch.equal(o2, sets[0]["out"]))}
-        del seqs
+    lists = None
     e2e_bases = sum(sets[i % ROT]["nbases"] for i in range(e2e_steps))
-    h2d = int(np.mean([s["nbases"] + 8 * (NSEQ + 1) for s in sets]))
+    h2d = int(np.mean([s["nbases"] + 8 * (s["n"] + 1) for s in sets]))
 
-    # ---- C5 slice on every rank (configs[4]: sharded tokenize + one-hot with H2D staging) ----------
+    # ---- parity of the timed output on EVERY rank: the reference's own tokenizer on a sample of this rank's batch ----
+    step(0)
+    torch.cuda.synchronize()
+    parity_rank = rank_parity(sets[0], as_list)
+
+    # ---- C5 on every rank (configs[4]: sharded tokenize + one-hot with H2D staging) ----------
     c5 = None
     if "c5" in sections:
         barrier()
         c5 = c5_slice(torch, capi, L, dev, st, rank)
         barrier()
+    c5f = None
+    if "c5full" in sections or ("c5" in sections and world == 8 and args.c5full != "off") or args.c5full == "on":
+        barrier()
+        c5f = c5_full(torch, capi, L, dev, st, rank, world, barrier, host_threads, with_cpu=(rank == 0))
+        barrier()
 
     # ---- reduce over ranks: max time ------------------------------------------------------------
     c5v = [c5["ms_h2d_inclusive"], c5["ms_device_resident"]] if c5 else [0.0, 0.0]
     c5s = [c5["bases"], c5["h2d_bytes"], c5["alg_bytes_device"], c5["bases_device"]] if c5 else [0.0] * 4
-    t = torch.tensor([ms_total, e2e_s * 1e3] + c5v, dtype=torch.float64, device="cuda")
-    tot = torch.tensor([float(bases_timed), float(e2e_bases), float(alg_bytes), float(launches)] + [float(x) for x in c5s],
+    c5fv = [c5f["ms_pass"]] if c5f else [0.0]
+    c5fs = [c5f["bases"], c5f["h2d_bytes"], float(c5f["parity"])] if c5f else [0.0, 0.0, 1.0]
+    t = torch.tensor([ms_total, e2e_s * 1e3, packed_s * 1e3, copy_us] + c5v + c5fv, dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(bases_timed), float(e2e_bases), float(alg_bytes), float(launches)] + [float(x) for x in c5s] + c5fs[:2],
                        dtype=torch.float64, device="cuda")
+    ok = torch.tensor([float(parity_rank["ok"]), float(e2e_ok is not False), float(packed_ok is not False), c5fs[2]], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    ms_total_max, e2e_ms_max, c5_ms_h2d, c5_ms_dev = t.tolist()
-    bases_all, e2e_bases_all, alg_all, launches_all, c5_bases, c5_h2d_bytes, c5_alg, c5_bases_dev = tot.tolist()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    ms_total_max, e2e_ms_max, packed_ms_max, copy_us_max, c5_ms_h2d, c5_ms_dev, c5f_ms = t.tolist()
+    bases_all, e2e_bases_all, alg_all, launches_all, c5_bases, c5_h2d_bytes, c5_alg, c5_bases_dev, c5f_bases, c5f_h2d = tot.tolist()
+    parity_all, e2e_all_ok, packed_all_ok, c5f_parity = [bool(x) for x in ok.tolist()]
+    if not parity_all:
+        raise SystemExit("bench.py: GPU output differs from the CPU reference on at least one rank -- refusing to report a number")
 
     extra = {}
     cpu = None
@@ -364,45 +455,62 @@ def run_ours(args):
         if "c4" in sections and world == 1:
             extra["c4_reduced_alphabets_1M_roundtrip"] = c4_measurements(torch, capi, L, dev, st, with_cpu="cpu" in sections)
         clocks = clocks_early if clocks_early is not None else sampler.stop()
+        cpu_more = {}
         if world == 1 and "cpu" in sections:
             cpu, ref_out = cpu_arm(sets[0]["buf"], sets[0]["offs"], steps=10, warmup=1, budget_s=20.0)
-            step(0)
-            torch.cuda.synchronize()
             parity = bool(np.array_equal(np.ascontiguousarray(ref_out).view(np.uint8), sets[0]["out"].cpu().numpy()))
             if not parity:
                 raise SystemExit("bench.py: GPU output differs from the CPU reference -- refusing to report a number")
+            # the reference as shipped (-O0, setup.py:50-55) and the one-thread picture
+            cpu_more["cpu_baseline_O0"] = cpu_arm_subprocess("O0", cpus)
+            cpu_more["cpu_baseline_1thread"] = cpu_arm_subprocess("O3", 1)
         peak, peak_src = measured_peak()
         per_launch_ms = ms_total / launches if launches else float("nan")          # this rank's launches
         achieved = (alg_bytes / max(launches, 1)) / (per_launch_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("tokenize_rows_ring_kernel")
+                tj = json.load(open(tp))
+                traffic = tj.get("tokenize_span_kernel")
+                traffic_src = {k: tj.get(k) for k in ("captured_at_commit", "source", "note")}
             except Exception:
                 traffic = None
+        copy_bytes = 2 * half
         line = {
             "metric": "tokenize_throughput", "value": bases_all / (ms_total_max * 1e-3) / 1e9, "unit": "Gbases/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "seqs_per_gpu": NSEQ, "padlen": PADLEN,
-                       "bases_per_step_per_gpu": int(np.mean([s["nbases"] for s in sets])),
-                       "l2": f"inputs+outputs rotate through {ROT} distinct 103 MB sets (> 126 MB L2)",
-                       "parallelism": f"{world} ranks, sequences sharded by index, no collective"},
+            "config": bench_config(world),
+            "bases_per_step_per_gpu": int(np.mean([s["nbases"] for s in sets])), "shard_of_rank0": shard_info,
             "e2e": {"value": e2e_bases_all / (e2e_ms_max * 1e-3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": PADLEN, "steps": e2e_steps,
-                    "repeats_ms_per_step": [round(x * 1e3 / e2e_steps, 4) for x in e2e_repeats], "api": "Tokenizer.batch_tokenize_packed(pinned host)",
-                    "matches_device_resident": e2e_ok, "list_of_bytes_api": e2e_list,
+                    "api": f"Tokenizer.batch_tokenize(list[bytes], padlen=1024, batch_first=True, nthreads={host_threads}) -- the reference's own call (src/tokenize.cpp:82-98)",
+                    "repeats_ms_per_step": [round(x * 1e3 / e2e_steps, 4) for x in e2e_repeats],
+                    "matches_device_resident": e2e_all_ok, "host_threads_per_rank": host_threads, "host_cpus": cpus,
+                    "packed_pinned_input": {"value": e2e_bases_all / (packed_ms_max * 1e-3) / 1e9, "unit": "Gbases/s",
+                                            "api": "Tokenizer.batch_tokenize_packed(pinned bytes, pinned offsets) -- additive entry point, no per-item host work",
+                                            "repeats_ms_per_step": [round(x * 1e3 / e2e_steps, 4) for x in packed_repeats],
+                                            "matches_device_resident": packed_all_ok},
                     "host_link": None if host_link is None else dict(
-                        host_link, frac=(h2d * e2e_steps * world / (e2e_ms_max * 1e-3) / 1e9) / host_link["h2d_gbs_all_ranks_concurrent"],
-                        note="frac = e2e H2D bytes/s over the pinned cudaMemcpyAsync H2D rate of all ranks copying at once (256 MiB copies)")},
+                        host_link,
+                        frac_list_api=(h2d * e2e_steps * world / (e2e_ms_max * 1e-3) / 1e9) / host_link["h2d_gbs_all_ranks_concurrent"],
+                        frac_packed=(h2d * e2e_steps * world / (packed_ms_max * 1e-3) / 1e9) / host_link["h2d_gbs_all_ranks_concurrent"],
+                        note="frac = e2e H2D bytes/s over the pinned H2D rate of all ranks copying at once (best of 256 MiB copies and double-buffered 46 MB copies)")},
             "gpu_launches": int(launches_all),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "tokenize_rows_ring_kernel<2,true> (K1r)",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "tokenize_span_kernel (K1s)",
                          "algorithmic_bytes_per_launch": int(alg_bytes / max(launches, 1)),
-                         "launch_us": per_launch_ms * 1e3},
-            "cpu_baseline": cpu, "parity_vs_cpu_reference": parity, "clocks": clocks, "extra": extra,
+                         "launch_us": per_launch_ms * 1e3,
+                         "copy_reference": {"what": "cudaMemcpyAsync device-to-device of the same traffic (read n + write n), same rotation, same run, max over ranks",
+                                            "bytes": copy_bytes, "us": copy_us_max, "GB/s": copy_bytes / copy_us_max / 1e3,
+                                            "frac_of_peak": copy_bytes / copy_us_max / 1e3 / peak,
+                                            "kernel_us_over_copy_us": per_launch_ms * 1e3 / copy_us_max}},
+            "cpu_baseline": cpu, "parity_vs_cpu_reference": parity, "parity_every_rank": dict(parity_rank, all_ranks_ok=parity_all),
+            "clocks": clocks, "extra": extra,
         }
+        line.update(cpu_more)
         if c5:
             hl = (host_link or {}).get("h2d_gbs_all_ranks_concurrent")
             line["c5_slice"] = {
@@ -415,10 +523,35 @@ def run_ours(args):
                 "device_resident": {"Gbases/s": c5_bases_dev / c5_ms_dev / 1e6, "ms_per_pass": c5_ms_dev, "GB/s_all_ranks": c5_alg / c5_ms_dev / 1e6,
                                     "frac_of_measured_hbm": c5_alg / c5_ms_dev / 1e6 / (peak * world)},
             }
+        if c5f:
+            hl = (host_link or {}).get("h2d_gbs_all_ranks_concurrent")
+            line["c5_full"] = dict(c5f["report"], n_gpus=world, seqs_total=int(c5f["nseq"]) * world, bases_total=int(c5f_bases),
+                                   ms_per_pass_max_over_ranks=c5f_ms, Gbases_per_s=c5f_bases / c5f_ms / 1e6,
+                                   h2d_GBs_all_ranks=c5f_h2d / c5f_ms / 1e6,
+                                   frac_of_host_link=None if not hl else c5f_h2d / c5f_ms / 1e6 / hl,
+                                   parity_sampled_chunk_every_rank=c5f_parity)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def rank_parity(s, as_list, sample=4096):
+    """The reference's own tokenizer (oracle/_ref; the C restatement if it is absent) on the first `sample` sequences of a
+    batch, compared bit for bit with the GPU output of that batch."""
+    from oracle.oracle import load_ref, OracleTokenizer
+    m = min(sample, s["n"])
+    offs = s["offs"][:m + 1]
+    buf = s["buf"][:int(offs[-1])]
+    R = load_ref()
+    if R is not None:
+        want = R.Tokenizer(KEY, **FLAGS).batch_tokenize(as_list(buf, offs), padlen=PADLEN, destchar="B", batch_first=True, nthreads=2)
+        kind = "reference (oracle/_ref)"
+    else:
+        want = OracleTokenizer(KEY, **FLAGS).batch_tokenize((buf, offs), padlen=PADLEN, batch_first=True)
+        kind = "port (oracle/bsq_oracle.c)"
+    got = s["out"][:m].cpu().numpy()
+    return {"ok": bool(np.array_equal(np.ascontiguousarray(want).view(np.uint8), got)), "rows_checked_per_rank": m, "checker": kind}
 
 
 C4_KEYS = ("SEB6", "SEB8", "SEB10", "SEB14", "SEV10", "MURPHY", "LIA10", "LIB10", "DAYHOFF")
@@ -429,7 +562,7 @@ def c4_measurements(torch, capi, L, dev, st, with_cpu):
     sequences (gen(104, 1e6, 50, 1024, AA20); pos tokenizers at padlen 1024, pbeos at 1026)."""
     import ctypes as C
     import bioseq_b200
-    from bioseq_b200.synth import gen, AA20
+    gen, AA20 = synth().gen, synth().AA20
     peak, _ = measured_peak()
     n = 1_000_000
     buf, offs = gen(104, n, 50, 1024, AA20)
@@ -471,8 +604,9 @@ def c4_measurements(torch, capi, L, dev, st, with_cpu):
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 3
+        nbytes = n * padlen + total + 8 * (n + 1)
         res["decode"][f"{key}_{flavour}_device"] = {"us_per_call": ms * 1e3, "Gtokens/s": n * padlen / ms / 1e6, "chars": int(total),
-                                                    "GB/s": (2 * n * padlen + total + 8 * (n + 1)) / ms / 1e6}
+                                                    "GB/s": nbytes / ms / 1e6, "frac_of_measured_hbm": nbytes / ms / 1e6 / peak}
         # the public call on a slice of rows: device decode + D2H of the characters + Python str objects
         ptk = bioseq_b200.Tokenizer(key, **flags)
         rows = 32768
@@ -484,7 +618,7 @@ def c4_measurements(torch, capi, L, dev, st, with_cpu):
                                                              "chars": sum(map(len, strs))}
         if with_cpu:
             # checker + CPU baseline of the round trip: the reference's own tokenizer on the same rows
-            from bioseq_b200.synth import as_list
+            as_list = synth().as_list
             from oracle.oracle import load_ref
             R = load_ref()
             if R is not None:
@@ -512,7 +646,7 @@ def c5_slice(torch, capi, L, dev, st, rank, nchunks=8, chunk=131072):
     pinned host -> device on a copy stream (double-buffered) and is tokenised (int8 (B,652)) and one-hot encoded
     (uint8 (652,B,23)) into a reused ring of two output buffers, like the full 8 M-sequences-per-GPU pass would."""
     import ctypes as C
-    from bioseq_b200.synth import gen, AA20
+    gen, AA20 = synth().gen, synth().AA20
     P, NC = 652, 23
     tk = capi.tokenizer(KEY, **FLAGS)
     host = []
@@ -574,6 +708,131 @@ def c5_slice(torch, capi, L, dev, st, rank, nchunks=8, chunk=131072):
             "nchunks": nchunks, "chunk": chunk, "padlen": P}
 
 
+def c5_full(torch, capi, L, dev, st, rank, world, barrier, host_threads, with_cpu, chunk=131072):
+    """BASELINE.json configs[4] at its stated size: 64 M synthetic protein sequences over 8 GPUs = 8 M per GPU (lengths
+    50..650, mean 350: 2.8 G residues per GPU; chunk seeds 105 + global chunk index as in SURVEY.md 8d C5), PROTEIN pbeos,
+    padlen 652.  Every rank streams its share from a FlatFile -- the reference's on-disk packed layout (src/fxstats.cpp:50-59:
+    u64 n | u64 offsets[n+1] | residues), consumed in bulk like FF2NP does (bioseq/loaders.py:11-26) -- in chunks of 131072
+    sequences: mapped file -> pinned bounce ring -> device (two staging slots: the copy of chunk k+1 overlaps the kernels of
+    chunk k), then int8 tokens (B, 652) and uint8 one-hot (652, B, 23) into a ring of two output buffers (the full one-hot
+    would be 122 GB per GPU).  BSQ_C5_SEQS overrides the sequences per GPU (smoke runs)."""
+    import ctypes as C
+    import shutil
+    import tempfile
+    sy = synth()
+    P, NC = 652, 23
+    nseq = int(os.environ.get("BSQ_C5_SEQS", str(8 * 1024 * 1024)))
+    nchunks = (nseq + chunk - 1) // chunk
+    tk = capi.tokenizer(KEY, **FLAGS)
+    root = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > (world + 1) * nseq * 400 else None
+    td = tempfile.mkdtemp(prefix=f"bsq_c5_rank{rank}_", dir=root)
+    path = os.path.join(td, "shard.ff")
+    t0 = time.perf_counter()
+    try:
+        sizes = [min(chunk, nseq - c * chunk) for c in range(nchunks)]
+        seeds = [105 + rank * nchunks + c for c in range(nchunks)]
+        offs = np.zeros(nseq + 1, dtype=np.int64)
+        pos = 0
+        for c in range(nchunks):
+            lens = sy.gen_lens(seeds[c], sizes[c], 50, 650)
+            np.cumsum(lens, out=offs[pos + 1:pos + 1 + sizes[c]])
+            offs[pos + 1:pos + 1 + sizes[c]] += offs[pos]
+            pos += sizes[c]
+        with open(path, "wb") as f:
+            f.write(np.array([nseq], dtype=np.uint64).tobytes())
+            f.write(offs.astype(np.uint64).tobytes())
+            for c in range(nchunks):
+                cb, co = sy.gen(seeds[c], sizes[c], 50, 650, sy.AA20)
+                f.write(cb.tobytes())
+        make_s = time.perf_counter() - t0
+        ff = capi.FlatFile(path)
+        assert ff.nseqs == nseq
+        fb, fo = ff.bytes_ptr, ff.offsets_ptr
+        stager = capi.Stager(dev)
+        toks = [torch.empty((chunk, P), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        oh = [torch.empty((P, chunk, NC), dtype=torch.uint8, device="cuda") for _ in range(2)]
+
+        def run_chunk(c, k):
+            n = sizes[c]
+            db, do = stager.stage(st, fb, fo + 8 * c * chunk, n)
+            L.bsq_tokenize(dev, st, db, do, n, P, C.byref(tk), 1, capi.I8, toks[k].data_ptr())
+            rc = L.bsq_onehot(dev, st, db, do, None, n, P, C.byref(tk), capi.I8, oh[k].data_ptr())
+            if rc:
+                capi.check(rc)
+            stager.release(st)
+
+        for c in range(min(2, nchunks)):   # warm-up: allocations, page-locking of the ring, kernels
+            run_chunk(c, c % 2)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        for c in range(nchunks):
+            run_chunk(c, c % 2)
+        torch.cuda.synchronize()
+        ms_pass = (time.perf_counter() - t0) * 1e3
+        # parity: one sampled chunk per rank, its first rows against the reference's own tokenizer
+        cs = (7 * rank + 3) % nchunks
+        run_chunk(cs, 0)
+        torch.cuda.synchronize()
+        m = min(2048, sizes[cs])
+        cb, co = sy.gen(seeds[cs], sizes[cs], 50, 650, sy.AA20)
+        seqs = sy.as_list(cb[:int(co[m])], co[:m + 1])
+        from oracle.oracle import load_ref, OracleTokenizer
+        R = load_ref()
+        if R is not None:
+            rt = R.Tokenizer(KEY, **FLAGS)
+            want_t = rt.batch_tokenize(seqs, padlen=P, destchar="B", batch_first=True, nthreads=2)
+            want_o = rt.batch_onehot_encode(seqs, padlen=P, destchar="B", nthreads=2)
+        else:
+            ot = OracleTokenizer(KEY, **FLAGS)
+            want_t = ot.batch_tokenize((cb[:int(co[m])], co[:m + 1]), padlen=P, batch_first=True)
+            want_o = ot.batch_onehot_encode((cb[:int(co[m])], co[:m + 1]), padlen=P, destchar="B")
+        ok = bool(np.array_equal(np.ascontiguousarray(want_t).view(np.uint8), toks[0][:m].cpu().numpy())) and \
+            bool(np.array_equal(np.ascontiguousarray(want_o).view(np.uint8), oh[0][:, :m, :].contiguous().cpu().numpy()))
+        cpu = None
+        if with_cpu and R is not None:
+            # CPU arm, extrapolated as SURVEY.md 8(d) prescribes: the reference on chunks that fit the host, scaled to 64 M
+            rt = R.Tokenizer(KEY, **FLAGS)
+            cores = os.cpu_count() or 1
+            nseq_cpu = min(1 << 20, nseq)
+            parts = [sy.gen(seeds[c], sizes[c], 50, 650, sy.AA20) for c in range((nseq_cpu + chunk - 1) // chunk)]
+            big = [x for cb_, co_ in parts for x in sy.as_list(cb_, co_)][:nseq_cpu]
+            bases_cpu = sum(map(len, big))
+            rt.batch_tokenize(big[:8192], padlen=P, destchar="B", batch_first=True, nthreads=cores)
+            tt = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                rt.batch_tokenize(big, padlen=P, destchar="B", batch_first=True, nthreads=cores)
+                tt.append(time.perf_counter() - t0)
+            small = big[:65536]
+            bases_small = sum(map(len, small))
+            to = []
+            for _ in range(2):
+                t0 = time.perf_counter()
+                rt.batch_onehot_encode(small, padlen=P, destchar="B", nthreads=cores)
+                to.append(time.perf_counter() - t0)
+            total_bases = 64 * (1 << 20) * 350.0
+            s_tok, s_oh = min(tt) / bases_cpu * total_bases, min(to) / bases_small * total_bases
+            cpu = {"kind": "reference", "cores": cores, "extrapolated": True,
+                   "sample": f"oracle/_ref -O3: batch_tokenize on {nseq_cpu} sequences ({bases_cpu} bases, best of 2: {min(tt) * 1e3:.1f} ms) and "
+                             f"batch_onehot_encode uint8 on 65536 sequences ({bases_small} bases, best of 2: {min(to) * 1e3:.1f} ms), nthreads={cores}, "
+                             "list[bytes] input already in memory; scaled linearly to 64 M sequences x mean 350",
+                   "tokenize_s_for_64M": s_tok, "onehot_s_for_64M": s_oh,
+                   "Gbases/s_tokenize_plus_onehot": total_bases / (s_tok + s_oh) / 1e9}
+        bases = int(offs[-1])
+        report = {"workload": ("configs[4] at full size: 8 M synthetic protein sequences per GPU (len 50-650, mean 350) streamed from a FlatFile per rank "
+                               f"in {nchunks} chunks of {chunk}: mapped file -> pinned bounce ring -> device (2 staging slots), int8 tokens (B,652) + "
+                               "uint8 one-hot (652,B,23) into a ring of 2 output buffers; PROTEIN pbeos"),
+                  "seqs_per_gpu": nseq, "chunks_per_gpu": nchunks, "padlen": P, "file_bytes_per_gpu": os.path.getsize(path),
+                  "file_dir": root or tempfile.gettempdir(), "file_make_s_rank0": make_s, "cpu_baseline": cpu,
+                  "device_bytes_written_per_gpu": nseq * P * (1 + NC)}
+        stager.close()
+        ff.close()
+        return {"ms_pass": ms_pass, "bases": bases, "h2d_bytes": bases + 8 * (nseq + nchunks), "parity": ok, "nseq": nseq, "report": report}
+    finally:
+        shutil.rmtree(td, ignore_errors=True)
+
+
 def f_rows_measurements(torch, capi, L, dev, st):
     """SURVEY.md 8(f) rows built next to the hot path, each at the C2 batch (65536 ragged protein sequences, P = 1024)
     unless stated: K5 one-hot straight into the CNN's (B,C,L) float layout, K6 tokenize -> embedding rows, K7 BLOSUM62
@@ -581,7 +840,7 @@ def f_rows_measurements(torch, capi, L, dev, st):
     import ctypes as C
     import tempfile
     import bioseq_b200
-    from bioseq_b200.synth import gen, AA20
+    gen, AA20 = synth().gen, synth().AA20
     peak, _ = measured_peak()
     res = {}
 
@@ -677,33 +936,42 @@ def f_rows_measurements(torch, capi, L, dev, st):
     return res
 
 
-def measure_host_link(torch, nbytes=256 << 20, reps=5):
-    """Pinned host->device copy rate of this rank's link (the roofline of the e2e number)."""
+def measure_host_link(torch, barrier, nbytes=256 << 20, reps=5):
+    """Pinned host->device copy rate of this rank's link with every rank copying at the same moment: the best of
+    (a) back-to-back 256 MiB copies and (b) 46 MB copies alternating between two buffers on two streams (the shape of
+    the staged pipelines) -- a denominator no measured section should exceed."""
     h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
     d.copy_(h, non_blocking=True)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(reps):
-        d.copy_(h, non_blocking=True)
-    b.record()
-    torch.cuda.synchronize()
-    big = nbytes * reps / (a.elapsed_time(b) * 1e-3) / 1e9
-    hs, ds = h[:4 << 20], d[:4 << 20]
-    a.record()
-    for _ in range(32):
-        ds.copy_(hs, non_blocking=True)
-    b.record()
-    torch.cuda.synchronize()
-    small = (4 << 20) * 32 / (a.elapsed_time(b) * 1e-3) / 1e9
-    return {"h2d_gbs": big, "h2d_gbs_4MiB_copies": small, "bytes": nbytes}
+    best_big = 0.0
+    for _ in range(2):
+        barrier()
+        a.record()
+        for _ in range(reps):
+            d.copy_(h, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        best_big = max(best_big, nbytes * reps / (a.elapsed_time(b) * 1e-3) / 1e9)
+    m = 46 << 20
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    best_db = 0.0
+    for _ in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(16):
+            with torch.cuda.stream(streams[k % 2]):
+                d[(k % 2) * m:(k % 2 + 1) * m].copy_(h[(k % 4) * m:(k % 4 + 1) * m], non_blocking=True)
+        torch.cuda.synchronize()
+        best_db = max(best_db, 16 * m / (time.perf_counter() - t0) / 1e9)
+    return {"h2d_gbs": max(best_big, best_db), "h2d_gbs_256MiB_copies": best_big, "h2d_gbs_double_buffered_46MB": best_db, "bytes": nbytes}
 
 
 def secondary_measurements(torch, capi, L, dev, st):
     """Other BASELINE.json configs, device-resident, reported under "extra" (not the headline)."""
     import ctypes as C
-    from bioseq_b200.synth import gen
+    gen = synth().gen
     peak, _ = measured_peak()
     res = {}
 
@@ -761,7 +1029,7 @@ def secondary_measurements(torch, capi, L, dev, st):
     del out, d_b, d_o
 
     # C2 variants: seq-first, unaligned padlen, protein one-hot u8, decode
-    from bioseq_b200.synth import AA20
+    AA20 = synth().AA20
     ptk = capi.tokenizer(KEY, **FLAGS)
     buf, offs = gen(102, NSEQ * 4, LO, HI, AA20)
     nbases = int(offs[-1])
@@ -797,7 +1065,8 @@ def secondary_measurements(torch, capi, L, dev, st):
         L.bsq_decode_lengths(dev, st, toks.data_ptr(), 1, n4, 1024, 1024, 1, C.byref(ptk), d_ro.data_ptr(), C.byref(tot))
         L.bsq_decode_chars(dev, st, toks.data_ptr(), 1, n4, 1024, 1024, 1, C.byref(ptk), d_ro.data_ptr(), d_ch.data_ptr())
     ms = timed(dec, 5)
-    res["c2x4_decode_tokens_device"] = {"Gtokens/s": n4 * 1024 / ms / 1e6, "GB/s": (2 * n4 * 1024 + total) / ms / 1e6,
+    nbytes = n4 * 1024 + total + 8 * (n4 + 1)   # B.P.s_in + sum(strlen) + 8 (B + 1): every token read once
+    res["c2x4_decode_tokens_device"] = {"Gtokens/s": n4 * 1024 / ms / 1e6, "GB/s": nbytes / ms / 1e6, "frac_of_measured_hbm": nbytes / ms / 1e6 / peak,
                                         "us_per_call": ms * 1e3, "chars": int(total)}
     return res
 
@@ -810,6 +1079,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--smi", default="value", choices=["value", "all", "off"],
                     help="nvidia-smi clock sampler: over the device-timed region only (default), the whole run, or off")
+    ap.add_argument("--ref-opt", default="O3", choices=["O3", "O0"], help="reference arm: which build of oracle/_ref to time")
+    ap.add_argument("--ref-threads", type=int, default=0, help="reference arm: nthreads (0 = all host cores)")
+    ap.add_argument("--c5full", default="auto", choices=["auto", "on", "off"],
+                    help="configs[4] at full size (8 M sequences per GPU streamed from a FlatFile): auto = only at --gpus 8")
     ap.add_argument("--sections", default="value,e2e,extra,frows,cpu,c4,c5",
                     help="comma list of measurement sections to run (profiling runs use --sections value)")
     args = ap.parse_args()

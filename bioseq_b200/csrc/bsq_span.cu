@@ -33,6 +33,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <unordered_map>
 
 #include "bsq_internal.h"
 #include "bsq_kernels.cuh"
@@ -82,8 +83,11 @@ struct SpanParams {
     int64_t nseq;
     int64_t total;    // nseq * padlen output bytes
     int64_t ntiles;
-    int64_t step_rows;  // a CTA's next tile starts (gridDim.x * tile bytes) further on: that many whole rows ...
-    int step_cols;      // ... plus that many columns
+    // Tiles beyond a CTA's first (= blockIdx.x) are handed out by an atomic counter, gridDim.x + atomicAdd(ctr, 1):
+    // whatever the placement and start time of the CTAs (a programmatically launched grid gets its SM slots as the
+    // previous grid drains), the work stays balanced.  ctr[0] = tiles handed out, ctr[1] = CTAs that have seen the end;
+    // the last of those resets both for the slot's next launch.  nullptr: static round-robin (tile += gridDim.x).
+    unsigned int *ctr;
     int padlen;
     int vt;           // 16-byte vectors per tile (a multiple of kSpanConsumers)
     int stage_bytes;  // data area of a stage
@@ -181,26 +185,41 @@ __device__ __forceinline__ uint4 span_row_codes(uint32_t srow, int n, int c0, co
     return make_uint4(t[0], t[1], t[2], t[3]);
 }
 
-// Same for -16 < c0 < 0: the second half of a vector that straddles two rows (padlen % 16 != 0); bytes left of
-// column 0 are don't-care.
+// Unaligned rows: columns c0 .. c0+15 with -16 < c0 <= padlen - 16; for c0 < 0 the bytes left of column 0 are the
+// previous row's tail and are set to the pad code (the caller has checked that the previous row ends before them).
 template <bool PRE>
-__device__ __forceinline__ uint4 span_row_codes_neg(uint32_t srow, int n, int c0, const SpanRegs &g) {
-    uint32_t t[4] = {0u, 0u, 0u, 0u};
-    if (c0 < n && c0 + 16 > g.bos) span_window16<PRE>(srow + static_cast<uint32_t>(c0), g.lutb, t);
-    if (g.bos) {  // BOS sits at byte -c0 of the vector
-        const uint4 ma = lds128(g.tab_m - 16u * static_cast<uint32_t>(c0)), mb = lds128(g.tab_m + 16u - 16u * static_cast<uint32_t>(c0));
-        t[0] = (t[0] & ~(mb.x & ~ma.x)) | (g.bos_w & mb.x & ~ma.x);
-        t[1] = (t[1] & ~(mb.y & ~ma.y)) | (g.bos_w & mb.y & ~ma.y);
-        t[2] = (t[2] & ~(mb.z & ~ma.z)) | (g.bos_w & mb.z & ~ma.z);
-        t[3] = (t[3] & ~(mb.w & ~ma.w)) | (g.bos_w & mb.w & ~ma.w);
+__device__ __forceinline__ uint4 span_row_codes_u(uint32_t srow, int n, int c0, const SpanRegs &g) {
+    uint32_t t[4];
+    span_window16<PRE>(srow + static_cast<uint32_t>(c0), g.lutb, t);
+    if (c0 <= 0) {  // bytes [0, -c0): pad; byte -c0: BOS when the tokenizer has one
+        const uint32_t a = g.tab_m - 16u * static_cast<uint32_t>(c0);
+        const uint4 ma = lds128(a), mb = lds128(a + 16u * static_cast<uint32_t>(g.bos));
+        t[0] = (t[0] & ~mb.x) | (g.bos_w & mb.x & ~ma.x) | (g.padq.x & ma.x);
+        t[1] = (t[1] & ~mb.y) | (g.bos_w & mb.y & ~ma.y) | (g.padq.x & ma.y);
+        t[2] = (t[2] & ~mb.z) | (g.bos_w & mb.z & ~ma.z) | (g.padq.x & ma.z);
+        t[3] = (t[3] & ~mb.w) | (g.bos_w & mb.w & ~ma.w) | (g.padq.x & ma.w);
     }
-    if (c0 + 16 > n) {
+    if (c0 + 16 > n) {  // the row's residues end inside this vector: keep n - c0 bytes, then EOS / pad
         const uint32_t a = g.tab_m + 16u * static_cast<uint32_t>(n - c0);
         const uint4 m = lds128(a), f = lds128(a + 17u * 16u);
         t[0] = (t[0] & m.x) | f.x; t[1] = (t[1] & m.y) | f.y;
         t[2] = (t[2] & m.z) | f.z; t[3] = (t[3] & m.w) | f.w;
     }
     return make_uint4(t[0], t[1], t[2], t[3]);
+}
+
+// The rare straddling vector whose first bytes are NOT pad: the previous row (rl - 1) is so long that its residues /
+// EOS reach into them.  Both rows' codes are built and merged.  Kept out of line: it must not cost the hot loop registers.
+template <bool PRE>
+__device__ __noinline__ uint4 span_straddle_general(uint32_t rows_a, uint32_t rl, int col, const SpanRegs &g) {
+    const int4 rp = lds128i(rows_a + 16u * rl - 16u), ri = lds128i(rows_a + 16u * rl);
+    const int cp = col + g.padlen;  // the vector's first column in the previous row (> padlen - 16)
+    uint4 prev = g.padq;
+    if (cp < rp.z) prev = span_row_codes_u<PRE>(static_cast<uint32_t>(rp.x), rp.y, cp, g);
+    const uint4 cur = span_row_codes_u<PRE>(static_cast<uint32_t>(ri.x), ri.y, col, g);
+    const uint4 m = lds128(g.tab_m - 16u * static_cast<uint32_t>(col));  // bytes [0, -col) come from the previous row
+    return make_uint4((prev.x & m.x) | (cur.x & ~m.x), (prev.y & m.y) | (cur.y & ~m.y), (prev.z & m.z) | (cur.z & ~m.z),
+                      (prev.w & m.w) | (cur.w & ~m.w));
 }
 
 // The four offsets that delimit a tile's span: rows r0 and r1 (first and last row the tile touches).
@@ -217,6 +236,7 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
     __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE];
     __shared__ __align__(16) int4 hdr[NSTAGE];           // c_first, nrows, nvec, -
     __shared__ __align__(16) uint32_t cst[kCstWords];    // loop invariants of the consumers (see SpanRegs)
+    __shared__ int tile_of[NSTAGE];                      // tile index of the stage's contents
 
     // Programmatic dependent launch: the next kernel of the stream may start its prologue now; ours (LUT, mask
     // tables, barriers: no global memory) runs before the previous kernel of the stream has finished.
@@ -246,56 +266,81 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
 
     if (warp == kSpanConsumerWarps) {
         // ------------------------------- producer -------------------------------
-        int64_t t = blockIdx.x;
-        if (t >= q.ntiles) return;
-        // first tile: one 64-bit division; later tiles advance by (step_rows, step_cols)
-        int64_t r0 = (t * tile_bytes) / q.padlen;
-        int c_first = static_cast<int>(t * tile_bytes - r0 * q.padlen);
-        // offsets of this CTA's first tile: into L2 while the previous kernel drains (a prefetch is only a hint,
-        // the real loads come after the wait)
-        if (16 * lane <= tile_bytes / q.padlen + 2 && r0 + 16 * lane <= q.nseq) asm volatile("prefetch.global.L2 [%0];" ::"l"(q.offs + r0 + 16 * lane));
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-        const int maxlen = max(q.padlen - sp.bos - sp.eos, 0);
-        auto last_row = [&](int64_t tt, int64_t rr0, int cc, int &c_last) {  // r1 and c_last of tile tt
-            const int64_t f0 = tt * tile_bytes;
-            const uint32_t e = static_cast<uint32_t>(cc) + static_cast<uint32_t>(min(static_cast<int64_t>(tile_bytes), q.total - f0)) - 1u;
-            const uint32_t dr = __umulhi(e, q.div_mul) >> q.div_shift;
-            c_last = static_cast<int>(e - dr * static_cast<uint32_t>(q.padlen));
-            return rr0 + dr;
+        // Tile coordinates: first row r0 and column c_first of the tile's first byte, last row r1 / column c_last.
+        struct Coord {
+            int64_t r0, r1;
+            int c_first, c_last;
         };
-        auto load_edges = [&](int64_t rr0, int64_t rr1) {
+        auto coord_of = [&](int64_t tt) {
+            Coord c;
+            const int64_t f0 = tt * tile_bytes;
+            c.r0 = f0 / q.padlen;
+            c.c_first = static_cast<int>(f0 - c.r0 * q.padlen);
+            const uint32_t e = static_cast<uint32_t>(c.c_first) + static_cast<uint32_t>(min(static_cast<int64_t>(tile_bytes), q.total - f0)) - 1u;
+            const uint32_t dr = __umulhi(e, q.div_mul) >> q.div_shift;
+            c.c_last = static_cast<int>(e - dr * static_cast<uint32_t>(q.padlen));
+            c.r1 = c.r0 + dr;
+            return c;
+        };
+        auto load_edges = [&](const Coord &c) {
             SpanEdges e;
-            e.a0 = __ldg(q.offs + rr0); e.a1 = __ldg(q.offs + rr0 + 1);
-            e.b0 = __ldg(q.offs + rr1); e.b1 = __ldg(q.offs + rr1 + 1);
+            e.a0 = __ldg(q.offs + c.r0); e.a1 = __ldg(q.offs + c.r0 + 1);
+            e.b0 = __ldg(q.offs + c.r1); e.b1 = __ldg(q.offs + c.r1 + 1);
             return e;
         };
-        int c_last;
-        int64_t r1 = last_row(t, r0, c_first, c_last);
-        SpanEdges cur = load_edges(r0, r1);
+        // next tile index of this CTA, requested one tile ahead of its use (lane 0 asks, everybody gets the answer)
+        auto next_tile = [&](int64_t tt) -> int64_t {
+            if (q.ctr == nullptr) return tt + gridDim.x;
+            unsigned int v = 0;
+            if (lane == 0) v = atomicAdd(q.ctr, 1u);
+            return static_cast<int64_t>(gridDim.x) + __shfl_sync(0xffffffffu, v, 0);
+        };
+        int64_t t = blockIdx.x;  // < ntiles (the grid is never larger)
+        Coord cc = coord_of(t);
+        // offsets of this CTA's first tile: into L2 while the previous kernel drains (a prefetch is only a hint,
+        // the real loads come after the wait)
+        if (16 * lane <= tile_bytes / q.padlen + 2 && cc.r0 + 16 * lane <= q.nseq) asm volatile("prefetch.global.L2 [%0];" ::"l"(q.offs + cc.r0 + 16 * lane));
+        const int maxlen = max(q.padlen - sp.bos - sp.eos, 0);
+        {
+            // ... and the tile's residues too, from the offsets as they read NOW.  The previous kernel of the stream may
+            // still be producing them, so these values are hints only: they go through L2 (ld.global.cg: nothing stale
+            // can stay in L1), address nothing but an L2 prefetch -- which is dropped when its address is not mapped
+            // (tools/probes/prefetch_probe.cu) -- and are read again for real after the wait.
+            int64_t sa0, sb0, sb1;
+            asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(sa0) : "l"(q.offs + cc.r0));
+            asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(sb0) : "l"(q.offs + cc.r1));
+            asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(sb1) : "l"(q.offs + cc.r1 + 1));
+            const int64_t span = min(max(sb1 - sa0, int64_t(0)), static_cast<int64_t>(q.stage_bytes));
+            (void)sb0;
+            const uintptr_t pa = reinterpret_cast<uintptr_t>(q.bytes + sa0) & ~uintptr_t(15);
+            const uint32_t pn = static_cast<uint32_t>((span + 31) & ~int64_t(15));
+            if (lane == 0 && pn > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa), "r"(pn) : "memory");
+        }
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        SpanEdges cur = load_edges(cc);
+        int64_t tn = next_tile(t);
         uint32_t it = 0;
         for (;; ++it) {
-            // the next tile's edge offsets are requested now and consumed one iteration later: their latency hides
-            // behind this tile's barrier wait, copy issue and row table
-            const int64_t tn = t + gridDim.x;
-            int64_t r0n = r0 + q.step_rows;
-            int cn = c_first + q.step_cols;
-            if (cn >= q.padlen) { cn -= q.padlen; ++r0n; }
-            int c_lastn = 0;
-            int64_t r1n = 0;
+            // the next tile's edge offsets (and the index of the tile after it) are requested now and consumed one
+            // iteration later: their latency hides behind this tile's barrier wait, copy issue and row table
+            const bool more = tn < q.ntiles;
+            Coord cn = cc;
             SpanEdges nxt = cur;
-            if (tn < q.ntiles) {
-                r1n = last_row(tn, r0n, cn, c_lastn);
-                nxt = load_edges(r0n, r1n);
+            int64_t tnn = tn;
+            if (more) {
+                cn = coord_of(tn);
+                nxt = load_edges(cn);
+                tnn = next_tile(tn);
             }
             const int s = static_cast<int>(it % NSTAGE);
             const uint32_t ph = (it / NSTAGE) & 1u;
             const int64_t f0 = t * tile_bytes, f1 = min(f0 + tile_bytes, q.total);
-            const int nrows = static_cast<int>(r1 - r0) + 1;
+            const int nrows = static_cast<int>(cc.r1 - cc.r0) + 1;
             // the span: residues of columns [c_first, padlen) of row r0 ... [0, c_last] of row r1
             const int len0 = static_cast<int>(min(max(cur.a1 - cur.a0, int64_t(0)), static_cast<int64_t>(maxlen)));
             const int len1 = static_cast<int>(min(max(cur.b1 - cur.b0, int64_t(0)), static_cast<int64_t>(maxlen)));
-            const int64_t lo = cur.a0 + min(max(c_first - sp.bos, 0), len0);
-            const int64_t hi = cur.b0 + min(max(c_last + 1 - sp.bos, 0), len1);
+            const int64_t lo = cur.a0 + min(max(cc.c_first - sp.bos, 0), len0);
+            const int64_t hi = cur.b0 + min(max(cc.c_last + 1 - sp.bos, 0), len1);
             const uintptr_t A_lo = reinterpret_cast<uintptr_t>(q.bytes + lo) & ~uintptr_t(15);
             const uintptr_t A_hi = (reinterpret_cast<uintptr_t>(q.bytes + hi) + 15) & ~uintptr_t(15);
             const uint32_t nbytes = hi > lo ? static_cast<uint32_t>(min(static_cast<int64_t>(A_hi - A_lo),
@@ -303,26 +348,54 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
                                             : 0u;
             uint8_t *stage = dyn + static_cast<size_t>(s) * stage_stride;
             int4 *rows = reinterpret_cast<int4 *>(stage + q.stage_bytes);
+            // shared address of the byte that column 0 of row r0 + i comes from
+            const int64_t base = static_cast<int64_t>(reinterpret_cast<uintptr_t>(q.bytes)) - static_cast<int64_t>(A_lo) + kSpanSlack - sp.bos +
+                                 static_cast<int64_t>(s_u32(stage));
+            auto row_entry = [&](int i) {  // {source address of column 0, bos + len, bos + len + eos, the previous row's bos + len + eos}
+                const int64_t o0 = __ldg(q.offs + cc.r0 + i), o1 = __ldg(q.offs + cc.r0 + i + 1);
+                const int n = sp.bos + static_cast<int>(min(max(o1 - o0, int64_t(0)), static_cast<int64_t>(maxlen)));
+                int pn = 0;
+                if (!ALIGNED && i > 0) pn = sp.bos + sp.eos + static_cast<int>(min(max(o0 - __ldg(q.offs + cc.r0 + i - 1), int64_t(0)), static_cast<int64_t>(maxlen)));
+                return make_int4(static_cast<int>(o0 + base), n, n + sp.eos, pn);
+            };
+            // the first 32 rows' entries are formed before the barrier wait (their offsets are in flight meanwhile)
+            int4 e0 = make_int4(0, 0, 0, 0);
+            if (lane < nrows) e0 = row_entry(lane);
             if (it >= NSTAGE) bar_wait(s_u32(empty + s), ph ^ 1u);  // the consumers are done with this stage
             if (lane == 0) {
                 if (nbytes) {
                     bar_expect_tx(s_u32(full + s), nbytes);
                     bulk_load(s_u32(stage + kSpanSlack), reinterpret_cast<const void *>(A_lo), nbytes, s_u32(full + s));
                 }
-                hdr[s] = make_int4(c_first, nrows, static_cast<int>((f1 - f0 + 15) >> 4), static_cast<int>(nbytes));
+                hdr[s] = make_int4(cc.c_first, nrows, static_cast<int>((f1 - f0 + 15) >> 4), static_cast<int>(nbytes));
+                tile_of[s] = static_cast<int>(t);
             }
-            // shared address of the byte that column 0 of row r0 + i comes from
-            const int64_t base = static_cast<int64_t>(reinterpret_cast<uintptr_t>(q.bytes)) - static_cast<int64_t>(A_lo) + kSpanSlack - sp.bos +
-                                 static_cast<int64_t>(s_u32(stage));
-            for (int i = lane; i < nrows; i += 32) {
-                const int64_t o0 = __ldg(q.offs + r0 + i), o1 = __ldg(q.offs + r0 + i + 1);
-                const int n = sp.bos + static_cast<int>(min(max(o1 - o0, int64_t(0)), static_cast<int64_t>(maxlen)));
-                rows[i] = make_int4(static_cast<int>(o0 + base), n, n + sp.eos, 0);
-            }
+            if (lane < nrows) rows[lane] = e0;
+            for (int i = lane + 32; i < nrows; i += 32) rows[i] = row_entry(i);
             __syncwarp();
             if (lane == 0) bar_arrive(s_u32(full + s));  // release: row table + header visible to whoever sees the phase flip
-            if (tn >= q.ntiles) break;
-            t = tn; r0 = r0n; c_first = cn; r1 = r1n; c_last = c_lastn; cur = nxt;
+            if (!more) break;
+            t = tn; tn = tnn; cc = cn; cur = nxt;
+        }
+        // end of work for this CTA: a stage whose header says so
+        {
+            ++it;
+            const int s = static_cast<int>(it % NSTAGE);
+            const uint32_t ph = (it / NSTAGE) & 1u;
+            if (it >= NSTAGE) bar_wait(s_u32(empty + s), ph ^ 1u);
+            if (lane == 0) {
+                hdr[s] = make_int4(0, 0, -1, 0);
+                bar_arrive(s_u32(full + s));
+            }
+        }
+        // the last CTA to see the end of the tiles re-arms the counter for the next launch that uses this slot
+        if (q.ctr != nullptr && lane == 0) {
+            __threadfence();
+            if (atomicAdd(q.ctr + 1, 1u) == gridDim.x - 1) {
+                q.ctr[0] = 0u;
+                q.ctr[1] = 0u;
+                __threadfence();
+            }
         }
         return;
     }
@@ -343,15 +416,14 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
     g.tab_m = lds32(cst_a + 36u);
     g.padq = lds128(cst_a + 48u);
     const uint32_t dyn_a = s_u32(dyn);
-    uint32_t it = 0;
-    for (int64_t t = blockIdx.x; t < q.ntiles; t += gridDim.x, ++it) {
+    for (uint32_t it = 0;; ++it) {
         const int s = static_cast<int>(it % NSTAGE);
         const uint32_t ph = (it / NSTAGE) & 1u;
         const uint32_t rows_a = dyn_a + static_cast<uint32_t>(s * stage_stride + q.stage_bytes);
         bar_wait(s_u32(full + s), ph);
         const int4 h = hdr[s];
-        const int nrows = h.y;
-        const int64_t tile0 = t * tile_bytes;
+        if (h.z < 0) break;  // no more tiles for this CTA
+        const int64_t tile0 = static_cast<int64_t>(tile_of[s]) * tile_bytes;
         if (PRE) {
             // phase 1: the staged residues become codes in place -- dense (every lane busy, no row logic, no
             // realignment): LDS.128, 16 look-ups, STS.128 per 16 bytes of the span
@@ -368,34 +440,40 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
         uint32_t F = static_cast<uint32_t>(h.x) + 16u * static_cast<uint32_t>(ctid);
         const uint32_t Fend = static_cast<uint32_t>(h.x) + 16u * static_cast<uint32_t>(h.z);
         uint8_t *dst = q.out + tile0 + 16 * ctid;
-        for (; F < Fend; F += 16u * kSpanConsumers, dst += 16 * kSpanConsumers) {
-            const uint32_t rl = __umulhi(F, g.mul) >> g.shift;
-            const int col = static_cast<int>(rl * static_cast<uint32_t>(g.neg_padlen) + F);
-            const int4 ri = lds128i(rows_a + 16u * rl);  // {shared address of column 0's source byte, bos + len, bos + len + eos, -}
-            if (ALIGNED) {
+        if (ALIGNED) {
+            for (; F < Fend; F += 16u * kSpanConsumers, dst += 16 * kSpanConsumers) {
+                const uint32_t rl = __umulhi(F, g.mul) >> g.shift;
+                const int col = static_cast<int>(rl * static_cast<uint32_t>(g.neg_padlen) + F);
+                const int4 ri = lds128i(rows_a + 16u * rl);  // {shared address of column 0's source byte, bos + len, bos + len + eos, -}
+                if (col >= ri.z) __stcs(reinterpret_cast<uint4 *>(dst), g.padq);
+                else __stcs(reinterpret_cast<uint4 *>(dst), span_row_codes<PRE>(static_cast<uint32_t>(ri.x), ri.y, col, g));
+            }
+        } else {
+            // padlen % 16 != 0: vectors stay 16-byte aligned in the flat output, so one vector per row straddles two rows.
+            // A vector belongs to the row that holds its LAST byte: its columns run from col in [-15, padlen - 16], the
+            // bytes left of column 0 are the previous row's tail -- pad, unless that row is nearly full (rare: the general
+            // path).  So the straddling vector costs one translation like any other, in the same instruction stream.
+            const bool partial_tail = tile0 + 16 * static_cast<int64_t>(h.z) > q.total;  // the batch's final vector is cut short
+            const uint32_t Fsafe = partial_tail ? Fend - 16u : Fend;
+            for (; F < Fsafe; F += 16u * kSpanConsumers, dst += 16 * kSpanConsumers) {
+                const uint32_t rl = __umulhi(F + 15u, g.mul) >> g.shift;
+                const int col = static_cast<int>(rl * static_cast<uint32_t>(g.neg_padlen) + F);
+                const int4 ri = lds128i(rows_a + 16u * rl);  // {source address of column 0, bos + len, bos + len + eos, the previous row's bos + len + eos}
                 if (col >= ri.z) {
                     __stcs(reinterpret_cast<uint4 *>(dst), g.padq);
+                } else if (col >= 0 || ri.w <= g.padlen + col) {
+                    __stcs(reinterpret_cast<uint4 *>(dst), span_row_codes_u<PRE>(static_cast<uint32_t>(ri.x), ri.y, col, g));
                 } else {
-                    __stcs(reinterpret_cast<uint4 *>(dst), span_row_codes<PRE>(static_cast<uint32_t>(ri.x), ri.y, col, g));
+                    __stcs(reinterpret_cast<uint4 *>(dst), span_straddle_general<PRE>(rows_a, rl, col, g));
                 }
-                continue;
             }
-            uint4 codes = g.padq;
-            if (col < ri.z) codes = span_row_codes<PRE>(static_cast<uint32_t>(ri.x), ri.y, col, g);
-            if (col + 16 > g.padlen && static_cast<int>(rl) + 1 < nrows) {  // the vector straddles into the next row
-                const int4 rj = lds128i(rows_a + 16u * rl + 16u);
-                const int c2 = col - g.padlen;
-                uint4 nxt = g.padq;
-                if (c2 < rj.z) nxt = span_row_codes_neg<PRE>(static_cast<uint32_t>(rj.x), rj.y, c2, g);
-                const uint4 m = lds128(g.tab_m + 16u * static_cast<uint32_t>(g.padlen - col));
-                codes.x = (codes.x & m.x) | (nxt.x & ~m.x); codes.y = (codes.y & m.y) | (nxt.y & ~m.y);
-                codes.z = (codes.z & m.z) | (nxt.z & ~m.z); codes.w = (codes.w & m.w) | (nxt.w & ~m.w);
-            }
-            const int64_t pos = tile0 + static_cast<int64_t>(F - static_cast<uint32_t>(h.x));
-            if (pos + 16 <= q.total) {
-                __stcs(reinterpret_cast<uint4 *>(dst), codes);
-            } else {  // the batch's final partial vector
-                const int keep = static_cast<int>(q.total - pos);
+            if (partial_tail && F == Fsafe) {  // exactly one lane of the CTA: the final vector, bytewise
+                const uint32_t rl = __umulhi(F, g.mul) >> g.shift;  // the row of its first byte (the batch's last row)
+                const int col = static_cast<int>(rl * static_cast<uint32_t>(g.neg_padlen) + F);
+                const int4 ri = lds128i(rows_a + 16u * rl);
+                uint4 codes = g.padq;
+                if (col < ri.z) codes = span_row_codes_u<PRE>(static_cast<uint32_t>(ri.x), ri.y, col, g);
+                const int keep = static_cast<int>(q.total - (tile0 + static_cast<int64_t>(F - static_cast<uint32_t>(h.x))));
                 const uint32_t w[4] = {codes.x, codes.y, codes.z, codes.w};
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
@@ -426,14 +504,50 @@ int span_env(const char *name, int dflt) {
 struct DevInfo {
     int sms = 0;
     bool attr_set[4][2][2][3] = {};
+    // tile counters of the dynamic scheduler: kCtrPairs x 2 slots x {handed out, CTAs done}, zero when idle (the
+    // kernel re-arms its slot itself).  A stream owns a pair of slots and alternates between them: kernels of one
+    // stream touch their counter only after the previous kernel of the stream has completed (griddepcontrol.wait /
+    // stream order), so two slots per stream can never be in use by more than their own launch.
+    unsigned int *ctr = nullptr;
+    bool ctr_failed = false;
+    std::unordered_map<cudaStream_t, int> pair_of;  // stream -> 2 * pair index + flip
 };
+constexpr int kCtrPairs = 1024;
+
+std::mutex g_dev_mu;
 DevInfo &dev_info(int dev) {
     static DevInfo info[64];
-    static std::mutex mu;
-    std::lock_guard<std::mutex> g(mu);
     DevInfo &d = info[dev & 63];
     if (d.sms == 0) cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
     return d;
+}
+
+// Counter slot for a launch on `st`, or nullptr (stream capture in progress, no memory, more than kCtrPairs streams):
+// the kernel then falls back to the static tile order.
+unsigned int *span_counter(DevInfo &d, cudaStream_t st) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (cap != cudaStreamCaptureStatusNone) return nullptr;  // a captured launch may be replayed concurrently with itself
+    if (d.ctr == nullptr) {
+        if (d.ctr_failed) return nullptr;
+        if (cudaMalloc(reinterpret_cast<void **>(&d.ctr), sizeof(unsigned int) * 4 * kCtrPairs) != cudaSuccess ||
+            cudaMemset(d.ctr, 0, sizeof(unsigned int) * 4 * kCtrPairs) != cudaSuccess) {
+            cudaGetLastError();
+            d.ctr = nullptr;
+            d.ctr_failed = true;
+            return nullptr;
+        }
+    }
+    auto it = d.pair_of.find(st);
+    if (it == d.pair_of.end()) {
+        if (static_cast<int>(d.pair_of.size()) >= kCtrPairs) return nullptr;
+        it = d.pair_of.emplace(st, 2 * static_cast<int>(d.pair_of.size())).first;
+    }
+    it->second ^= 1;
+    return d.ctr + 2 * it->second;  // slot index = 2 * pair + flip, two words per slot
 }
 
 }  // namespace
@@ -454,14 +568,16 @@ int launch_tokenize_span(int device, cudaStream_t st, const SeqView &v, int64_t 
                          bool pdl_allowed) {
     // A/B knobs (read once; BSQ_TUNE=1 re-reads them at every launch for in-process sweeps)
     static const bool tune = span_env("BSQ_TUNE", 0) != 0;
-    static int vt_max = 0, nstage = 0, ctas_env = 0, two_phase = 1, minb = 5;
+    static int vt_max = 0, nstage = 0, ctas_env = 0, two_phase = 0, minb = 4, dynamic = 1;
     if (vt_max == 0 || tune) {
-        vt_max = std::max(256, span_env("BSQ_SPAN_VT", 1024) / 256 * 256);
-        nstage = std::min(4, std::max(2, span_env("BSQ_SPAN_STAGES", 3)));
+        vt_max = std::max(256, span_env("BSQ_SPAN_VT", 1536) / 256 * 256);
+        nstage = std::min(4, std::max(2, span_env("BSQ_SPAN_STAGES", 2)));
         ctas_env = span_env("BSQ_SPAN_CTAS", 0);
         two_phase = span_env("BSQ_SPAN_2P", 0);
-        minb = std::min(6, std::max(4, span_env("BSQ_SPAN_MINB", 5)));
+        minb = std::min(6, std::max(4, span_env("BSQ_SPAN_MINB", 4)));
+        dynamic = span_env("BSQ_SPAN_DYN", 1);
     }
+    std::lock_guard<std::mutex> dev_lock(g_dev_mu);
     DevInfo &di = dev_info(device);
     const int sms = di.sms > 0 ? di.sms : 148;
     const int64_t total = nseq * padlen;
@@ -498,9 +614,7 @@ int launch_tokenize_span(int device, cudaStream_t st, const SeqView &v, int64_t 
     const bool aligned = padlen % 16 == 0;
 
     const int64_t blocks = std::min<int64_t>(ntiles, grid_full);
-    const int64_t step = blocks * vt * 16;
-    q.step_rows = step / padlen;
-    q.step_cols = static_cast<int>(step % padlen);
+    q.ctr = (dynamic && ntiles < 0x7fffffffll) ? span_counter(di, st) : nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(blocks));
     cfg.blockDim = dim3(kSpanThreads);
@@ -510,8 +624,10 @@ int launch_tokenize_span(int device, cudaStream_t st, const SeqView &v, int64_t 
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    // two whole persistent grids must fit on the SMs at once (see launch_bf in bsq_kernels.cu)
-    const bool pdl = pdl_allowed && 2 * per_sm * (smem + static_smem) <= 227 * 1024 && 2 * per_sm * kSpanThreads <= 2048;
+    // Programmatic dependent launch hides this launch's ramp behind the previous kernel's tail.  With the dynamic tile
+    // order any co-residency is fine; with the static order two whole persistent grids must fit on the SMs at once
+    // (otherwise the late CTAs pile up on the first SMs to drain and the fixed partition becomes unbalanced).
+    const bool pdl = pdl_allowed && (q.ctr != nullptr || (2 * per_sm * (smem + static_smem) <= 227 * 1024 && 2 * per_sm * kSpanThreads <= 2048));
     cfg.numAttrs = pdl ? 1 : 0;
 
 #define BSQ_SPAN_LAUNCH(NS, AL, PR, MB)                                                                                           \

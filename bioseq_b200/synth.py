@@ -20,6 +20,11 @@ def gen(seed, n, lo, hi, alpha):
     return np.ascontiguousarray(buf), offs
 
 
+def gen_lens(seed, n, lo, hi):
+    """The lengths ``gen(seed, n, lo, hi, ...)`` draws (its first use of the generator), without the residues."""
+    return np.random.default_rng(seed).integers(lo, hi, size=n, endpoint=True)
+
+
 def gen_mask(seed, nbytes, p_keep=0.85):
     rng = np.random.default_rng(seed)
     return (rng.random(nbytes) < p_keep).astype(np.uint8)

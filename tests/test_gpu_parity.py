@@ -596,3 +596,90 @@ def test_concurrent_python_threads_share_pool_and_stager():
         th.join(timeout=120)
     assert not any(th.is_alive() for th in threads), "deadlock in the host pipeline"
     assert not errors, errors
+
+
+# ------------------------------------------------------------------------------------- the live reference on the GPU box
+def test_oracle_pinned_to_live_reference_on_this_box():
+    """The oracle <-> reference pin of tests/test_oracle.py, run here as well: the driver's GPU test pass selects `-m gpu`
+    only, and it is the reference itself (oracle/_ref, shipped prebuilt) that makes the oracle an oracle."""
+    import test_oracle as TO
+    if TO.R is None:
+        pytest.skip("oracle/_ref not present")
+    for seed in range(6):
+        TO.test_live_reference_tokenize_onehot_decode(seed)
+    TO.test_live_reference_str_inputs_utf8()
+    TO.test_live_reference_decode_itemsizes()
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_gpu_vs_live_reference_dropin_calls(seed):
+    """The drop-in Python class against the reference's own class, same calls, same arguments: list of str / bytes /
+    bytearray items in, arrays (tokens in both layouts and every dtype, one-hot with and without mask) and decoded
+    strings out."""
+    R = load_ref()
+    if R is None:
+        pytest.skip("oracle/_ref not present")
+    rng = np.random.default_rng(4242 + seed)
+    keys = [k for k in alphabet_keys() if k != "BYTES"]   # BYTES ids wrap differently by design (DESIGN.md section 5)
+    for trial in range(10):
+        key = keys[int(rng.integers(len(keys)))]
+        flags = dict(bos=bool(rng.integers(2)), eos=bool(rng.integers(2)), padchar=bool(rng.integers(2)))
+        n = int(rng.integers(0, 300))
+        hi = int(rng.integers(0, 700))
+        buf, offs = gen(int(rng.integers(1 << 30)), n, 0, hi, MIX[:-3])   # (bytes >= 0x80 are undefined in the reference)
+        seqs = as_list(buf, offs)
+        kind = int(rng.integers(3))
+        if kind == 1:
+            seqs = [bytearray(s) for s in seqs]
+        elif kind == 2:
+            seqs = [s.decode("latin-1") if all(c < 0x80 for c in s) else s for s in seqs]
+        padlen = hi + 2 + int(rng.integers(0, 40))
+        dc = "bhilqfd"[int(rng.integers(7))]
+        bf = bool(rng.integers(2))
+        ref_t, t = R.Tokenizer(key, **flags), bioseq_b200.Tokenizer(key, **flags)
+        a = ref_t.batch_tokenize(seqs, padlen=padlen, destchar=dc, batch_first=bf, nthreads=2)
+        b = t.batch_tokenize(seqs, padlen=padlen, destchar=dc, batch_first=bf, nthreads=int(rng.integers(1, 9)))
+        assert_same_bits(a, b.cpu().numpy())
+        if dc not in "fd":
+            assert ref_t.decode_tokens(a) == t.decode_tokens(b)
+        mask = None
+        if rng.integers(2) and n:
+            m = gen_mask(int(rng.integers(1 << 30)), buf.size, 0.7)
+            mask = [m[offs[i]:offs[i + 1]] for i in range(n)]
+        a = ref_t.batch_onehot_encode(seqs, padlen=padlen, destchar=dc, mask=mask)
+        b = t.batch_onehot_encode(seqs, padlen=padlen, destchar=dc, mask=mask)
+        assert_same_bits(a, b.cpu().numpy())
+
+
+def test_streamed_items_ranges_and_growth():
+    """bsq_tokenize_stream_items: many ranges, pinned-pack growth in the middle of a call, batches that shrink and grow
+    from call to call, every host thread count; always equal to the packed device call."""
+    tok = bioseq_b200.Tokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    for n, lo, hi, padlen in ((70000, 0, 120, 128), (9000, 900, 1000, 1002), (3, 0, 5, 8), (200000, 0, 30, 32), (20000, 500, 2000, 2048)):
+        buf, offs = gen(n + hi, n, lo, hi, b"ACDEFGHIKLMNPQRSTVWYXacd")
+        seqs = as_list(buf, offs)
+        want = tok.batch_tokenize_packed(torch.from_numpy(buf).cuda(), torch.from_numpy(offs).cuda(), padlen=padlen, batch_first=True)
+        for nt in (1, 3, 8, 16):
+            assert torch.equal(tok.batch_tokenize(seqs, padlen=padlen, batch_first=True, nthreads=nt), want)
+        assert torch.equal(tok.batch_tokenize(seqs, padlen=padlen, nthreads=5), want.t())
+
+
+def test_sharded_single_process_entry():
+    """Tokenizer.batch_tokenize_sharded: one packed host batch -> one shard per device (here: the same device twice is
+    refused; one device = the whole batch; with 2+ GPUs the shards concatenate to the single-device result)."""
+    tok = bioseq_b200.Tokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    buf, offs = gen(9, 5000, 0, 300, b"ACDEFGHIKLMNPQRSTVWY")
+    want = tok.batch_tokenize_packed(torch.from_numpy(buf).cuda(), torch.from_numpy(offs).cuda(), padlen=304, batch_first=True)
+    outs, bounds = tok.batch_tokenize_sharded(buf, offs, padlen=304, batch_first=True, devices=[0])
+    assert list(bounds) == [0, 5000] and torch.equal(outs[0], want)
+    ndev = torch.cuda.device_count()
+    if ndev >= 2:
+        outs, bounds = tok.batch_tokenize_sharded(buf, offs, padlen=304, batch_first=True)
+        assert len(outs) == ndev and bounds[0] == 0 and bounds[-1] == 5000
+        assert torch.equal(torch.cat([o.to("cuda:0") for o in outs], dim=0), want)
+        sizes = [int(offs[bounds[g + 1]] - offs[bounds[g]]) for g in range(ndev)]
+        assert max(sizes) - min(sizes) <= 2 * 300
+        outs, _ = tok.batch_tokenize_sharded(buf, offs, padlen=304, batch_first=False)
+        assert torch.equal(torch.cat([o.to("cuda:0") for o in outs], dim=1), want.t())
+    with pytest.raises(ValueError):
+        tok.batch_tokenize_sharded(buf, offs, padlen=304, devices=[0, 0])

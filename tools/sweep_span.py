@@ -33,7 +33,7 @@ for name, n, rot, reps, padlen, hi in (("c2", 65536, 4, 200, 1024, 1022), ("c2x4
     cases.append((name, n, rot, reps, padlen, sets))
 
 def run(cfg):
-    for k in ("BSQ_SPAN", "BSQ_SPAN_VT", "BSQ_SPAN_STAGES", "BSQ_SPAN_CTAS", "BSQ_PDL", "BSQ_SPAN_2P", "BSQ_SPAN_MINB"):
+    for k in ("BSQ_SPAN", "BSQ_SPAN_VT", "BSQ_SPAN_STAGES", "BSQ_SPAN_CTAS", "BSQ_PDL", "BSQ_SPAN_2P", "BSQ_SPAN_MINB", "BSQ_SPAN_DYN"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in cfg.items()})
     out = []
@@ -60,7 +60,7 @@ def snapshot():
 os.environ["BSQ_SPAN"] = "0"
 want = snapshot()
 def check(cfg):
-    for k in ("BSQ_SPAN", "BSQ_SPAN_VT", "BSQ_SPAN_STAGES", "BSQ_SPAN_CTAS", "BSQ_PDL", "BSQ_SPAN_2P", "BSQ_SPAN_MINB"):
+    for k in ("BSQ_SPAN", "BSQ_SPAN_VT", "BSQ_SPAN_STAGES", "BSQ_SPAN_CTAS", "BSQ_PDL", "BSQ_SPAN_2P", "BSQ_SPAN_MINB", "BSQ_SPAN_DYN"):
         os.environ.pop(k, None)
     os.environ.update({k: str(v) for k, v in cfg.items()})
     got = snapshot()
@@ -72,12 +72,9 @@ def check(cfg):
 run({"BSQ_SPAN": 0})
 run({"BSQ_SPAN": 0, "BSQ_PDL": 0})
 grid = []
-for tp in (0, 1):
-    for mb in (5, 4):
-        for vt, stg, ctas in ((1024, 3, 4), (1024, 3, 5), (1024, 2, 5), (2048, 2, 3), (2048, 2, 4), (512, 3, 5), (512, 4, 5)):
-            if ctas > mb: continue
-            grid.append({"BSQ_SPAN_2P": tp, "BSQ_SPAN_MINB": mb, "BSQ_SPAN_VT": vt, "BSQ_SPAN_STAGES": stg, "BSQ_SPAN_CTAS": ctas, "BSQ_PDL": 0})
+for tp in (1, 0):
+    for mb, vt, stg, ctas in ((4, 1024, 3, 4), (4, 2048, 2, 3), (4, 1024, 2, 4), (4, 1024, 4, 4), (4, 1536, 2, 4), (4, 1536, 3, 3), (5, 1024, 2, 5), (5, 1024, 3, 4)):
+        grid.append({"BSQ_SPAN_DYN": 1, "BSQ_SPAN_2P": tp, "BSQ_SPAN_MINB": mb, "BSQ_SPAN_VT": vt, "BSQ_SPAN_STAGES": stg, "BSQ_SPAN_CTAS": ctas, "BSQ_PDL": 1})
 for cfg in grid:
     if check(cfg):
         run(cfg)
-run({"BSQ_SPAN_2P": 0, "BSQ_SPAN_MINB": 5, "BSQ_SPAN_VT": 1024, "BSQ_SPAN_STAGES": 3, "BSQ_SPAN_CTAS": 2, "BSQ_PDL": 1})
