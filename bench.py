@@ -255,8 +255,13 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
+        # The path has no data-path collective: the ranks only meet at barriers and to reduce their timings.  Those
+        # go over gloo (host tensors) while anything is being timed, and NCCL is brought up AFTER the timed sections for
+        # the final reduction of the reported numbers: an initialised NCCL communicator makes every kernel launch of the
+        # process ~1-2 us slower (measured on one GPU with a 1-rank group: 21.1 -> 22.0 us per 20 us launch, without PDL
+        # 22.8 -> 24.9; gpurun_out/r02m), which is 5-10 % of this workload's step and has nothing to do with the path.
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("gloo")
     dev = local
     L = capi.lib()
     tok = capi.tokenizer(KEY, **FLAGS)
@@ -283,7 +288,7 @@ def run_ours(args):
 
     sampler = ClockSampler(local)
     # clocks ramp from idle: keep the GPU busy for a moment before anything is timed
-    t_end = time.perf_counter() + (0.5 if "extra" in args.sections else 0.0)
+    t_end = time.perf_counter() + 0.5
     i = 0
     while time.perf_counter() < t_end:
         step(i); i += 1
@@ -303,8 +308,10 @@ def run_ours(args):
     L.bsq_launch_count_reset()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     ev[0].record()
+    t_host0 = time.perf_counter()
     for i in range(args.steps):
         step(i)
+    host_us_per_launch = (time.perf_counter() - t_host0) / args.steps * 1e6   # host time to enqueue a step (the device must not wait for it)
     ev[1].record()
     barrier()
     launches = int(L.bsq_launch_count())
@@ -399,7 +406,7 @@ def run_ours(args):
     if "e2e" in sections:
         barrier()
         host_link = measure_host_link(torch, barrier)
-        hl = torch.tensor([host_link["h2d_gbs"]], dtype=torch.float64, device="cuda")
+        hl = torch.tensor([host_link["h2d_gbs"]], dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(hl, op=dist.ReduceOp.SUM)
         host_link["h2d_gbs_all_ranks_concurrent"] = hl.tolist()[0]
@@ -417,7 +424,7 @@ def run_ours(args):
     c5 = None
     if "c5" in sections:
         barrier()
-        c5 = c5_slice(torch, capi, L, dev, st, rank)
+        c5 = c5_slice(torch, capi, L, dev, st, rank, barrier)
         barrier()
     c5f = None
     if "c5full" in sections or ("c5" in sections and world == 8 and args.c5full != "off") or args.c5full == "on":
@@ -428,17 +435,24 @@ def run_ours(args):
     # ---- reduce over ranks: max time ------------------------------------------------------------
     c5v = [c5["ms_h2d_inclusive"], c5["ms_device_resident"]] if c5 else [0.0, 0.0]
     c5s = [c5["bases"], c5["h2d_bytes"], c5["alg_bytes_device"], c5["bases_device"]] if c5 else [0.0] * 4
-    c5fv = [c5f["ms_pass"]] if c5f else [0.0]
+    c5fv = [c5f["ms_pass"], c5f["ms_pass_mapped"]] if c5f else [0.0, 0.0]
     c5fs = [c5f["bases"], c5f["h2d_bytes"], float(c5f["parity"])] if c5f else [0.0, 0.0, 1.0]
     t = torch.tensor([ms_total, e2e_s * 1e3, packed_s * 1e3, copy_us] + c5v + c5fv, dtype=torch.float64, device="cuda")
     tot = torch.tensor([float(bases_timed), float(e2e_bases), float(alg_bytes), float(launches)] + [float(x) for x in c5s] + c5fs[:2],
                        dtype=torch.float64, device="cuda")
     ok = torch.tensor([float(parity_rank["ok"]), float(e2e_ok is not False), float(packed_ok is not False), c5fs[2]], dtype=torch.float64, device="cuda")
+    nccl_ranks = 1
     if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-    ms_total_max, e2e_ms_max, packed_ms_max, copy_us_max, c5_ms_h2d, c5_ms_dev, c5f_ms = t.tolist()
+        # every timed section is over: NCCL (NVLink / NVSwitch) carries the reduction of the reported numbers
+        barrier()
+        pg = dist.new_group(backend="nccl", device_id=torch.device("cuda", local))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=pg)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM, group=pg)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=pg)
+        one = torch.ones(1, dtype=torch.float64, device="cuda")
+        dist.all_reduce(one, op=dist.ReduceOp.SUM, group=pg)
+        nccl_ranks = int(one.item())
+    ms_total_max, e2e_ms_max, packed_ms_max, copy_us_max, c5_ms_h2d, c5_ms_dev, c5f_ms, c5f_ms_mapped = t.tolist()
     bases_all, e2e_bases_all, alg_all, launches_all, c5_bases, c5_h2d_bytes, c5_alg, c5_bases_dev, c5f_bases, c5f_h2d = tot.tolist()
     parity_all, e2e_all_ok, packed_all_ok, c5f_parity = [bool(x) for x in ok.tolist()]
     if not parity_all:
@@ -481,7 +495,7 @@ def run_ours(args):
             "metric": "tokenize_throughput", "value": bases_all / (ms_total_max * 1e-3) / 1e9, "unit": "Gbases/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total_max / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": bench_config(world),
+            "config": bench_config(world), "ranks_seen_by_nccl": nccl_ranks,
             "bases_per_step_per_gpu": int(np.mean([s["nbases"] for s in sets])), "shard_of_rank0": shard_info,
             "e2e": {"value": e2e_bases_all / (e2e_ms_max * 1e-3) / 1e9, "unit": "Gbases/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": PADLEN, "steps": e2e_steps,
@@ -502,7 +516,7 @@ def run_ours(args):
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": "tokenize_span_kernel (K1s)",
                          "algorithmic_bytes_per_launch": int(alg_bytes / max(launches, 1)),
-                         "launch_us": per_launch_ms * 1e3,
+                         "launch_us": per_launch_ms * 1e3, "host_enqueue_us_per_launch": host_us_per_launch,
                          "copy_reference": {"what": "cudaMemcpyAsync device-to-device of the same traffic (read n + write n), same rotation, same run, max over ranks",
                                             "bytes": copy_bytes, "us": copy_us_max, "GB/s": copy_bytes / copy_us_max / 1e3,
                                             "frac_of_peak": copy_bytes / copy_us_max / 1e3 / peak,
@@ -529,6 +543,8 @@ def run_ours(args):
                                    ms_per_pass_max_over_ranks=c5f_ms, Gbases_per_s=c5f_bases / c5f_ms / 1e6,
                                    h2d_GBs_all_ranks=c5f_h2d / c5f_ms / 1e6,
                                    frac_of_host_link=None if not hl else c5f_h2d / c5f_ms / 1e6 / hl,
+                                   mapped_file_pass={"ms_per_pass_max_over_ranks": c5f_ms_mapped, "Gbases_per_s": c5f_bases / c5f_ms_mapped / 1e6,
+                                                     "h2d_GBs_all_ranks": c5f_h2d / c5f_ms_mapped / 1e6},
                                    parity_sampled_chunk_every_rank=c5f_parity)
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -640,7 +656,7 @@ def c4_measurements(torch, capi, L, dev, st, with_cpu):
     return res
 
 
-def c5_slice(torch, capi, L, dev, st, rank, nchunks=8, chunk=131072):
+def c5_slice(torch, capi, L, dev, st, rank, barrier, nchunks=8, chunk=131072):
     """BASELINE.json configs[4], one GPU's share in bounded form: `nchunks` chunks of `chunk` protein sequences
     (lengths 50..650, seeds 105+chunk index as in SURVEY.md 8d C5), PROTEIN pbeos, padlen 652.  Each chunk goes
     pinned host -> device on a copy stream (double-buffered) and is tokenised (int8 (B,652)) and one-hot encoded
@@ -684,6 +700,7 @@ def c5_slice(torch, capi, L, dev, st, rank, nchunks=8, chunk=131072):
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     reps = 2
+    barrier()   # all ranks load the host links at the same moment (the data generation above takes seconds and drifts)
     t0 = time.perf_counter()
     a.record()
     for _ in range(reps):
@@ -745,31 +762,41 @@ def c5_full(torch, capi, L, dev, st, rank, world, barrier, host_threads, with_cp
                 cb, co = sy.gen(seeds[c], sizes[c], 50, 650, sy.AA20)
                 f.write(cb.tobytes())
         make_s = time.perf_counter() - t0
-        ff = capi.FlatFile(path)
-        assert ff.nseqs == nseq
-        fb, fo = ff.bytes_ptr, ff.offsets_ptr
         stager = capi.Stager(dev)
         toks = [torch.empty((chunk, P), dtype=torch.uint8, device="cuda") for _ in range(2)]
         oh = [torch.empty((P, chunk, NC), dtype=torch.uint8, device="cuda") for _ in range(2)]
+        ms, open_s = {}, {}
+        for mode, kw in (("pinned", dict(pinned=True)), ("mapped", dict(prefault=True))):
+            # pinned: the file is read into page-locked memory once (like loading a dataset), chunks DMA straight from it;
+            # mapped: page-cache mapping, chunks bounce through the stager's pinned ring (pool threads, write-combining stores)
+            t0 = time.perf_counter()
+            ff = capi.FlatFile(path, **kw)
+            open_s[mode] = time.perf_counter() - t0
+            assert ff.nseqs == nseq
+            fb, fo = ff.bytes_ptr, ff.offsets_ptr
 
-        def run_chunk(c, k):
-            n = sizes[c]
-            db, do = stager.stage(st, fb, fo + 8 * c * chunk, n)
-            L.bsq_tokenize(dev, st, db, do, n, P, C.byref(tk), 1, capi.I8, toks[k].data_ptr())
-            rc = L.bsq_onehot(dev, st, db, do, None, n, P, C.byref(tk), capi.I8, oh[k].data_ptr())
-            if rc:
-                capi.check(rc)
-            stager.release(st)
+            def run_chunk(c, k):
+                n = sizes[c]
+                db, do = stager.stage(st, fb, fo + 8 * c * chunk, n)
+                L.bsq_tokenize(dev, st, db, do, n, P, C.byref(tk), 1, capi.I8, toks[k].data_ptr())
+                rc = L.bsq_onehot(dev, st, db, do, None, n, P, C.byref(tk), capi.I8, oh[k].data_ptr())
+                if rc:
+                    capi.check(rc)
+                stager.release(st)
 
-        for c in range(min(2, nchunks)):   # warm-up: allocations, page-locking of the ring, kernels
-            run_chunk(c, c % 2)
-        torch.cuda.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        for c in range(nchunks):
-            run_chunk(c, c % 2)
-        torch.cuda.synchronize()
-        ms_pass = (time.perf_counter() - t0) * 1e3
+            for c in range(min(2, nchunks)):   # warm-up: allocations, page-locking of the ring, kernels
+                run_chunk(c, c % 2)
+            torch.cuda.synchronize()
+            barrier()
+            t0 = time.perf_counter()
+            for c in range(nchunks):
+                run_chunk(c, c % 2)
+            torch.cuda.synchronize()
+            ms[mode] = (time.perf_counter() - t0) * 1e3
+            if mode == "pinned":
+                stager.sync_copies()
+                ff.close()
+        ms_pass = ms["pinned"]
         # parity: one sampled chunk per rank, its first rows against the reference's own tokenizer
         cs = (7 * rank + 3) % nchunks
         run_chunk(cs, 0)
@@ -821,14 +848,15 @@ def c5_full(torch, capi, L, dev, st, rank, world, barrier, host_threads, with_cp
                    "Gbases/s_tokenize_plus_onehot": total_bases / (s_tok + s_oh) / 1e9}
         bases = int(offs[-1])
         report = {"workload": ("configs[4] at full size: 8 M synthetic protein sequences per GPU (len 50-650, mean 350) streamed from a FlatFile per rank "
-                               f"in {nchunks} chunks of {chunk}: mapped file -> pinned bounce ring -> device (2 staging slots), int8 tokens (B,652) + "
+                               f"in {nchunks} chunks of {chunk}: file held in page-locked memory -> device (2 staging slots; the mapped-file pass "
+                               "bounces through the pinned ring instead), int8 tokens (B,652) + "
                                "uint8 one-hot (652,B,23) into a ring of 2 output buffers; PROTEIN pbeos"),
                   "seqs_per_gpu": nseq, "chunks_per_gpu": nchunks, "padlen": P, "file_bytes_per_gpu": os.path.getsize(path),
-                  "file_dir": root or tempfile.gettempdir(), "file_make_s_rank0": make_s, "cpu_baseline": cpu,
+                  "file_dir": root or tempfile.gettempdir(), "file_make_s_rank0": make_s, "file_open_s_rank0": open_s, "cpu_baseline": cpu,
                   "device_bytes_written_per_gpu": nseq * P * (1 + NC)}
         stager.close()
         ff.close()
-        return {"ms_pass": ms_pass, "bases": bases, "h2d_bytes": bases + 8 * (nseq + nchunks), "parity": ok, "nseq": nseq, "report": report}
+        return {"ms_pass": ms_pass, "ms_pass_mapped": ms["mapped"], "bases": bases, "h2d_bytes": bases + 8 * (nseq + nchunks), "parity": ok, "nseq": nseq, "report": report}
     finally:
         shutil.rmtree(td, ignore_errors=True)
 
@@ -1007,6 +1035,21 @@ def secondary_measurements(torch, capi, L, dev, st):
                        out.data_ptr() + 4096 * 1024 * j)
     ms = timed(c1, 256)
     report("c1_dna_4096x1000_bf_u8_streamed", ms, 4096 * 1000, 4096 * 1000 + 8 * 4097 + 4096 * 1024)
+    # the same 64 batches, 16 per launch (bsq_tokenize_many): what a caller with many small per-step batches uses
+    import ctypes as C2
+    groups = []
+    for g in range(nb // 16):
+        js = range(16 * g, 16 * g + 16)
+        pb = (C2.c_void_p * 16)(*[d_b.data_ptr() for _ in js])
+        po = (C2.c_void_p * 16)(*[d_o.data_ptr() + 8 * 4096 * j for j in js])
+        ns = (C2.c_int64 * 16)(*[4096 for _ in js])
+        pd = (C2.c_void_p * 16)(*[out.data_ptr() + 4096 * 1024 * j for j in js])
+        groups.append((pb, po, ns, pd))
+    def c1many(i):
+        pb, po, ns, pd = groups[i % len(groups)]
+        L.bsq_tokenize_many(dev, st, 16, pb, po, ns, 1024, C.byref(tok), 1, capi.I8, pd)
+    ms = timed(c1many, 64) / 16
+    report("c1_dna_4096x1000_bf_u8_many_16_per_launch", ms, 4096 * 1000, 4096 * 1000 + 8 * 4097 + 4096 * 1024)
     def c1big(i):
         L.bsq_tokenize(dev, st, d_b.data_ptr(), d_o.data_ptr(), 4096 * nb, 1024, C.byref(tok), 1, capi.I8, out.data_ptr())
     ms = timed(c1big, 10)

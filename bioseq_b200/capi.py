@@ -91,6 +91,7 @@ def lib():
         "bsq_shard_bounds": (i32, [vp, i64, i32, vp]),
         "bsq_tokenize_host_sharded": (i32, [vp, vp, i32, vp, vp, i64, i64, tokp, i32, i32, i32, vp, vp]),
         "bsq_memcpy_d2d": (i32, [i32, vp, vp, vp, C.c_size_t]),
+        "bsq_tokenize_many": (i32, [i32, vp, i32, vp, vp, vp, i64, tokp, i32, i32, vp]),
     }
     for name, (res, args) in sigs.items():
         fn = getattr(L, name)
@@ -108,7 +109,7 @@ EXPORTS = ("bsq_abi_version bsq_last_error bsq_launch_count bsq_launch_count_res
            "bsq_flatfile_max_seq_len bsq_flatfile_offsets bsq_flatfile_bytes bsq_flatfile_is_pinned bsq_fastx_lengths "
            "bsq_free bsq_stage_host bsq_stage_release bsq_stager_set_augment bsq_onehot_bcl bsq_embed bsq_augment_blosum62 "
            "bsq_blosum62_thresholds bsq_tokenize_items bsq_onehot_items bsq_fetch_rows bsq_parallel_for "
-           "bsq_tokenize_stream_items bsq_onehot_stream_items bsq_shard_bounds bsq_tokenize_host_sharded bsq_memcpy_d2d").split()
+           "bsq_tokenize_stream_items bsq_onehot_stream_items bsq_shard_bounds bsq_tokenize_host_sharded bsq_memcpy_d2d bsq_tokenize_many").split()
 
 
 def last_error():
@@ -152,6 +153,16 @@ def _ptr(x):
 def tokenize(device, stream, d_bytes, d_offsets, nseq, padlen, tok, batch_first, kind, d_out):
     check(lib().bsq_tokenize(device, stream, _ptr(d_bytes), _ptr(d_offsets), nseq, padlen, C.byref(tok),
                              int(batch_first), kind, _ptr(d_out)))
+
+
+def tokenize_many(device, stream, batches, padlen, tok, batch_first, kind):
+    """batches: list of (d_bytes, d_offsets, nseq, d_out).  One launch per group of up to 32 batches (bsq_tokenize_many)."""
+    n = len(batches)
+    pb = (C.c_void_p * n)(*[_ptr(b[0]) for b in batches])
+    po = (C.c_void_p * n)(*[_ptr(b[1]) for b in batches])
+    ns = (C.c_int64 * n)(*[int(b[2]) for b in batches])
+    pd = (C.c_void_p * n)(*[_ptr(b[3]) for b in batches])
+    check(lib().bsq_tokenize_many(device, stream, n, pb, po, ns, padlen, C.byref(tok), int(batch_first), kind, pd))
 
 
 def onehot(device, stream, d_bytes, d_offsets, d_mask, nseq, padlen, tok, kind, d_out):
@@ -278,9 +289,10 @@ class Pack:
 class FlatFile:
     """bsq_flatfile through the C ABI: what a non-Python host binds (the Python class lives in cbioseq)."""
 
-    def __init__(self, path, maxseqlen=-1, pinned=False):
+    def __init__(self, path, maxseqlen=-1, pinned=False, prefault=False):
         self.h = C.c_void_p()
-        check(lib().bsq_flatfile_open(C.byref(self.h), os.fsencode(path), maxseqlen, int(pinned)))
+        mode = 1 if pinned else (2 if prefault else 0)   # BSQ_FF_PINNED / BSQ_FF_MMAP_PREFAULT / BSQ_FF_MMAP
+        check(lib().bsq_flatfile_open(C.byref(self.h), os.fsencode(path), maxseqlen, mode))
 
     @staticmethod
     def make(inpath, outpath=""):

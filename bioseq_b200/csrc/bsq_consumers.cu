@@ -398,6 +398,7 @@ extern "C" {
 
 int bsq_onehot_bcl(int device, void *stream, const uint8_t *d_bytes, const int64_t *d_offsets, const uint8_t *d_mask,
                    int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out) {
+    bsq::DeviceRestore restore_device;
     using namespace bsq;
     if (int rc = check_launch_args(device, nseq, padlen, tok, kind, d_out)) return rc;
     if (nseq == 0) return BSQ_OK;
@@ -443,6 +444,7 @@ int bsq_onehot_bcl(int device, void *stream, const uint8_t *d_bytes, const int64
 
 int bsq_embed(int device, void *stream, const uint8_t *d_bytes, const int64_t *d_offsets, int64_t nseq, int64_t padlen,
               const bsq_tokenizer *tok, int batch_first, const void *d_weight, int64_t nrows, int64_t row_bytes, void *d_out) {
+    bsq::DeviceRestore restore_device;
     using namespace bsq;
     if (int rc = check_launch_args(device, nseq, padlen, tok, BSQ_I8, d_out)) return rc;
     if (d_weight == nullptr || (reinterpret_cast<uintptr_t>(d_weight) & 15u))
@@ -501,6 +503,7 @@ int bsq_blosum62_thresholds(uint32_t *out, uint8_t *row_of, uint8_t *aa) {
 
 int bsq_augment_blosum62(int device, void *stream, uint8_t *d_bytes, const int64_t *d_offsets, int64_t nseq, int chain_len,
                          double augment_frac, uint64_t seed, int64_t seq_index_base) {
+    bsq::DeviceRestore restore_device;
     using namespace bsq;
     if (nseq < 0 || chain_len < 0) return fail(BSQ_ERR_ARG, "negative count");
     if (!(augment_frac >= 0.0)) return fail(BSQ_ERR_ARG, "augment_frac must be >= 0");

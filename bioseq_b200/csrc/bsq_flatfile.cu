@@ -168,7 +168,7 @@ int bsq_flatfile_make(const char *inpath, const char *outpath, int64_t *nseqs, i
 
 int bsq_flatfile_open(bsq_flatfile **outp, const char *path, int64_t maxseqlen, int mode) {
     if (outp == nullptr || path == nullptr) return fail(BSQ_ERR_ARG, "null argument");
-    if (mode != BSQ_FF_MMAP && mode != BSQ_FF_PINNED) return fail(BSQ_ERR_ARG, "bad FlatFile mode");
+    if (mode != BSQ_FF_MMAP && mode != BSQ_FF_PINNED && mode != BSQ_FF_MMAP_PREFAULT) return fail(BSQ_ERR_ARG, "bad FlatFile mode");
     const int fd = ::open(path, O_RDONLY);
     if (fd < 0) return fail(BSQ_ERR_IO, std::strerror(errno));  // the reference surfaces mio's system_error text
     struct stat sb;
@@ -183,8 +183,12 @@ int bsq_flatfile_open(bsq_flatfile **outp, const char *path, int64_t maxseqlen, 
         return fail(BSQ_ERR_IO, std::string(path) + ": not a FlatFile (shorter than its header)");
     }
     uint8_t *base = nullptr;
-    if (mode == BSQ_FF_MMAP) {
-        void *m = ::mmap(nullptr, size, PROT_READ, MAP_SHARED, fd, 0);
+    if (mode == BSQ_FF_MMAP || mode == BSQ_FF_MMAP_PREFAULT) {
+        int flags = MAP_SHARED;
+#ifdef MAP_POPULATE
+        if (mode == BSQ_FF_MMAP_PREFAULT) flags |= MAP_POPULATE;  // page tables filled now, not fault by fault under the first pass
+#endif
+        void *m = ::mmap(nullptr, size, PROT_READ, flags, fd, 0);
         const int e = errno;
         ::close(fd);
         if (m == MAP_FAILED) return fail(BSQ_ERR_IO, std::strerror(e));
@@ -211,7 +215,7 @@ int bsq_flatfile_open(bsq_flatfile **outp, const char *path, int64_t maxseqlen, 
         ::close(fd);
     }
     auto release = [&]() {
-        if (mode == BSQ_FF_MMAP) ::munmap(base, size);
+        if (mode != BSQ_FF_PINNED) ::munmap(base, size);
         else cudaFreeHost(base);
     };
     uint64_t n;
@@ -249,7 +253,7 @@ int bsq_flatfile_open(bsq_flatfile **outp, const char *path, int64_t maxseqlen, 
 void bsq_flatfile_close(bsq_flatfile *f) {
     if (f == nullptr) return;
     if (f->base != nullptr) {
-        if (f->mode == BSQ_FF_MMAP) ::munmap(f->base, f->size);
+        if (f->mode != BSQ_FF_PINNED) ::munmap(f->base, f->size);
         else cudaFreeHost(f->base);
     }
     delete f;

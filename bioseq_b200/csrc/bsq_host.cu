@@ -325,7 +325,7 @@ void bsq_launch_count_reset(void) { bsq::g_launches = 0; }
 // host-staged pipeline
 // ---------------------------------------------------------------------------------------
 namespace {
-constexpr int kRingSlots = 3;
+constexpr int kRingSlots = 4;
 constexpr size_t kChunkBytes = size_t(4) << 20;  // residues per pipeline stage
 constexpr int64_t kSeqAlign = 128;               // chunk boundaries: whole tiles / 16-byte aligned rows
 constexpr size_t kFetchBytes = size_t(8) << 20;  // decoded characters per device -> host stage
@@ -348,14 +348,14 @@ struct bsq_stager {
     cudaStream_t copy_stream = nullptr;
     DevSlot slot[kDevSlots];
     int cur = 0;  // slot of the call in progress / of the last call
-    uint8_t *ring[kRingSlots] = {nullptr, nullptr, nullptr};
-    cudaEvent_t ring_free[kRingSlots] = {nullptr, nullptr, nullptr};
-    bool ring_used[kRingSlots] = {false, false, false};
+    uint8_t *ring[kRingSlots] = {};
+    cudaEvent_t ring_free[kRingSlots] = {};
+    bool ring_used[kRingSlots] = {};
     int ring_next = 0;
     std::vector<cudaEvent_t> events;  // one per chunk in flight
     // device -> host ring of bsq_fetch_rows
-    uint8_t *fetch_ring[kRingSlots] = {nullptr, nullptr, nullptr};
-    cudaEvent_t fetch_ev[kRingSlots] = {nullptr, nullptr, nullptr};
+    uint8_t *fetch_ring[kRingSlots] = {};
+    cudaEvent_t fetch_ev[kRingSlots] = {};
     // BLOSUM62 augmentation applied to every staged range before it is tokenised (chain_len 0 = off)
     int aug_chain = 0;
     double aug_frac = 0.0;
@@ -417,49 +417,147 @@ bool is_pinned_cached(bsq_stager *s, const void *p, size_t n) {
     return v;
 }
 
-// host -> device copy of n bytes on the copy stream; pageable sources bounce through the
-// pinned ring (the memcpy into slot k overlaps the DMA of slot k-1).
+// Software write-combining for the host copies into pinned memory (the gather of item batches, the bounce of pageable
+// sources).  In the gather a thread's share of a range lands in ONE contiguous run of the pinned pack, so the ~0.5 KB items are first appended to a 4 KiB line-aligned buffer in L1 and leave as whole 64-byte lines
+// with non-temporal stores.  Against memcpy + clwb this removes the read-for-ownership of every destination line and the
+// separate write-back pass: per batch the host memory system moves source read + pack write + DMA read instead of
+// those plus a second read of the pack -- and the host memory bandwidth is what bounds the drop-in call on the 16-core
+// B200 host (12 threads: 0.875 ms per 35 MB batch with memcpy + clwb).
+struct WcStream {
+    alignas(64) uint8_t buf[4096];
+    uint8_t *dst;   // next line-aligned destination address
+    size_t fill = 0;
+    explicit WcStream(uint8_t *aligned_dst) : dst(aligned_dst) {}
+    void flush_lines(size_t nbytes) {  // nbytes: a multiple of 64, <= fill
+#if defined(__x86_64__)
+        for (size_t o = 0; o < nbytes; o += 64) {
+            const __m128i a = _mm_load_si128(reinterpret_cast<const __m128i *>(buf + o)), b = _mm_load_si128(reinterpret_cast<const __m128i *>(buf + o + 16));
+            const __m128i c = _mm_load_si128(reinterpret_cast<const __m128i *>(buf + o + 32)), d = _mm_load_si128(reinterpret_cast<const __m128i *>(buf + o + 48));
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + o), a);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + o + 16), b);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + o + 32), c);
+            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + o + 48), d);
+        }
+#else
+        std::memcpy(dst, buf, nbytes);
+#endif
+        dst += nbytes;
+    }
+    void append(const uint8_t *p, size_t n) {
+        while (n > 0) {
+            const size_t m = std::min(n, sizeof(buf) - fill);
+            std::memcpy(buf + fill, p, m);
+            fill += m; p += m; n -= m;
+            if (fill == sizeof(buf)) {
+                flush_lines(sizeof(buf));
+                fill = 0;
+            }
+        }
+    }
+    // whole lines out; the trailing partial line (shared with the next thread's run) goes with ordinary stores
+    void finish() {
+        const size_t whole = fill & ~size_t(63);
+        flush_lines(whole);
+        if (fill > whole) {
+            std::memcpy(dst, buf + whole, fill - whole);
+            writeback_lines(dst, fill - whole);
+        }
+        fill = 0;
+    }
+};
+
+// host -> device copy of n bytes on the copy stream.  Pinned sources go as one cudaMemcpyAsync.  Pageable sources
+// (plain numpy arrays, a mapped FlatFile) bounce through a ring of pinned 4 MiB slots: pool threads fill slot after slot
+// (write-combining non-temporal stores, each thread a contiguous share of the slot) and run up to kRingSlots - 1 slots
+// ahead of the DMA engine, while this thread enqueues the copy of every slot as soon as it is full.  One pool job per
+// transfer: no per-slot dispatch (it cost ~50 us of condition-variable wake-ups per 75 us of DMA).
+struct BounceShared {
+    const uint8_t *src;
+    size_t n, nchunks;
+    int nt;
+    uint8_t *ring[kRingSlots];
+    std::vector<std::atomic<int>> filled;  // per chunk: threads done
+    std::atomic<int64_t> released{0};      // chunks whose DMA has completed + kRingSlots = chunks that may be filled
+    std::atomic<bool> abort{false};
+};
+void bounce_worker(BounceShared &b, int t) {
+    for (size_t k = 0; k < b.nchunks; ++k) {
+        spin_until([&] { return b.released.load(std::memory_order_acquire) > static_cast<int64_t>(k) || b.abort.load(std::memory_order_relaxed); });
+        if (b.abort.load(std::memory_order_relaxed)) return;
+        const size_t c0 = k * kChunkBytes, m = std::min(kChunkBytes, b.n - c0);
+        // shares on 64-byte boundaries of the slot: whole lines per thread
+        const size_t lines = (m + 63) / 64;
+        const size_t lo = std::min(m, lines * t / b.nt * 64), hi = std::min(m, lines * (t + 1) / b.nt * 64);
+        if (hi > lo) {
+            WcStream wc(b.ring[k % kRingSlots] + lo);
+            wc.append(b.src + c0 + lo, hi - lo);
+            wc.finish();
+            copy_fence();
+        }
+        b.filled[k].fetch_add(1, std::memory_order_release);
+    }
+}
+
 int stage_copy(bsq_stager *s, void *dst, const void *src, size_t n, bool src_pinned) {
     if (n == 0) return BSQ_OK;
     if (src_pinned) {
         BSQ_CUDA_TRY(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, s->copy_stream));
         return BSQ_OK;
     }
-    size_t done = 0;
-    while (done < n) {
-        const size_t m = std::min(kChunkBytes, n - done);
-        const int k = s->ring_next;
-        s->ring_next = (k + 1) % kRingSlots;
+    for (int k = 0; k < kRingSlots; ++k)
         if (s->ring[k] == nullptr) {
             BSQ_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&s->ring[k]), kChunkBytes, cudaHostAllocDefault));
             BSQ_CUDA_TRY(cudaEventCreateWithFlags(&s->ring_free[k], cudaEventDisableTiming));
         }
-        if (s->ring_used[k]) BSQ_CUDA_TRY(cudaEventSynchronize(s->ring_free[k]));
-        // one thread copies at ~11 GB/s, a fifth of the link: spread the bounce copy over the worker pool
-        // (35 MB batch from a pageable numpy array: 3.3 ms -> ~1 ms)
-        const uint8_t *from = static_cast<const uint8_t *>(src) + done;
-        uint8_t *to = s->ring[k];
-        const int nt = static_cast<int>(std::min<size_t>(static_cast<size_t>(pool_threads(1 << 20)), std::max<size_t>(1, m >> 19)));
-        if (nt > 1) {
-            Pool &pool = Pool::get();
-            pool.start(nt, [=](int t) {
-                const size_t lo = m * static_cast<size_t>(t) / nt, hi = m * static_cast<size_t>(t + 1) / nt;
-                std::memcpy(to + lo, from + lo, hi - lo);
-                writeback_lines(to + lo, hi - lo);  // the DMA engine reads these lines next
-                copy_fence();
-            });
-            pool.wait();
+    // slots still being read by the DMA of an earlier call
+    for (int k = 0; k < kRingSlots; ++k)
+        if (s->ring_used[k]) {
+            BSQ_CUDA_TRY(cudaEventSynchronize(s->ring_free[k]));
+            s->ring_used[k] = false;
+        }
+    BounceShared b;
+    b.src = static_cast<const uint8_t *>(src);
+    b.n = n;
+    b.nchunks = (n + kChunkBytes - 1) / kChunkBytes;
+    for (int k = 0; k < kRingSlots; ++k) b.ring[k] = s->ring[k];
+    b.filled = std::vector<std::atomic<int>>(b.nchunks);
+    for (auto &f : b.filled) f.store(0, std::memory_order_relaxed);
+    b.released.store(kRingSlots, std::memory_order_relaxed);
+    int nt = static_cast<int>(std::min<size_t>(static_cast<size_t>(pool_threads(1 << 20)), std::max<size_t>(1, n >> 19)));  // >= 512 KiB per thread
+    b.nt = nt;
+    Pool &pool = Pool::get();
+    const bool pooled = nt > 1;
+    if (pooled) pool.start(nt, [&b](int t) { bounce_worker(b, t); });
+    int rc = BSQ_OK;
+    for (size_t k = 0; k < b.nchunks && rc == BSQ_OK; ++k) {
+        const int slot = static_cast<int>(k % kRingSlots);
+        const size_t c0 = k * kChunkBytes, m = std::min(kChunkBytes, n - c0);
+        if (pooled) {
+            spin_until([&] { return b.filled[k].load(std::memory_order_acquire) == nt; });
         } else {
-            std::memcpy(to, from, m);
-            writeback_lines(to, m);
+            if (k >= static_cast<size_t>(kRingSlots) && cudaEventSynchronize(s->ring_free[slot]) != cudaSuccess) {
+                rc = fail(BSQ_ERR_CUDA, "bounce copy failed");
+                break;
+            }
+            WcStream wc(s->ring[slot]);
+            wc.append(b.src + c0, m);
+            wc.finish();
             copy_fence();
         }
-        BSQ_CUDA_TRY(cudaMemcpyAsync(static_cast<uint8_t *>(dst) + done, s->ring[k], m, cudaMemcpyHostToDevice, s->copy_stream));
-        BSQ_CUDA_TRY(cudaEventRecord(s->ring_free[k], s->copy_stream));
-        s->ring_used[k] = true;
-        done += m;
+        if (rc == BSQ_OK && cudaMemcpyAsync(static_cast<uint8_t *>(dst) + c0, s->ring[slot], m, cudaMemcpyHostToDevice, s->copy_stream) != cudaSuccess)
+            rc = fail(BSQ_ERR_CUDA, "cudaMemcpyAsync failed in the bounce ring");
+        if (rc == BSQ_OK && cudaEventRecord(s->ring_free[slot], s->copy_stream) != cudaSuccess) rc = fail(BSQ_ERR_CUDA, "cudaEventRecord failed");
+        s->ring_used[slot] = true;
+        // the slot of chunk k + 1 - kRingSlots ... is free again once ITS copy has completed: release the next chunk
+        if (pooled && rc == BSQ_OK && k + 1 >= static_cast<size_t>(kRingSlots) && k + 1 < b.nchunks) {
+            const int nslot = static_cast<int>((k + 1) % kRingSlots);
+            if (cudaEventSynchronize(s->ring_free[nslot]) != cudaSuccess) rc = fail(BSQ_ERR_CUDA, "bounce copy failed");
+            b.released.store(static_cast<int64_t>(k) + 2, std::memory_order_release);
+        }
     }
-    return BSQ_OK;
+    if (rc) b.abort.store(true);
+    if (pooled) pool.wait();
+    return rc;
 }
 
 struct RunArgs {
@@ -627,55 +725,6 @@ void items_walk(ItemsShared &sh, int64_t k, int t) {
     sh.sum[j] = sum; sh.mx[j] = mx; sh.special[j] = special;
     sh.walked[static_cast<size_t>(k)].fetch_add(1, std::memory_order_release);
 }
-
-// Software write-combining for the gather: a thread's share of a range lands in ONE contiguous run of the pinned
-// pack, so the ~0.5 KB items are first appended to a 4 KiB line-aligned buffer in L1 and leave as whole 64-byte lines
-// with non-temporal stores.  Against memcpy + clwb this removes the read-for-ownership of every destination line and the
-// separate write-back pass: per batch the host memory system moves source read + pack write + DMA read instead of
-// those plus a second read of the pack -- and the host memory bandwidth is what bounds the drop-in call on the 16-core
-// B200 host (12 threads: 0.875 ms per 35 MB batch with memcpy + clwb).
-struct WcStream {
-    alignas(64) uint8_t buf[4096];
-    uint8_t *dst;   // next line-aligned destination address
-    size_t fill = 0;
-    explicit WcStream(uint8_t *aligned_dst) : dst(aligned_dst) {}
-    void flush_lines(size_t nbytes) {  // nbytes: a multiple of 64, <= fill
-#if defined(__x86_64__)
-        for (size_t o = 0; o < nbytes; o += 64) {
-            const __m128i a = _mm_load_si128(reinterpret_cast<const __m128i *>(buf + o)), b = _mm_load_si128(reinterpret_cast<const __m128i *>(buf + o + 16));
-            const __m128i c = _mm_load_si128(reinterpret_cast<const __m128i *>(buf + o + 32)), d = _mm_load_si128(reinterpret_cast<const __m128i *>(buf + o + 48));
-            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + o), a);
-            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + o + 16), b);
-            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + o + 32), c);
-            _mm_stream_si128(reinterpret_cast<__m128i *>(dst + o + 48), d);
-        }
-#else
-        std::memcpy(dst, buf, nbytes);
-#endif
-        dst += nbytes;
-    }
-    void append(const uint8_t *p, size_t n) {
-        while (n > 0) {
-            const size_t m = std::min(n, sizeof(buf) - fill);
-            std::memcpy(buf + fill, p, m);
-            fill += m; p += m; n -= m;
-            if (fill == sizeof(buf)) {
-                flush_lines(sizeof(buf));
-                fill = 0;
-            }
-        }
-    }
-    // whole lines out; the trailing partial line (shared with the next thread's run) goes with ordinary stores
-    void finish() {
-        const size_t whole = fill & ~size_t(63);
-        flush_lines(whole);
-        if (fill > whole) {
-            std::memcpy(dst, buf + whole, fill - whole);
-            writeback_lines(dst, fill - whole);
-        }
-        fill = 0;
-    }
-};
 
 void items_gather(ItemsShared &sh, int64_t k, int t) {
     const int64_t a = sh.cut(k, t), b = sh.cut(k, t + 1);
@@ -979,6 +1028,7 @@ int fetch_rows(bsq_stager *s, cudaStream_t st, const uint8_t *d_chars, const int
 extern "C" {
 
 int bsq_stager_create(bsq_stager **out, int device) {
+    bsq::DeviceRestore restore_device;
     if (out == nullptr) return fail(BSQ_ERR_ARG, "null argument");
     BSQ_CUDA_TRY(cudaSetDevice(device));
     bsq_stager *s = new bsq_stager();
@@ -994,6 +1044,7 @@ int bsq_stager_create(bsq_stager **out, int device) {
 }
 
 void bsq_stager_destroy(bsq_stager *s) {
+    bsq::DeviceRestore restore_device;
     if (s == nullptr) return;
     cudaSetDevice(s->device);
     cudaDeviceSynchronize();
@@ -1039,6 +1090,7 @@ int bsq_stager_set_augment(bsq_stager *s, int chain_len, double augment_frac, ui
 
 int bsq_stage_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const int64_t *h_offsets, int64_t nseq,
                    const uint8_t **d_bytes, const int64_t **d_offsets) {
+    bsq::DeviceRestore restore_device;
     if (s == nullptr || d_bytes == nullptr || d_offsets == nullptr) return fail(BSQ_ERR_ARG, "null argument");
     if (nseq < 0 || h_offsets == nullptr) return fail(BSQ_ERR_ARG, "bad offsets");
     BSQ_CUDA_TRY(cudaSetDevice(s->device));
@@ -1071,6 +1123,7 @@ int bsq_stage_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const in
 }
 
 int bsq_stage_release(bsq_stager *s, void *stream) {
+    bsq::DeviceRestore restore_device;
     if (s == nullptr) return fail(BSQ_ERR_ARG, "null stager");
     BSQ_CUDA_TRY(cudaSetDevice(s->device));
     return stage_end(s, static_cast<cudaStream_t>(stream));
@@ -1078,32 +1131,38 @@ int bsq_stage_release(bsq_stager *s, void *stream) {
 
 int bsq_tokenize_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const int64_t *h_offsets, int64_t nseq,
                       int64_t padlen, const bsq_tokenizer *tok, int batch_first, int kind, void *d_out) {
+    bsq::DeviceRestore restore_device;
     return staged_run(s, static_cast<cudaStream_t>(stream), h_bytes, h_offsets, nullptr, nseq, padlen, tok, 0, batch_first,
                       kind, d_out);
 }
 
 int bsq_onehot_host(bsq_stager *s, void *stream, const uint8_t *h_bytes, const int64_t *h_offsets, const uint8_t *h_mask,
                     int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out) {
+    bsq::DeviceRestore restore_device;
     return staged_run(s, static_cast<cudaStream_t>(stream), h_bytes, h_offsets, h_mask, nseq, padlen, tok, 1, 0, kind, d_out);
 }
 
 int bsq_tokenize_items(bsq_stager *s, bsq_pack *p, void *stream, const void *const *ptrs, const int64_t *lens, int64_t n,
                        int64_t padlen, const bsq_tokenizer *tok, int batch_first, int kind, void *d_out, int nthreads) {
+    bsq::DeviceRestore restore_device;
     return items_run(s, p, static_cast<cudaStream_t>(stream), ptrs, lens, n, padlen, tok, 0, batch_first, kind, d_out, nthreads);
 }
 
 int bsq_onehot_items(bsq_stager *s, bsq_pack *p, void *stream, const void *const *ptrs, const int64_t *lens, int64_t n,
                      int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out, int nthreads) {
+    bsq::DeviceRestore restore_device;
     return items_run(s, p, static_cast<cudaStream_t>(stream), ptrs, lens, n, padlen, tok, 1, 0, kind, d_out, nthreads);
 }
 
 int bsq_tokenize_stream_items(bsq_stager *s, void *stream, int64_t n, bsq_resolve_fn resolve, bsq_fixup_fn fixup, void *ctx,
                               int64_t padlen, const bsq_tokenizer *tok, int batch_first, int kind, void *d_out, int nthreads) {
+    bsq::DeviceRestore restore_device;
     return items_stream_run(s, static_cast<cudaStream_t>(stream), n, resolve, fixup, ctx, padlen, tok, 0, batch_first, kind, d_out, nthreads);
 }
 
 int bsq_onehot_stream_items(bsq_stager *s, void *stream, int64_t n, bsq_resolve_fn resolve, bsq_fixup_fn fixup, void *ctx,
                             int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out, int nthreads) {
+    bsq::DeviceRestore restore_device;
     return items_stream_run(s, static_cast<cudaStream_t>(stream), n, resolve, fixup, ctx, padlen, tok, 1, 0, kind, d_out, nthreads);
 }
 
@@ -1128,6 +1187,7 @@ int bsq_shard_bounds(const int64_t *h_offsets, int64_t nseq, int nshards, int64_
 int bsq_tokenize_host_sharded(bsq_stager *const *stagers, void *const *streams, int ndev, const uint8_t *h_bytes, const int64_t *h_offsets,
                               int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int onehot, int batch_first, int kind,
                               void *const *d_outs, const int64_t *bounds) {
+    bsq::DeviceRestore restore_device;
     if (stagers == nullptr || streams == nullptr || d_outs == nullptr || bounds == nullptr || ndev <= 0) return fail(BSQ_ERR_ARG, "bad shard arguments");
     if (int rc = bsq_check_lengths_host(h_offsets, nseq, padlen, tok)) return rc;
     std::vector<int> rcs(static_cast<size_t>(ndev), BSQ_OK);
@@ -1153,6 +1213,7 @@ int bsq_tokenize_host_sharded(bsq_stager *const *stagers, void *const *streams, 
 }
 
 int bsq_memcpy_d2d(int device, void *stream, void *d_dst, const void *d_src, size_t nbytes) {
+    bsq::DeviceRestore restore_device;
     BSQ_CUDA_TRY(cudaSetDevice(device));
     BSQ_CUDA_TRY(cudaMemcpyAsync(d_dst, d_src, nbytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
     return BSQ_OK;
@@ -1173,6 +1234,7 @@ int bsq_parallel_for(int nthreads, void (*fn)(int, int, void *), void *ctx) {
 
 int bsq_fetch_rows(bsq_stager *s, void *stream, const uint8_t *d_chars, const int64_t *h_offsets, int64_t rows, void *const *dst,
                    int nthreads) {
+    bsq::DeviceRestore restore_device;
     return fetch_rows(s, static_cast<cudaStream_t>(stream), d_chars, h_offsets, rows, dst, nthreads);
 }
 

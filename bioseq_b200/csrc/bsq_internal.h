@@ -28,6 +28,28 @@ int check_launch_args(int device, int64_t nseq, int64_t padlen, const bsq_tokeni
 
 }  // namespace bsq
 
+#ifdef __CUDACC__
+namespace bsq {
+// Entry points take their device explicitly and switch to it; the caller's current device is put back on return
+// (a host that drives several devices from one thread -- torch does -- must not find it changed behind its back).
+struct DeviceRestore {
+    int prev = -1;
+    DeviceRestore() {
+        if (cudaGetDevice(&prev) != cudaSuccess) {
+            cudaGetLastError();
+            prev = -1;
+        }
+    }
+    ~DeviceRestore() {
+        int now = -1;
+        if (prev >= 0 && cudaGetDevice(&now) == cudaSuccess && now != prev) cudaSetDevice(prev);
+    }
+    DeviceRestore(const DeviceRestore &) = delete;
+    DeviceRestore &operator=(const DeviceRestore &) = delete;
+};
+}  // namespace bsq
+#endif
+
 #define BSQ_CUDA_TRY(expr)                                                                       \
     do {                                                                                         \
         cudaError_t err__ = (expr);                                                              \

@@ -1681,6 +1681,7 @@ extern "C" {
 
 int bsq_tokenize(int device, void *stream, const uint8_t *d_bytes, const int64_t *d_offsets, int64_t nseq,
                  int64_t padlen, const bsq_tokenizer *tok, int batch_first, int kind, void *d_out) {
+    bsq::DeviceRestore restore_device;
     if (int rc = check_common(device, nseq, padlen, tok, kind, d_out)) return rc;
     if (nseq == 0) return BSQ_OK;
     if (d_offsets == nullptr) return fail(BSQ_ERR_ARG, "null offsets");
@@ -1688,8 +1689,35 @@ int bsq_tokenize(int device, void *stream, const uint8_t *d_bytes, const int64_t
                            kind, d_out, /*first_off=*/-1);
 }
 
+int bsq_tokenize_many(int device, void *stream, int nbatch, const uint8_t *const *d_bytes, const int64_t *const *d_offsets,
+                      const int64_t *nseq, int64_t padlen, const bsq_tokenizer *tok, int batch_first, int kind, void *const *d_out) {
+    bsq::DeviceRestore restore_device;
+    if (nbatch < 0 || (nbatch > 0 && (d_bytes == nullptr || d_offsets == nullptr || nseq == nullptr || d_out == nullptr)))
+        return fail(BSQ_ERR_ARG, "bad batch arguments");
+    for (int k = 0; k < nbatch; ++k) {
+        if (int rc = check_common(device, nseq[k], padlen, tok, kind, d_out[k])) return rc;
+        if (nseq[k] > 0 && d_offsets[k] == nullptr) return fail(BSQ_ERR_ARG, "null offsets");
+    }
+    if (nbatch == 0) return BSQ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (batch_first && bsq_kind_size(kind) == 1 && span_kernel_applicable(padlen)) {
+        const Prepared p = prepare(*tok, 0);
+        for (int k0 = 0; k0 < nbatch; k0 += kSpanManyMax) {  // one launch per group of up to 32 batches
+            const int nb = std::min(kSpanManyMax, nbatch - k0);
+            if (int rc = launch_tokenize_span_many(device, st, nb, d_bytes + k0, d_offsets + k0, nseq + k0, padlen, p,
+                                                   reinterpret_cast<uint8_t *const *>(d_out + k0), pdl_enabled()))
+                return rc;
+        }
+        return BSQ_OK;
+    }
+    for (int k = 0; k < nbatch; ++k)  // layouts / element types without a multi-batch kernel: one launch each
+        if (int rc = launch_tokenize(st, d_bytes[k], d_offsets[k], nseq[k], nseq[k], padlen, *tok, batch_first, kind, d_out[k], -1)) return rc;
+    return BSQ_OK;
+}
+
 int bsq_onehot(int device, void *stream, const uint8_t *d_bytes, const int64_t *d_offsets, const uint8_t *d_mask,
                int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int kind, void *d_out) {
+    bsq::DeviceRestore restore_device;
     if (int rc = check_common(device, nseq, padlen, tok, kind, d_out)) return rc;
     if (nseq == 0) return BSQ_OK;
     if (d_offsets == nullptr) return fail(BSQ_ERR_ARG, "null offsets");
@@ -1728,6 +1756,7 @@ int scratch_alloc(int device, void **p, size_t bytes, cudaStream_t st) {
 
 int bsq_check_lengths_device(int device, void *stream, const int64_t *d_offsets, int64_t nseq, int64_t padlen,
                              const bsq_tokenizer *tok) {
+    bsq::DeviceRestore restore_device;
     if (tok == nullptr) return fail(BSQ_ERR_ARG, "null tokenizer");
     if (padlen <= 0) return fail(BSQ_ERR_ARG, "batch tokenize requires padlen is provded.");
     if (nseq <= 0) return BSQ_OK;
@@ -1752,6 +1781,7 @@ int bsq_check_lengths_device(int device, void *stream, const int64_t *d_offsets,
 int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows, int64_t cols,
                        int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok, int64_t *d_row_offsets,
                        int64_t *total_chars) {
+    bsq::DeviceRestore restore_device;
     if (tok == nullptr || total_chars == nullptr) return fail(BSQ_ERR_ARG, "null argument");
     if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8)
         return fail(BSQ_ERR_ARG, "Unexpected itemsize: expected 1, 2, 4, or 8. Found " + std::to_string(itemsize));  // src/tokenize.h:123
@@ -1805,6 +1835,7 @@ int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int items
 int bsq_decode_chars(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows, int64_t cols,
                      int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok, const int64_t *d_row_offsets,
                      uint8_t *d_chars) {
+    bsq::DeviceRestore restore_device;
     if (tok == nullptr) return fail(BSQ_ERR_ARG, "null tokenizer");
     if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8) return fail(BSQ_ERR_ARG, "bad itemsize");
     if (rows <= 0 || cols <= 0) return BSQ_OK;

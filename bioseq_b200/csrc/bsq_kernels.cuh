@@ -74,6 +74,14 @@ Prepared prepare(const bsq_tokenizer &tok, int mode);
 bool span_kernel_applicable(int64_t padlen);
 int launch_tokenize_span(int device, cudaStream_t st, const SeqView &v, int64_t nseq, int64_t padlen, const Prepared &p,
                          uint8_t *out, bool pdl_allowed);
+// A slot of the per-stream tile counters of the dynamic schedulers (bsq_span.cu), or nullptr when none can be used
+// (stream capture in progress, out of memory): the kernels then keep their static tile order.
+unsigned int *tile_counter_slot(int device, cudaStream_t st);
+// n / d = umulhi(n, mul) >> shift for 0 <= n < 2^31, 2 <= d <= 2^30.
+void span_magic(uint32_t d, uint32_t *mul, uint32_t *shift);
+constexpr int kSpanManyMax = 32;  // batches per launch of launch_tokenize_span_many
+int launch_tokenize_span_many(int device, cudaStream_t st, int nbatch, const uint8_t *const *d_bytes, const int64_t *const *d_offs,
+                              const int64_t *nseqs, int64_t padlen, const Prepared &p, uint8_t *const *outs, bool pdl_allowed);
 
 #ifdef __CUDACC__
 

@@ -42,6 +42,8 @@ namespace bsq {
 
 namespace {
 
+constexpr unsigned kWaitBackoffNs = 64;
+
 constexpr int kSpanConsumerWarps = 8;
 constexpr int kSpanConsumers = kSpanConsumerWarps * 32;
 constexpr int kSpanThreads = kSpanConsumers + 32;
@@ -60,14 +62,20 @@ __device__ __forceinline__ void bar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void bar_wait(uint32_t bar, uint32_t parity) {
+    // A warp that polls in a tight loop takes issue slots from the warps that have work (ncu r02n: 40 % of the
+    // executed instructions were polls); after a failed first try it backs off with nanosleep between tries.
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra BSQ_SPAN_WAIT_DONE_%=;\n"
         "BSQ_SPAN_WAIT_%=:\n"
+        "nanosleep.u32 %2;\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@!p bra BSQ_SPAN_WAIT_%=;\n"
+        "BSQ_SPAN_WAIT_DONE_%=:\n"
         "}\n" ::"r"(bar),
-        "r"(parity)
+        "r"(parity), "r"(kWaitBackoffNs)
         : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -76,13 +84,24 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void *src, uint32_
                  : "memory");
 }
 
-struct SpanParams {
+// One launch can serve several batches that share padlen and tokenizer (bsq_tokenize_many: the small per-step batches of
+// the reference's training loops, training/cnnpretrain.py:123-125,145): their tiles are numbered one batch after the other.
+constexpr int kSpanMaxBatches = 32;
+struct SpanBatch {
     const uint8_t *bytes;
     const int64_t *offs;
     uint8_t *out;
     int64_t nseq;
-    int64_t total;    // nseq * padlen output bytes
+    int64_t total;       // nseq * padlen output bytes
+    int64_t first_tile;  // index of the batch's first tile
+};
+struct SpanBatches {
+    SpanBatch b[kSpanMaxBatches];
+};
+
+struct SpanParams {
     int64_t ntiles;
+    int nbatch;
     // Tiles beyond a CTA's first (= blockIdx.x) are handed out by an atomic counter, gridDim.x + atomicAdd(ctr, 1):
     // whatever the placement and start time of the CTAs (a programmatically launched grid gets its SM slots as the
     // previous grid drains), the work stays balanced.  ctr[0] = tiles handed out, ctr[1] = CTAs that have seen the end;
@@ -229,14 +248,14 @@ struct SpanEdges {
 
 template <int NSTAGE, bool ALIGNED, bool PRE, int MINB>
 __global__ void __launch_bounds__(kSpanThreads, MINB)
-tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp) {
+tokenize_span_kernel(const SpanParams q, const __grid_constant__ SpanBatches mb, const LutParam lutp, const Specials sp) {
     extern __shared__ __align__(128) uint8_t dyn[];  // NSTAGE x { data[stage_bytes], rows[max_rows] x 16 B }
     __shared__ __align__(256) uint8_t lut[256];
     __shared__ TailTab tab;
     __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE];
     __shared__ __align__(16) int4 hdr[NSTAGE];           // c_first, nrows, nvec, -
     __shared__ __align__(16) uint32_t cst[kCstWords];    // loop invariants of the consumers (see SpanRegs)
-    __shared__ int tile_of[NSTAGE];                      // tile index of the stage's contents
+    __shared__ uint8_t *tile_out[NSTAGE];                // where the stage's tile starts in its batch's output
 
     // Programmatic dependent launch: the next kernel of the stream may start its prologue now; ours (LUT, mask
     // tables, barriers: no global memory) runs before the previous kernel of the stream has finished.
@@ -268,24 +287,29 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
         // ------------------------------- producer -------------------------------
         // Tile coordinates: first row r0 and column c_first of the tile's first byte, last row r1 / column c_last.
         struct Coord {
-            int64_t r0, r1;
-            int c_first, c_last;
+            int64_t r0, r1, f0;
+            int c_first, c_last, batch, len;  // len: bytes of the tile (the batch's last tile may be short)
         };
         auto coord_of = [&](int64_t tt) {
             Coord c;
-            const int64_t f0 = tt * tile_bytes;
-            c.r0 = f0 / q.padlen;
-            c.c_first = static_cast<int>(f0 - c.r0 * q.padlen);
-            const uint32_t e = static_cast<uint32_t>(c.c_first) + static_cast<uint32_t>(min(static_cast<int64_t>(tile_bytes), q.total - f0)) - 1u;
+            int bi = 0;
+            while (bi + 1 < q.nbatch && tt >= mb.b[bi + 1].first_tile) ++bi;
+            c.batch = bi;
+            c.f0 = (tt - mb.b[bi].first_tile) * tile_bytes;
+            c.len = static_cast<int>(min(static_cast<int64_t>(tile_bytes), mb.b[bi].total - c.f0));
+            c.r0 = c.f0 / q.padlen;
+            c.c_first = static_cast<int>(c.f0 - c.r0 * q.padlen);
+            const uint32_t e = static_cast<uint32_t>(c.c_first) + static_cast<uint32_t>(c.len) - 1u;
             const uint32_t dr = __umulhi(e, q.div_mul) >> q.div_shift;
             c.c_last = static_cast<int>(e - dr * static_cast<uint32_t>(q.padlen));
             c.r1 = c.r0 + dr;
             return c;
         };
         auto load_edges = [&](const Coord &c) {
+            const int64_t *offs = mb.b[c.batch].offs;
             SpanEdges e;
-            e.a0 = __ldg(q.offs + c.r0); e.a1 = __ldg(q.offs + c.r0 + 1);
-            e.b0 = __ldg(q.offs + c.r1); e.b1 = __ldg(q.offs + c.r1 + 1);
+            e.a0 = __ldg(offs + c.r0); e.a1 = __ldg(offs + c.r0 + 1);
+            e.b0 = __ldg(offs + c.r1); e.b1 = __ldg(offs + c.r1 + 1);
             return e;
         };
         // next tile index of this CTA, requested one tile ahead of its use (lane 0 asks, everybody gets the answer)
@@ -299,7 +323,8 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
         Coord cc = coord_of(t);
         // offsets of this CTA's first tile: into L2 while the previous kernel drains (a prefetch is only a hint,
         // the real loads come after the wait)
-        if (16 * lane <= tile_bytes / q.padlen + 2 && cc.r0 + 16 * lane <= q.nseq) asm volatile("prefetch.global.L2 [%0];" ::"l"(q.offs + cc.r0 + 16 * lane));
+        const int64_t *offs0 = mb.b[cc.batch].offs;
+        if (16 * lane <= tile_bytes / q.padlen + 2 && cc.r0 + 16 * lane <= mb.b[cc.batch].nseq) asm volatile("prefetch.global.L2 [%0];" ::"l"(offs0 + cc.r0 + 16 * lane));
         const int maxlen = max(q.padlen - sp.bos - sp.eos, 0);
         {
             // ... and the tile's residues too, from the offsets as they read NOW.  The previous kernel of the stream may
@@ -307,12 +332,12 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
             // can stay in L1), address nothing but an L2 prefetch -- which is dropped when its address is not mapped
             // (tools/probes/prefetch_probe.cu) -- and are read again for real after the wait.
             int64_t sa0, sb0, sb1;
-            asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(sa0) : "l"(q.offs + cc.r0));
-            asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(sb0) : "l"(q.offs + cc.r1));
-            asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(sb1) : "l"(q.offs + cc.r1 + 1));
+            asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(sa0) : "l"(offs0 + cc.r0));
+            asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(sb0) : "l"(offs0 + cc.r1));
+            asm volatile("ld.global.cg.s64 %0, [%1];" : "=l"(sb1) : "l"(offs0 + cc.r1 + 1));
             const int64_t span = min(max(sb1 - sa0, int64_t(0)), static_cast<int64_t>(q.stage_bytes));
             (void)sb0;
-            const uintptr_t pa = reinterpret_cast<uintptr_t>(q.bytes + sa0) & ~uintptr_t(15);
+            const uintptr_t pa = reinterpret_cast<uintptr_t>(mb.b[cc.batch].bytes + sa0) & ~uintptr_t(15);
             const uint32_t pn = static_cast<uint32_t>((span + 31) & ~int64_t(15));
             if (lane == 0 && pn > 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pa), "r"(pn) : "memory");
         }
@@ -334,28 +359,29 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
             }
             const int s = static_cast<int>(it % NSTAGE);
             const uint32_t ph = (it / NSTAGE) & 1u;
-            const int64_t f0 = t * tile_bytes, f1 = min(f0 + tile_bytes, q.total);
+            const uint8_t *bytes = mb.b[cc.batch].bytes;
+            const int64_t *offs = mb.b[cc.batch].offs;
             const int nrows = static_cast<int>(cc.r1 - cc.r0) + 1;
             // the span: residues of columns [c_first, padlen) of row r0 ... [0, c_last] of row r1
             const int len0 = static_cast<int>(min(max(cur.a1 - cur.a0, int64_t(0)), static_cast<int64_t>(maxlen)));
             const int len1 = static_cast<int>(min(max(cur.b1 - cur.b0, int64_t(0)), static_cast<int64_t>(maxlen)));
             const int64_t lo = cur.a0 + min(max(cc.c_first - sp.bos, 0), len0);
             const int64_t hi = cur.b0 + min(max(cc.c_last + 1 - sp.bos, 0), len1);
-            const uintptr_t A_lo = reinterpret_cast<uintptr_t>(q.bytes + lo) & ~uintptr_t(15);
-            const uintptr_t A_hi = (reinterpret_cast<uintptr_t>(q.bytes + hi) + 15) & ~uintptr_t(15);
+            const uintptr_t A_lo = reinterpret_cast<uintptr_t>(bytes + lo) & ~uintptr_t(15);
+            const uintptr_t A_hi = (reinterpret_cast<uintptr_t>(bytes + hi) + 15) & ~uintptr_t(15);
             const uint32_t nbytes = hi > lo ? static_cast<uint32_t>(min(static_cast<int64_t>(A_hi - A_lo),
                                                                          static_cast<int64_t>(q.stage_bytes - kSpanSlack - kSpanTail)))
                                             : 0u;
             uint8_t *stage = dyn + static_cast<size_t>(s) * stage_stride;
             int4 *rows = reinterpret_cast<int4 *>(stage + q.stage_bytes);
             // shared address of the byte that column 0 of row r0 + i comes from
-            const int64_t base = static_cast<int64_t>(reinterpret_cast<uintptr_t>(q.bytes)) - static_cast<int64_t>(A_lo) + kSpanSlack - sp.bos +
+            const int64_t base = static_cast<int64_t>(reinterpret_cast<uintptr_t>(bytes)) - static_cast<int64_t>(A_lo) + kSpanSlack - sp.bos +
                                  static_cast<int64_t>(s_u32(stage));
             auto row_entry = [&](int i) {  // {source address of column 0, bos + len, bos + len + eos, the previous row's bos + len + eos}
-                const int64_t o0 = __ldg(q.offs + cc.r0 + i), o1 = __ldg(q.offs + cc.r0 + i + 1);
+                const int64_t o0 = __ldg(offs + cc.r0 + i), o1 = __ldg(offs + cc.r0 + i + 1);
                 const int n = sp.bos + static_cast<int>(min(max(o1 - o0, int64_t(0)), static_cast<int64_t>(maxlen)));
                 int pn = 0;
-                if (!ALIGNED && i > 0) pn = sp.bos + sp.eos + static_cast<int>(min(max(o0 - __ldg(q.offs + cc.r0 + i - 1), int64_t(0)), static_cast<int64_t>(maxlen)));
+                if (!ALIGNED && i > 0) pn = sp.bos + sp.eos + static_cast<int>(min(max(o0 - __ldg(offs + cc.r0 + i - 1), int64_t(0)), static_cast<int64_t>(maxlen)));
                 return make_int4(static_cast<int>(o0 + base), n, n + sp.eos, pn);
             };
             // the first 32 rows' entries are formed before the barrier wait (their offsets are in flight meanwhile)
@@ -367,8 +393,9 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
                     bar_expect_tx(s_u32(full + s), nbytes);
                     bulk_load(s_u32(stage + kSpanSlack), reinterpret_cast<const void *>(A_lo), nbytes, s_u32(full + s));
                 }
-                hdr[s] = make_int4(cc.c_first, nrows, static_cast<int>((f1 - f0 + 15) >> 4), static_cast<int>(nbytes));
-                tile_of[s] = static_cast<int>(t);
+                // {first column, bytes to keep of a final partial vector (0: none), vectors, staged bytes}
+                hdr[s] = make_int4(cc.c_first, cc.len & 15, (cc.len + 15) >> 4, static_cast<int>(nbytes));
+                tile_out[s] = mb.b[cc.batch].out + cc.f0;
             }
             if (lane < nrows) rows[lane] = e0;
             for (int i = lane + 32; i < nrows; i += 32) rows[i] = row_entry(i);
@@ -423,7 +450,7 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
         bar_wait(s_u32(full + s), ph);
         const int4 h = hdr[s];
         if (h.z < 0) break;  // no more tiles for this CTA
-        const int64_t tile0 = static_cast<int64_t>(tile_of[s]) * tile_bytes;
+        uint8_t *const otile = tile_out[s];
         if (PRE) {
             // phase 1: the staged residues become codes in place -- dense (every lane busy, no row logic, no
             // realignment): LDS.128, 16 look-ups, STS.128 per 16 bytes of the span
@@ -439,7 +466,7 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
         // F: column-space offset of the lane's vector from column 0 of the tile's first row
         uint32_t F = static_cast<uint32_t>(h.x) + 16u * static_cast<uint32_t>(ctid);
         const uint32_t Fend = static_cast<uint32_t>(h.x) + 16u * static_cast<uint32_t>(h.z);
-        uint8_t *dst = q.out + tile0 + 16 * ctid;
+        uint8_t *dst = otile + 16 * ctid;
         if (ALIGNED) {
             for (; F < Fend; F += 16u * kSpanConsumers, dst += 16 * kSpanConsumers) {
                 const uint32_t rl = __umulhi(F, g.mul) >> g.shift;
@@ -453,7 +480,7 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
             // A vector belongs to the row that holds its LAST byte: its columns run from col in [-15, padlen - 16], the
             // bytes left of column 0 are the previous row's tail -- pad, unless that row is nearly full (rare: the general
             // path).  So the straddling vector costs one translation like any other, in the same instruction stream.
-            const bool partial_tail = tile0 + 16 * static_cast<int64_t>(h.z) > q.total;  // the batch's final vector is cut short
+            const bool partial_tail = h.y != 0;  // the batch's final vector is cut short
             const uint32_t Fsafe = partial_tail ? Fend - 16u : Fend;
             for (; F < Fsafe; F += 16u * kSpanConsumers, dst += 16 * kSpanConsumers) {
                 const uint32_t rl = __umulhi(F + 15u, g.mul) >> g.shift;
@@ -473,7 +500,7 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
                 const int4 ri = lds128i(rows_a + 16u * rl);
                 uint4 codes = g.padq;
                 if (col < ri.z) codes = span_row_codes_u<PRE>(static_cast<uint32_t>(ri.x), ri.y, col, g);
-                const int keep = static_cast<int>(q.total - (tile0 + static_cast<int64_t>(F - static_cast<uint32_t>(h.x))));
+                const int keep = h.y;
                 const uint32_t w[4] = {codes.x, codes.y, codes.z, codes.w};
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
@@ -487,14 +514,6 @@ tokenize_span_kernel(const SpanParams q, const LutParam lutp, const Specials sp)
     }
 }
 
-// n / d = umulhi(n, mul) >> shift for every 0 <= n < 2^31 and 2 <= d <= 2^30 (round-up magic number with one
-// bit of headroom: no add-back step, two instructions per division).
-void span_magic(uint32_t d, uint32_t *mul, uint32_t *shift) {
-    uint32_t s = 0;
-    while ((1ull << s) < d) ++s;
-    *mul = static_cast<uint32_t>((1ull << (31 + s)) / d + 1);
-    *shift = s - 1;
-}
 
 int span_env(const char *name, int dflt) {
     const char *e = std::getenv(name);
@@ -552,6 +571,20 @@ unsigned int *span_counter(DevInfo &d, cudaStream_t st) {
 
 }  // namespace
 
+// n / d = umulhi(n, mul) >> shift for every 0 <= n < 2^31 and 2 <= d <= 2^30 (round-up magic number with one
+// bit of headroom: no add-back step, two instructions per division).
+void span_magic(uint32_t d, uint32_t *mul, uint32_t *shift) {
+    uint32_t s = 0;
+    while ((1ull << s) < d) ++s;
+    *mul = static_cast<uint32_t>((1ull << (31 + s)) / d + 1);
+    *shift = s - 1;
+}
+
+unsigned int *tile_counter_slot(int device, cudaStream_t st) {
+    std::lock_guard<std::mutex> dev_lock(g_dev_mu);
+    return span_counter(dev_info(device), st);
+}
+
 bool span_kernel_applicable(int64_t padlen) {
     static const bool tune = span_env("BSQ_TUNE", 0) != 0;
     static bool on = span_env("BSQ_SPAN", 1) != 0;
@@ -563,9 +596,9 @@ bool span_kernel_applicable(int64_t padlen) {
     return on && padlen >= minp && padlen <= (1ll << 30);
 }
 
-// Launches K1s over `nseq` rows; `device` is the current device.  Returns BSQ_OK or an error code.
-int launch_tokenize_span(int device, cudaStream_t st, const SeqView &v, int64_t nseq, int64_t padlen, const Prepared &p, uint8_t *out,
-                         bool pdl_allowed) {
+// Launches K1s over `nbatch` (<= kSpanMaxBatches) batches that share padlen and tokenizer; `device` is the current device.
+int launch_tokenize_span_many(int device, cudaStream_t st, int nbatch, const uint8_t *const *d_bytes, const int64_t *const *d_offs,
+                              const int64_t *nseqs, int64_t padlen, const Prepared &p, uint8_t *const *outs, bool pdl_allowed) {
     // A/B knobs (read once; BSQ_TUNE=1 re-reads them at every launch for in-process sweeps)
     static const bool tune = span_env("BSQ_TUNE", 0) != 0;
     static int vt_max = 0, nstage = 0, ctas_env = 0, two_phase = 0, minb = 4, dynamic = 1;
@@ -577,15 +610,20 @@ int launch_tokenize_span(int device, cudaStream_t st, const SeqView &v, int64_t 
         minb = std::min(6, std::max(4, span_env("BSQ_SPAN_MINB", 4)));
         dynamic = span_env("BSQ_SPAN_DYN", 1);
     }
+    if (nbatch <= 0 || nbatch > kSpanMaxBatches) return fail(BSQ_ERR_ARG, "bad batch count");
     std::lock_guard<std::mutex> dev_lock(g_dev_mu);
     DevInfo &di = dev_info(device);
     const int sms = di.sms > 0 ? di.sms : 148;
-    const int64_t total = nseq * padlen;
-    const int64_t V = (total + 15) / 16;
+    int64_t V = 0, max_nseq = 0;  // 16-byte output vectors of all batches
+    for (int k = 0; k < nbatch; ++k) {
+        V += (nseqs[k] * padlen + 15) / 16;
+        max_nseq = std::max(max_nseq, nseqs[k]);
+    }
+    if (V == 0) return BSQ_OK;
     // stage: slack + span (<= tile bytes + 32) + tail, plus the row table
     auto smem_for = [&](int vt) {
         const int stage_bytes = (kSpanSlack + vt * 16 + 32 + kSpanTail + 127) / 128 * 128;
-        const int max_rows = static_cast<int>(std::min<int64_t>(vt * 16 / padlen + 3, nseq + 1));
+        const int max_rows = static_cast<int>(std::min<int64_t>(vt * 16 / padlen + 3, max_nseq + 1));
         return static_cast<size_t>(nstage) * (stage_bytes + 16 * ((max_rows + 7) / 8 * 8));
     };
     const size_t static_smem = 256 + sizeof(TailTab) + 16 * nstage * 2 + 1024;
@@ -597,18 +635,27 @@ int launch_tokenize_span(int device, cudaStream_t st, const SeqView &v, int64_t 
     const int64_t rounds = std::max<int64_t>(1, (V + grid_full * vt_max - 1) / (grid_full * vt_max));
     int64_t vt = (V + grid_full * rounds - 1) / (grid_full * rounds);
     vt = std::min<int64_t>(vt_max, (vt + kSpanConsumers - 1) / kSpanConsumers * kSpanConsumers);
-    const int64_t ntiles = (V + vt - 1) / vt;
+    SpanBatches mb = {};
+    int64_t ntiles = 0;
+    int nb = 0;
+    for (int k = 0; k < nbatch; ++k) {
+        if (nseqs[k] <= 0) continue;
+        SpanBatch &b = mb.b[nb++];
+        b.bytes = d_bytes[k];
+        b.offs = d_offs[k];
+        b.out = outs[k];
+        b.nseq = nseqs[k];
+        b.total = nseqs[k] * padlen;
+        b.first_tile = ntiles;
+        ntiles += ((b.total + 15) / 16 + vt - 1) / vt;
+    }
     SpanParams q;
-    q.bytes = v.bytes;
-    q.offs = v.offs;
-    q.out = out;
-    q.nseq = nseq;
-    q.total = total;
     q.ntiles = ntiles;
+    q.nbatch = nb;
     q.padlen = static_cast<int>(padlen);
     q.vt = static_cast<int>(vt);
     q.stage_bytes = (kSpanSlack + static_cast<int>(vt) * 16 + 32 + kSpanTail + 127) / 128 * 128;
-    q.max_rows = (static_cast<int>(std::min<int64_t>(vt * 16 / padlen + 3, nseq + 1)) + 7) / 8 * 8;
+    q.max_rows = (static_cast<int>(std::min<int64_t>(vt * 16 / padlen + 3, max_nseq + 1)) + 7) / 8 * 8;
     span_magic(static_cast<uint32_t>(padlen), &q.div_mul, &q.div_shift);
     const size_t smem = static_cast<size_t>(nstage) * (q.stage_bytes + 16 * q.max_rows);
     const bool aligned = padlen % 16 == 0;
@@ -637,7 +684,7 @@ int launch_tokenize_span(int device, cudaStream_t st, const SeqView &v, int64_t 
             BSQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));                    \
             di.attr_set[NS - 1][AL][PR][MB - 4] = true;                                                                           \
         }                                                                                                                         \
-        BSQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, q, p.lut, p.sp));                                                             \
+        BSQ_CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, q, mb, p.lut, p.sp));                                                         \
     } while (0)
 #define BSQ_SPAN_LAUNCH3(NS, MB)                                                                                                  \
     do {                                                                                                                          \
@@ -660,6 +707,11 @@ int launch_tokenize_span(int device, cudaStream_t st, const SeqView &v, int64_t 
 #undef BSQ_SPAN_LAUNCH
     count_launch();
     return BSQ_OK;
+}
+
+int launch_tokenize_span(int device, cudaStream_t st, const SeqView &v, int64_t nseq, int64_t padlen, const Prepared &p, uint8_t *out,
+                         bool pdl_allowed) {
+    return launch_tokenize_span_many(device, st, 1, &v.bytes, &v.offs, &nseq, padlen, p, &out, pdl_allowed);
 }
 
 }  // namespace bsq

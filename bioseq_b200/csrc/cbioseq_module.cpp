@@ -289,14 +289,15 @@ ArrayArg array_arg(const py::object &obj, const char *what, int itemsize, const 
 // per sequence).
 class FlatFile {
 public:
-    FlatFile(const std::string &path, py::ssize_t maxseqlen, bool pinned) : path_(path) {
-        check(bsq_flatfile_open(&f_, path.c_str(), maxseqlen, pinned ? BSQ_FF_PINNED : BSQ_FF_MMAP));
+    static int mode_of(bool pinned, bool prefault) { return pinned ? BSQ_FF_PINNED : (prefault ? BSQ_FF_MMAP_PREFAULT : BSQ_FF_MMAP); }
+    FlatFile(const std::string &path, py::ssize_t maxseqlen, bool pinned, bool prefault) : path_(path) {
+        check(bsq_flatfile_open(&f_, path.c_str(), maxseqlen, mode_of(pinned, prefault)));
     }
-    FlatFile(const std::string &inpath, const std::string &outpath, bool pinned)
+    FlatFile(const std::string &inpath, const std::string &outpath, bool pinned, bool prefault)
         : path_(outpath.empty() ? inpath + ".ff" : outpath) {
         int64_t n = 0, longest = 0;
         check(bsq_flatfile_make(inpath.c_str(), outpath.c_str(), &n, &longest));
-        check(bsq_flatfile_open(&f_, path_.c_str(), longest, pinned ? BSQ_FF_PINNED : BSQ_FF_MMAP));
+        check(bsq_flatfile_open(&f_, path_.c_str(), longest, mode_of(pinned, prefault)));
     }
     FlatFile(const FlatFile &) = delete;
     FlatFile &operator=(const FlatFile &) = delete;
@@ -909,10 +910,10 @@ PYBIND11_MODULE(cbioseq, m) {
         .def_property_readonly("seq", &FlatFileIterator::sequence);
 
     py::class_<FlatFile>(m, "FlatFile")
-        .def(py::init<std::string, py::ssize_t, bool>(), py::arg("inputfile"), py::arg("maxseqlen") = -1, py::kw_only(),
-             py::arg("pinned") = false)
-        .def(py::init<std::string, std::string, bool>(), py::arg("inputfile"), py::arg("outputfile"), py::kw_only(),
-             py::arg("pinned") = false)
+        .def(py::init<std::string, py::ssize_t, bool, bool>(), py::arg("inputfile"), py::arg("maxseqlen") = -1, py::kw_only(),
+             py::arg("pinned") = false, py::arg("prefault") = false)
+        .def(py::init<std::string, std::string, bool, bool>(), py::arg("inputfile"), py::arg("outputfile"), py::kw_only(),
+             py::arg("pinned") = false, py::arg("prefault") = false)
         .def_property_readonly("path", &FlatFile::path)
         .def("access", &FlatFile::access)
         .def("access", &FlatFile::slice_access)

@@ -131,6 +131,16 @@ int bsq_tokenize(int device, void *stream, const uint8_t *d_bytes, const int64_t
                  int64_t nseq, int64_t padlen, const bsq_tokenizer *tok, int batch_first,
                  int kind, void *d_out);
 
+/* Several batches that share padlen and tokenizer in one launch (batch-first one-byte tokens; other layouts / element
+ * types fall back to one launch per batch): batch k = (d_bytes[k], d_offsets[k], nseq[k]) -> d_out[k].  The reference's
+ * per-step callers tokenise small batches (training/cnnpretrain.py:123-125,145, bioseq/decoders.py:505): a 4096 x 1000
+ * batch is 8 MB of traffic, 1.3 us at the HBM roofline and launch-latency-bound when launched alone; up to 32 of them
+ * share one persistent grid here.  The pointer arrays are host arrays and are not referenced after the return.
+ * (Single launches are also capturable into a CUDA graph: the kernel then uses its static tile order.) */
+int bsq_tokenize_many(int device, void *stream, int nbatch, const uint8_t *const *d_bytes, const int64_t *const *d_offsets,
+                      const int64_t *nseq, int64_t padlen, const bsq_tokenizer *tok, int batch_first, int kind,
+                      void *const *d_out);
+
 /* batch_onehot_encode: d_out is (padlen, nseq, alphabet_size), always sequence-first
  * (src/tokenize.h:323-326); one 1 per position, all-zero rows for invalid or masked-out
  * residues and -- unless padchar -- for the tail (src/tokenize.h:345-368).
@@ -299,6 +309,8 @@ typedef struct bsq_flatfile bsq_flatfile;
 
 #define BSQ_FF_MMAP 0   /* map the file read-only (pageable: staged through the pinned ring)        */
 #define BSQ_FF_PINNED 1 /* read the file into cudaHostAlloc'ed memory once (direct DMA afterwards) */
+#define BSQ_FF_MMAP_PREFAULT 2 /* BSQ_FF_MMAP with the page tables populated at open (MAP_POPULATE): a streamed first
+                                  pass over a page-cache-resident file then runs at copy speed instead of fault speed */
 
 /* FlatFile::make (src/fxstats.cpp:33-64): parse a FASTA/FASTQ file (plain or gzip; kseq.h
  * record rules) and write the flat file.  outpath NULL or "" -> inpath + ".ff".  Returns the

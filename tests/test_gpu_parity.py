@@ -683,3 +683,24 @@ def test_sharded_single_process_entry():
         assert torch.equal(torch.cat([o.to("cuda:0") for o in outs], dim=1), want.t())
     with pytest.raises(ValueError):
         tok.batch_tokenize_sharded(buf, offs, padlen=304, devices=[0, 0])
+
+
+@pytest.mark.parametrize("padlen,batch_first,destchar", [(1024, True, "B"), (1026, True, "B"), (300, True, "B"), (1024, False, "B"), (1024, True, "i")])
+def test_tokenize_many_equals_single_launches(padlen, batch_first, destchar):
+    """bsq_tokenize_many: k small batches, one launch (groups of 32); other layouts / dtypes fall back to one launch each."""
+    tok, orc = capi.tokenizer("PROTEIN", bos=True, eos=True, padchar=True), OracleTokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    kind = capi.kind_of(destchar)
+    rng = np.random.default_rng(padlen)
+    sizes = [int(x) for x in rng.integers(0, 400, size=40)] + [0, 1, 4096]
+    batches, wants = [], []
+    for k, n in enumerate(sizes):
+        buf, offs = gen(1000 + k, n, 0, padlen - 2, MIX)
+        d_b = to_dev(np.concatenate([buf, np.zeros(32, np.uint8)]))
+        d_o = to_dev(offs)
+        out = torch.full((n, padlen) if batch_first else (padlen, n), 77, dtype=TORCH_DT[kind], device="cuda")
+        batches.append((d_b, d_o, n, out))
+        wants.append(orc.batch_tokenize((buf, offs), padlen=padlen, destchar=destchar, batch_first=batch_first))
+    capi.tokenize_many(0, stream(), batches, padlen, tok, batch_first, kind)
+    torch.cuda.synchronize()
+    for (d_b, d_o, n, out), want in zip(batches, wants):
+        assert_same_bits(want, out.cpu().numpy())
