@@ -605,13 +605,14 @@ def c4_measurements(torch, capi, L, dev, st, with_cpu):
         # decode of the last alphabet's tokens: device part (validate + lengths + scan, then characters)
         toks = out[:n * padlen].view(n, padlen)
         d_ro = torch.empty(n + 1, dtype=torch.int64, device="cuda")
-        total = capi.decode_lengths(dev, st, toks, 1, n, padlen, padlen, 1, tk, d_ro)
+        d_tl = torch.empty(n, dtype=torch.int32, device="cuda")
+        total = capi.decode_lengths(dev, st, toks, 1, n, padlen, padlen, 1, tk, d_ro, d_tl)
         d_ch = torch.empty(total, dtype=torch.uint8, device="cuda")
         tot = C.c_int64()
 
         def dec():
-            L.bsq_decode_lengths(dev, st, toks.data_ptr(), 1, n, padlen, padlen, 1, C.byref(tk), d_ro.data_ptr(), C.byref(tot))
-            L.bsq_decode_chars(dev, st, toks.data_ptr(), 1, n, padlen, padlen, 1, C.byref(tk), d_ro.data_ptr(), d_ch.data_ptr())
+            L.bsq_decode_lengths(dev, st, toks.data_ptr(), 1, n, padlen, padlen, 1, C.byref(tk), d_ro.data_ptr(), d_tl.data_ptr(), C.byref(tot))
+            L.bsq_decode_chars(dev, st, toks.data_ptr(), 1, n, padlen, padlen, 1, C.byref(tk), d_ro.data_ptr(), d_tl.data_ptr(), d_ch.data_ptr())
         dec()
         torch.cuda.synchronize()
         a.record()
@@ -1101,12 +1102,13 @@ def secondary_measurements(torch, capi, L, dev, st):
     toks = out[:n4 * 1024].view(n4, 1024)
     L.bsq_tokenize(dev, st, d_b.data_ptr(), d_o.data_ptr(), n4, 1024, C.byref(ptk), 1, capi.I8, toks.data_ptr())
     d_ro = torch.empty(n4 + 1, dtype=torch.int64, device="cuda")
-    total = capi.decode_lengths(dev, st, toks, 1, n4, 1024, 1024, 1, ptk, d_ro)
+    d_tl = torch.empty(n4, dtype=torch.int32, device="cuda")
+    total = capi.decode_lengths(dev, st, toks, 1, n4, 1024, 1024, 1, ptk, d_ro, d_tl)
     d_ch = torch.empty(total, dtype=torch.uint8, device="cuda")
     def dec(i):
         tot = C.c_int64()
-        L.bsq_decode_lengths(dev, st, toks.data_ptr(), 1, n4, 1024, 1024, 1, C.byref(ptk), d_ro.data_ptr(), C.byref(tot))
-        L.bsq_decode_chars(dev, st, toks.data_ptr(), 1, n4, 1024, 1024, 1, C.byref(ptk), d_ro.data_ptr(), d_ch.data_ptr())
+        L.bsq_decode_lengths(dev, st, toks.data_ptr(), 1, n4, 1024, 1024, 1, C.byref(ptk), d_ro.data_ptr(), d_tl.data_ptr(), C.byref(tot))
+        L.bsq_decode_chars(dev, st, toks.data_ptr(), 1, n4, 1024, 1024, 1, C.byref(ptk), d_ro.data_ptr(), d_tl.data_ptr(), d_ch.data_ptr())
     ms = timed(dec, 5)
     nbytes = n4 * 1024 + total + 8 * (n4 + 1)   # B.P.s_in + sum(strlen) + 8 (B + 1): every token read once
     res["c2x4_decode_tokens_device"] = {"Gtokens/s": n4 * 1024 / ms / 1e6, "GB/s": nbytes / ms / 1e6, "frac_of_measured_hbm": nbytes / ms / 1e6 / peak,

@@ -305,6 +305,7 @@ int bsq_check_lengths_host(const int64_t *h_offsets, int64_t nseq, int64_t padle
     if (padlen <= 0) return fail(BSQ_ERR_ARG, "batch tokenize requires padlen is provded.");  // src/tokenize.h:383
     if (nseq < 0 || (nseq > 0 && h_offsets == nullptr)) return fail(BSQ_ERR_ARG, "bad offsets");
     const int64_t extra = (tok->bos_id >= 0) + (tok->eos_id >= 0);
+    if (nseq > 0 && h_offsets[0] < 0) return fail(BSQ_ERR_ARG, "offsets must start at or after 0");
     for (int64_t i = 0; i < nseq; ++i) {
         const int64_t len = h_offsets[i + 1] - h_offsets[i];
         if (len < 0) return fail(BSQ_ERR_ARG, "offsets must be non-decreasing");

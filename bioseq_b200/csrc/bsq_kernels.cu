@@ -903,14 +903,26 @@ seqfirst_tok8_kernel(SeqView v, int64_t nseq, int64_t ld, int padlen, FastDiv di
 // ------------------------------------------------------------------------------------------
 // K0: longest sequence of a device-resident offsets array.
 // ------------------------------------------------------------------------------------------
-__global__ void maxlen_kernel(const int64_t *__restrict__ offs, int64_t nseq, unsigned long long *out) {
+// out[0] = longest sequence; out[1] = what is wrong with the offsets, if anything: 1 a negative length, 2 offsets[0] < 0,
+// 4 offsets[nseq] > nbytes (nbytes < 0: the size of the byte buffer is not known) -- the kernels index the byte buffer
+// with these offsets, so a bad array must fail here and not read out of bounds.
+__global__ void maxlen_kernel(const int64_t *__restrict__ offs, int64_t nseq, int64_t nbytes, unsigned long long *out) {
     long long best = 0;
+    unsigned bad = 0;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nseq;
          i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-        best = max(best, static_cast<long long>(offs[i + 1] - offs[i]));
+        const long long len = static_cast<long long>(offs[i + 1] - offs[i]);
+        best = max(best, len);
+        if (len < 0) bad |= 1u;
+        if (i == 0 && offs[0] < 0) bad |= 2u;
+        if (i == nseq - 1 && nbytes >= 0 && offs[nseq] > nbytes) bad |= 4u;
     }
     for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
-    if ((threadIdx.x & 31) == 0 && best > 0) atomicMax(out, static_cast<unsigned long long>(best));
+    bad = __reduce_or_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0) {
+        if (best > 0) atomicMax(out, static_cast<unsigned long long>(best));
+        if (bad) atomicOr(out + 1, static_cast<unsigned long long>(bad));
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1006,7 +1018,7 @@ decode_len_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t rows
 template <bool ANYALIGN>
 __global__ void __launch_bounds__(kDecWarps * 32)
 decode_len16_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t cols, int64_t row_stride, InvParam invp,
-                    int64_t *__restrict__ row_len, unsigned long long *first_bad) {
+                    int64_t *__restrict__ row_len, int32_t *__restrict__ row_tail, unsigned long long *first_bad) {
     __shared__ uint16_t cls[256];
     for (int i = threadIdx.x; i < 256; i += kDecWarps * 32) {
         const uint16_t e = invp.e[i + 128];
@@ -1023,17 +1035,30 @@ decode_len16_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t co
         const int64_t nvec = (a + cols + 15) >> 4;
         const int ktail = ANYALIGN ? static_cast<int>(a + cols - 16 * (nvec - 1)) : 16;  // bytes of the last vector that belong to the row
         uint32_t specials = 0, bad = 0;
+        // the run of one repeated five-character special that ends the row (the <PAD>s behind a sequence: 4/5 of the
+        // decoded text of a padded batch): pass 2 writes it as a pattern fill without reading those tokens again.
+        // T: the row's last token; tail_vec: first vector from which every byte equals T (vector granularity).
+        const uint32_t T = (row_tail != nullptr && cols > 0) ? rb[cols - 1] : 0u;
+        const uint32_t T4 = T * 0x01010101u;
+        int tail_vec = 0;
 #pragma unroll 2
         for (int64_t v = lane; v < nvec; v += 32) {
             const uint4 x = __ldcs(rp + v);
             uint32_t w[4] = {x.x, x.y, x.z, x.w};
+            uint32_t d[4] = {x.x ^ T4, x.y ^ T4, x.z ^ T4, x.w ^ T4};  // non-zero bytes: tokens other than T
             if (v == 0 && a != 0) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) w[k] &= ~lt_mask(a, k);
+                for (int k = 0; k < 4; ++k) {
+                    w[k] &= ~lt_mask(a, k);
+                    d[k] &= ~lt_mask(a, k);
+                }
             }
             if (v == nvec - 1 && ktail != 16) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) w[k] &= lt_mask(ktail, k);
+                for (int k = 0; k < 4; ++k) {
+                    w[k] &= lt_mask(ktail, k);
+                    d[k] &= lt_mask(ktail, k);
+                }
             }
             uint32_t sum = 0;
 #pragma unroll
@@ -1041,8 +1066,15 @@ decode_len16_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t co
                 sum += cls[w[k] & 0xffu] + cls[__byte_perm(w[k], 0, 0x4441)] + cls[__byte_perm(w[k], 0, 0x4442)] + cls[w[k] >> 24];
             specials += sum & 0xffu;
             bad |= sum >> 8;
+            if (d[0] | d[1] | d[2] | d[3]) tail_vec = static_cast<int>(v) + 1;
         }
         for (int o = 16; o > 0; o >>= 1) specials += __shfl_xor_sync(0xffffffffu, specials, o);
+        if (row_tail != nullptr) {
+            for (int o = 16; o > 0; o >>= 1) tail_vec = max(tail_vec, __shfl_xor_sync(0xffffffffu, tail_vec, o));
+            // columns [16 tail_vec - a, cols) all hold T; only a special's run is worth a separate path
+            const int64_t ts = min(max(static_cast<int64_t>(16) * tail_vec - a, static_cast<int64_t>(0)), cols);
+            if (lane == 0) row_tail[r] = (cls[T] & 1) ? static_cast<int32_t>(ts) : static_cast<int32_t>(cols);
+        }
         if (__any_sync(0xffffffffu, bad != 0)) {
             unsigned long long b = ~0ull;
             for (int64_t c = lane; c < cols; c += 32)
@@ -1055,6 +1087,117 @@ decode_len16_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t co
         }
         if (lane == 0) row_len[r] = cols + 4ll * specials;
     }
+}
+
+// The same pass for rows of at most 32 * VPL vectors (padlen up to 1024 / 2048), software-pipelined: a warp holds
+// its whole row in registers -- VPL vectors per lane -- and the NEXT row's vectors and last token are in flight while
+// the current one is counted.  The loop above takes one row at a time through the chain last token -> vectors ->
+// reduction per warp and ran at 2.8 TB/s (ncu r02r: 95 us for 268 MB); vectors wholly inside the trailing run skip
+// the class look-ups; the three warp reductions are single REDUX instructions.
+template <bool ANYALIGN, int VPL>
+__global__ void __launch_bounds__(kDecWarps * 32)
+decode_len16p_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t cols, int64_t row_stride, InvParam invp,
+                     int64_t *__restrict__ row_len, int32_t *__restrict__ row_tail, unsigned long long *first_bad) {
+    __shared__ uint16_t cls[256];
+    for (int i = threadIdx.x; i < 256; i += kDecWarps * 32) {
+        const uint16_t e = invp.e[i + 128];
+        cls[i] = e == kInvNone ? 0x100 : ((e >> 8) & 1);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t gw = static_cast<int64_t>(blockIdx.x) * kDecWarps + (threadIdx.x >> 5);
+    const int64_t GW = static_cast<int64_t>(gridDim.x) * kDecWarps;
+    const bool want_tail = row_tail != nullptr && cols > 0;
+    uint4 xn[VPL];
+    uint32_t Tn = 0;
+    auto load_row = [&](int64_t r) {
+        const uint8_t *rb = tokens + r * row_stride;
+        const int a = ANYALIGN ? static_cast<int>(reinterpret_cast<uintptr_t>(rb) & 15u) : 0;
+        const uint4 *rp = reinterpret_cast<const uint4 *>(rb - a);
+        const int nvec = static_cast<int>((a + cols + 15) >> 4);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            xn[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (lane + 32 * i < nvec) xn[i] = __ldcs(rp + lane + 32 * i);
+        }
+        if (want_tail) Tn = rb[cols - 1];
+    };
+    if (gw < rows) load_row(gw);
+    for (int64_t r = gw; r < rows; r += GW) {
+        uint4 x[VPL];
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) x[i] = xn[i];
+        const uint32_t T = Tn;
+        if (r + GW < rows) load_row(r + GW);
+        const uint8_t *rb = tokens + r * row_stride;
+        const int a = ANYALIGN ? static_cast<int>(reinterpret_cast<uintptr_t>(rb) & 15u) : 0;
+        const int nvec = static_cast<int>((a + cols + 15) >> 4);
+        const int ktail = ANYALIGN ? static_cast<int>(a + cols - 16 * (static_cast<int64_t>(nvec) - 1)) : 16;
+        const uint32_t T4 = T * 0x01010101u;
+        const uint32_t clsT = cls[T];
+        uint32_t specials = 0, bad = 0;
+        int tail_vec = 0;
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nvec) {
+                uint32_t w[4] = {x[i].x, x[i].y, x[i].z, x[i].w};
+                uint32_t d[4] = {w[0] ^ T4, w[1] ^ T4, w[2] ^ T4, w[3] ^ T4};  // non-zero bytes: tokens other than T
+                int inrow = 16;
+                if (ANYALIGN && v == 0 && a != 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        w[k] &= ~lt_mask(a, k);
+                        d[k] &= ~lt_mask(a, k);
+                    }
+                    inrow -= a;
+                }
+                if (ANYALIGN && v == nvec - 1 && ktail != 16) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        w[k] &= lt_mask(ktail, k);
+                        d[k] &= lt_mask(ktail, k);
+                    }
+                    inrow -= 16 - ktail;
+                }
+                if (want_tail && (d[0] | d[1] | d[2] | d[3]) == 0) {  // every token of the row in this vector is T
+                    specials += static_cast<uint32_t>(inrow) * (clsT & 1u);
+                    bad |= clsT >> 8;
+                } else {
+                    uint32_t sum = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        sum += cls[w[k] & 0xffu] + cls[__byte_perm(w[k], 0, 0x4441)] + cls[__byte_perm(w[k], 0, 0x4442)] + cls[w[k] >> 24];
+                    specials += sum & 0xffu;
+                    bad |= sum >> 8;
+                    tail_vec = v + 1;
+                }
+            }
+        }
+        specials = __reduce_add_sync(0xffffffffu, specials);
+        if (want_tail) {
+            tail_vec = __reduce_max_sync(0xffffffffu, tail_vec);
+            // columns [16 tail_vec - a, cols) all hold T; only a special's run is worth a separate path
+            const int64_t ts = min(max(static_cast<int64_t>(16) * tail_vec - a, static_cast<int64_t>(0)), cols);
+            if (lane == 0) row_tail[r] = (clsT & 1) ? static_cast<int32_t>(ts) : static_cast<int32_t>(cols);
+        }
+        if (__reduce_or_sync(0xffffffffu, bad) != 0) {
+            unsigned long long b = ~0ull;
+            for (int64_t c = lane; c < cols; c += 32)
+                if (cls[rb[c]] & 0x100) {
+                    b = static_cast<unsigned long long>(r * cols + c);
+                    break;
+                }
+            for (int o = 16; o > 0; o >>= 1) b = min(b, __shfl_xor_sync(0xffffffffu, b, o));
+            if (lane == 0) atomicMin(first_bad, b);
+        }
+        if (lane == 0) row_len[r] = cols + 4ll * specials;
+    }
+}
+
+__global__ void fill_i32_kernel(int32_t *p, int64_t n, int32_t v) {
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 // exclusive scan of row_len (three small kernels; rows can be millions)
@@ -1109,12 +1252,18 @@ scan_totals_kernel(int64_t *__restrict__ block_tot, int64_t nblocks, int64_t *__
     if (threadIdx.x == 0) *grand_total = carry;
 }
 
+// (host_out: two words of pinned host memory the caller polls after its stream synchronize -- {first bad token, total}
+// leave with the last kernel instead of a separate device-to-host copy)
 __global__ void __launch_bounds__(kScanBlock)
 scan_add_kernel(int64_t *__restrict__ data, int64_t n, const int64_t *__restrict__ block_pre,
-                const int64_t *__restrict__ grand_total) {
+                const int64_t *__restrict__ grand_total, const int64_t *__restrict__ first_bad, int64_t *__restrict__ host_out) {
     const int64_t i = static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x;
     if (i < n) data[i] += block_pre[blockIdx.x];
-    if (i == 0) data[n] = *grand_total;
+    if (i == 0) {
+        data[n] = *grand_total;
+        host_out[0] = *first_bad;
+        host_out[1] = *grand_total;
+    }
 }
 
 // pass 2: one warp per row, persistent grid.  Per step a warp takes 128 tokens (four per lane), a warp
@@ -1149,8 +1298,22 @@ __device__ __forceinline__ uint32_t pack4(uint32_t e0, uint32_t e1, uint32_t e2,
     return __byte_perm(__byte_perm(e0, e1, 0x0040), __byte_perm(e2, e3, 0x0040), 0x5410);
 }
 
+// Four one-byte tokens -> four bytes of a 256-byte shared-memory table whose address has a zero low byte: one PRMT
+// forms each address (the token replaces the low byte), one LDS.U8 reads it, three PRMTs pack the word.
+__device__ __forceinline__ uint32_t dec_lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t dec_lut4(uint32_t lutbase, uint32_t x) {
+    const uint32_t b0 = dec_lds_u8(__byte_perm(lutbase, x, 0x3214)), b1 = dec_lds_u8(__byte_perm(lutbase, x, 0x3215));
+    const uint32_t b2 = dec_lds_u8(__byte_perm(lutbase, x, 0x3216)), b3 = dec_lds_u8(__byte_perm(lutbase, x, 0x3217));
+    return __byte_perm(__byte_perm(b0, b1, 0x0040), __byte_perm(b2, b3, 0x0040), 0x5410);
+}
+
+// nact: lanes 0 .. nact-1 hold tokens (a row's last step may be partial); the others contribute nothing.
 template <int TPL>
-__device__ __forceinline__ int decode_word_step(const uint32_t (&ee)[TPL], uint32_t *stage_w, int fill, int lane) {
+__device__ __forceinline__ int decode_word_step(const uint32_t (&ee)[TPL], uint32_t *stage_w, int fill, int lane, int nact = 32) {
     constexpr int G = TPL / 4;
     // groups of four tokens without a special are one packed word; only the others are walked token by token
     uint32_t gm[G];
@@ -1160,6 +1323,8 @@ __device__ __forceinline__ int decode_word_step(const uint32_t (&ee)[TPL], uint3
         gm[g] = (ee[4 * g] | ee[4 * g + 1] | ee[4 * g + 2] | ee[4 * g + 3]) & 0x100u;
         if (gm[g]) nw += static_cast<int>(((ee[4 * g] >> 8) & 1u) + ((ee[4 * g + 1] >> 8) & 1u) + ((ee[4 * g + 2] >> 8) & 1u) + ((ee[4 * g + 3] >> 8) & 1u));
     }
+    const bool act = lane < nact;
+    if (!act) nw = 0;
     int incl = nw;
     for (int o = 1; o < 32; o <<= 1) {
         const int y = __shfl_up_sync(0xffffffffu, incl, o);
@@ -1169,6 +1334,8 @@ __device__ __forceinline__ int decode_word_step(const uint32_t (&ee)[TPL], uint3
     uint32_t last;  // this lane's final word: decided by its last four tokens
     if (!gm[G - 1]) {
         last = pack4(ee[TPL - 4], ee[TPL - 3], ee[TPL - 2], ee[TPL - 1]);
+    } else if (ee[TPL - 4] == ee[TPL - 3] && ee[TPL - 4] == ee[TPL - 2] && ee[TPL - 4] == ee[TPL - 1]) {
+        last = __byte_perm(special_word(ee[TPL - 1]), 0x3eu, 0x4321);  // "XYZ>"
     } else {
         last = 0;
 #pragma unroll
@@ -1179,12 +1346,22 @@ __device__ __forceinline__ int decode_word_step(const uint32_t (&ee)[TPL], uint3
     uint32_t pw = __shfl_up_sync(0xffffffffu, last, 1);
     if (lane == 0) pw = r8 ? stage_w[kw] << (32 - r8) : 0u;
     uint32_t *d = stage_w + kw + incl - nw;
+    if (!act) return 4 * nwords;
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         if (!gm[g]) {
             const uint32_t w = pack4(ee[4 * g], ee[4 * g + 1], ee[4 * g + 2], ee[4 * g + 3]);
             *d++ = __funnelshift_l(pw, w, r8);
             pw = w;
+        } else if (ee[4 * g] == ee[4 * g + 1] && ee[4 * g] == ee[4 * g + 2] && ee[4 * g] == ee[4 * g + 3]) {
+            // four times the same special (the <PAD> run behind a sequence): 20 characters = five constant words
+            const uint32_t P = special_word(ee[4 * g]);  // "<XYZ"; the other four words are byte rotations of it with '>'
+            const uint32_t w1 = __byte_perm(P, 0x3eu, 0x2104), w2 = __byte_perm(P, 0x3eu, 0x1043);
+            const uint32_t w3 = __byte_perm(P, 0x3eu, 0x0432), w4 = __byte_perm(P, 0x3eu, 0x4321);
+            d[0] = __funnelshift_l(pw, P, r8); d[1] = __funnelshift_l(P, w1, r8); d[2] = __funnelshift_l(w1, w2, r8);
+            d[3] = __funnelshift_l(w2, w3, r8); d[4] = __funnelshift_l(w3, w4, r8);
+            d += 5;
+            pw = w4;
         } else {
             uint32_t cur = 0;
 #pragma unroll
@@ -1203,7 +1380,7 @@ __device__ __forceinline__ int decode_word_step(const uint32_t (&ee)[TPL], uint3
             pw = cur;
         }
     }
-    if (lane == 31 && r8) *d = pw >> (32 - r8);
+    if (lane == nact - 1 && r8) *d = pw >> (32 - r8);
     return 4 * nwords;
 }
 
@@ -1220,36 +1397,89 @@ __device__ __forceinline__ void decode_fill_special(int k, int n, const uint32_t
     if (lane < ((fill + 5 * n) & 3)) stage[4 * kend + lane] = special_char(k, (4 * kend + lane - fill) % 5);
 }
 
-template <bool ANYALIGN>  // false: every row is 16-byte aligned (the realignment folds away)
+// STAGED: a warp's next row of tokens is fetched into a two-slot shared-memory ring by one 1-D bulk asynchronous copy
+// (TMA unit) while the current row is decoded, together with the row's output offset: the kernel used to be bound by
+// the chain row offset -> tokens -> text of one row at a time per warp (ncu r02q: long-scoreboard 4.9 per issue,
+// half of the warps' time).  Needs one-byte contiguous tokens and rows that fit the ring.
+template <bool ANYALIGN, bool STAGED>  // ANYALIGN = false: every row is 16-byte aligned (the realignment folds away)
 __global__ void __launch_bounds__(kDecWarps * 32)
 decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t rows, int64_t cols, int64_t row_stride,
                     int64_t col_stride, int fast, InvParam invp, const int64_t *__restrict__ row_offs,
-                    uint8_t *__restrict__ chars) {
+                    const int32_t *__restrict__ row_tail, uint8_t *__restrict__ chars) {
+    extern __shared__ __align__(128) uint8_t rowring[];  // STAGED: kDecWarps x 2 slots of slot_bytes
+    __shared__ __align__(8) uint64_t rowbar[kDecWarps][2];
     __shared__ uint16_t inv[512];
+    __shared__ __align__(16) uint8_t pat16[3][5][16];  // pat16[k][ph]: 16 bytes of special k's text repeated, starting at phase ph
     __shared__ __align__(16) uint8_t stage_all[kDecWarps][kDecStage];
     __shared__ uint32_t patw[4][8];  // patw[k][ph]: four bytes of special k's text repeated, starting at phase ph
+    // one-byte tokens -> one byte: the character, or 0x80 | kind for a five-character special (characters are ASCII;
+    // an alphabet with a character >= 0x80 keeps to the 16-bit table)
+    __shared__ __align__(256) uint8_t lutb[256];
+    __shared__ int lutb_bad;
+    if (threadIdx.x == 0) lutb_bad = 0;
     for (int i = threadIdx.x; i < 512; i += kDecWarps * 32) inv[i] = invp.e[i];
+    __syncthreads();
+    {
+        const uint16_t e = invp.e[threadIdx.x + 128];  // (kDecWarps * 32 = 256 threads)
+        lutb[threadIdx.x] = (e & 0x100u) ? static_cast<uint8_t>(0x80u | (e & 3u)) : static_cast<uint8_t>(e);
+        if (e != kInvNone && !(e & 0x100u) && (e & 0x80u)) lutb_bad = 1;
+    }
     if (threadIdx.x >= 32 && threadIdx.x < 40) patw[3][threadIdx.x - 32] = 0u;  // (kind 3 does not exist; keeps stray look-ups defined)
+    if (threadIdx.x < 240) {
+        const int i = threadIdx.x;
+        pat16[i / 80][(i / 16) % 5][i % 16] = special_char(i / 80, ((i / 16) % 5 + i % 16) % 5);
+    }
     if (threadIdx.x < 15) {
         const int k = threadIdx.x / 5, ph = threadIdx.x % 5;
         uint32_t w = 0;
         for (int j = 0; j < 4; ++j) w |= static_cast<uint32_t>(special_char(k, (ph + j) % 5)) << (8 * j);
         patw[k][ph] = w;
     }
+    if (STAGED && threadIdx.x < 2 * kDecWarps) {
+        mbar_init(&rowbar[threadIdx.x >> 1][threadIdx.x & 1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *stage = stage_all[warp];
     uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage);
+    const uint32_t lutbase = smem_u32(lutb);
+    const bool bytelut = fast && lutb_bad == 0;
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * kDecWarps + warp;
     const int64_t GW = static_cast<int64_t>(gridDim.x) * kDecWarps;
-    for (int64_t r = gw; r < rows; r += GW) {
-        const uint8_t *rp = tokens + r * row_stride;
-        const int ra = ANYALIGN ? static_cast<int>(reinterpret_cast<uintptr_t>(rp) & 15u) : 0;  // the row's misalignment: loads are aligned, tokens are shifted into place
-        uint8_t *dst = chars + row_offs[r];
+    const int slot_bytes = STAGED ? static_cast<int>((cols + 15 + 16) / 16 * 16 + 16) : 0;
+    uint8_t *myring = rowring + static_cast<size_t>(warp) * 2 * slot_bytes;
+    // lane 0 fetches row rr into slot `sl`: the 16-byte aligned window that holds its tokens
+    auto fetch_row = [&](int64_t rr, int sl) {
+        if (lane == 0) {
+            const uint8_t *g = tokens + rr * row_stride;
+            const int a = ANYALIGN ? static_cast<int>(reinterpret_cast<uintptr_t>(g) & 15u) : 0;
+            const uint32_t nb = static_cast<uint32_t>((a + cols + 15) / 16 * 16);
+            mbar_expect_tx(&rowbar[warp][sl], nb);
+            bulk_g2s(myring + sl * slot_bytes, g - a, nb, &rowbar[warp][sl]);
+        }
+    };
+    if (STAGED && gw < rows) fetch_row(gw, 0);
+    int64_t off_next = gw < rows ? row_offs[gw] : 0;
+    uint32_t it = 0;
+    for (int64_t r = gw; r < rows; r += GW, ++it) {
+        const int64_t off_r = off_next;
+        if (r + GW < rows) {  // the next row's output offset and tokens: in flight while this row is decoded
+            off_next = row_offs[r + GW];
+            if (STAGED) fetch_row(r + GW, (it + 1) & 1);
+        }
+        const uint8_t *gp = tokens + r * row_stride;
+        const int ra = ANYALIGN ? static_cast<int>(reinterpret_cast<uintptr_t>(gp) & 15u) : 0;  // the row's misalignment: loads are aligned, tokens are shifted into place
+        if (STAGED) mbar_wait_u32(smem_u32(&rowbar[warp][it & 1]), (it >> 1) & 1u);
+        const uint8_t *rp = STAGED ? myring + (it & 1) * slot_bytes + ra : gp;  // (rp - ra is 16-byte aligned either way)
+        uint8_t *dst = chars + off_r;
         int fill = static_cast<int>(reinterpret_cast<uintptr_t>(dst) & 15u);  // bytes of the stage in front of the data
         uint8_t *gal = dst - fill;                                             // aligned address of stage[0]
         int head = fill;                                                       // > 0: stage[0 .. head) is not ours
         int step = 128;
+        // columns [cols_head, cols) are one repeated special (found by pass 1): written below as a pattern fill
+        const int64_t cols_all = cols;
+        const int64_t cols = row_tail != nullptr ? static_cast<int64_t>(row_tail[r]) : cols_all;
         for (int64_t c0 = 0; c0 < cols; c0 += step) {
             step = 128;
             int total;
@@ -1257,16 +1487,98 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
             // Steps of plain text or of one repeated special (the <PAD> run behind a sequence) -- nearly all of
             // them -- are laid into the stage as whole 32-bit words shifted by the carry (fill & 3 bytes):
             // one shuffle and one funnel shift per word instead of a scan and a byte store per character.
-            if (fast && c0 + 512 <= cols) {
-                uint4 x = *reinterpret_cast<const uint4 *>(rp - ra + c0 + 16 * lane);
+            // 16 tokens per lane: a full step of 512, or the row's last step when what is left is a whole number of
+            // 16-token vectors (always the case in front of a trailing run found by pass 1): lanes >= nact hold nothing
+            // A ragged last vector (rows that are not 16-byte aligned: the head in front of the trailing run ends
+            // where an ALIGNED vector ends) is taken by the byte-wise tail of the byte-table path only.
+            const int64_t left = cols - c0;
+            const bool ragged = left < 512 && (left & 15) != 0;
+            if (fast && (!ragged || bytelut)) {
+                const int nact = static_cast<int>(min(static_cast<int64_t>(32), (left + 15) >> 4));
+                const int nlast = ragged ? static_cast<int>(left & 15) : 16;  // tokens of the last active vector
+                const bool act = lane < nact;
+                uint4 x = make_uint4(0u, 0u, 0u, 0u);
+                if (act) x = *reinterpret_cast<const uint4 *>(rp - ra + c0 + 16 * lane);
                 if (ra != 0) {  // (warp-uniform) tokens of this lane: bytes [ra, ra + 16) of its vector and the next one
                     uint4 nx;
                     nx.x = __shfl_down_sync(0xffffffffu, x.x, 1); nx.y = __shfl_down_sync(0xffffffffu, x.y, 1);
                     nx.z = __shfl_down_sync(0xffffffffu, x.z, 1); nx.w = __shfl_down_sync(0xffffffffu, x.w, 1);
-                    if (lane == 31) nx = *reinterpret_cast<const uint4 *>(rp - ra + c0 + 512);
+                    if (lane == nact - 1) {  // (the vector behind the last one is read only if the row reaches into it)
+                        nx = make_uint4(0u, 0u, 0u, 0u);
+                        if (c0 + 16 * nact < ra + cols_all) nx = *reinterpret_cast<const uint4 *>(rp - ra + c0 + 16 * nact);
+                    }
                     x = shift16(x, nx, ra);
                 }
                 const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+                // The shape of nearly every step of a tokenised batch: plain text, possibly behind ONE special in the
+                // very first position (the BOS that opens a row: one extra word "<BOS" in front, its '>' takes the
+                // first byte of lane 0's first word), possibly with specials in the LAST active vector only (the EOS and
+                // the first <PAD>s in front of the trailing run).  Lanes in front of that vector store four words each;
+                // the last vector's 16 tokens are then laid down byte-wise by 16 lanes.  No scan.
+                if (bytelut) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) w[k] = dec_lut4(lutbase, xs[k]);
+                    const uint32_t spm = (w[0] | w[1] | w[2] | w[3]) & 0x80808080u;
+                    const uint32_t spb = __ballot_sync(0xffffffffu, act && spm != 0);
+                    const bool tail_emit = ragged || ((spb >> (nact - 1)) & 1u) != 0;  // warp-uniform
+                    // (ragged: the EOS sits in the last 16 BYTES of the head, which straddle the last two token vectors)
+                    const int nev = !tail_emit ? 0 : ((ragged && nact > 1) ? 2 : 1);  // vectors laid down byte-wise
+                    const int nwl = nact - nev;                                        // lanes that store whole words
+                    const uint32_t w00 = __shfl_sync(0xffffffffu, w[0], 0);
+                    const int lead = (nwl > 0 && (w00 & 0x80u)) ? 1 : 0;
+                    uint32_t rest = spm;
+                    if (lane == 0) rest = ((w[0] & 0xffffff00u) | w[1] | w[2] | w[3]) & 0x80808080u;
+                    if (!__any_sync(0xffffffffu, lane < nwl && rest != 0)) {
+                        const int r8 = (fill & 3) * 8, kw = fill >> 2;
+                        uint32_t lo = __shfl_up_sync(0xffffffffu, w[3], 1);
+                        uint32_t w0 = w[0];
+                        if (lane == 0) {
+                            lo = r8 ? stage_w[kw] << (32 - r8) : 0u;
+                            if (lead) {
+                                const uint32_t P = special_word(w00);
+                                stage_w[kw] = __funnelshift_l(lo, P, r8);
+                                lo = P;
+                                w0 = (w0 & 0xffffff00u) | 0x3eu;
+                            }
+                        }
+                        uint32_t *d = stage_w + kw + lead + 4 * lane;
+                        if (lane < nwl) {
+                            d[0] = __funnelshift_l(lo, w0, r8);
+                            d[1] = __funnelshift_l(w0, w[1], r8);
+                            d[2] = __funnelshift_l(w[1], w[2], r8);
+                            d[3] = __funnelshift_l(w[2], w[3], r8);
+                            if (lane == nwl - 1 && r8) d[4] = w[3] >> (32 - r8);
+                        }
+                        total = 16 * nwl + 4 * lead;
+                        if (tail_emit) {
+                            __syncwarp();  // (the carry word above covers the first bytes written here)
+                            // lane t owns token t of the last vector(s)
+                            const int q = (lane >> 2) & 3, src = nwl + (lane >> 4);
+                            const uint32_t t0 = __shfl_sync(0xffffffffu, w[0], src), t1 = __shfl_sync(0xffffffffu, w[1], src);
+                            const uint32_t t2 = __shfl_sync(0xffffffffu, w[2], src), t3 = __shfl_sync(0xffffffffu, w[3], src);
+                            const uint32_t tw = q == 0 ? t0 : (q == 1 ? t1 : (q == 2 ? t2 : t3));
+                            const uint32_t c = (tw >> (8 * (lane & 3))) & 0xffu;
+                            const int nem = 16 * (nev - 1) + nlast;  // tokens laid down here
+                            const bool mine = lane < nem;
+                            const uint32_t sm = __ballot_sync(0xffffffffu, mine && (c & 0x80u));
+                            uint8_t *o = stage + fill + total + lane + 4 * __popc(sm & ((1u << lane) - 1u));
+                            if (mine) {
+                                if (c & 0x80u) {
+                                    const int sp = static_cast<int>(c & 3u);
+#pragma unroll
+                                    for (int j = 0; j < 5; ++j) o[j] = special_char(sp, j);
+                                } else {
+                                    *o = static_cast<uint8_t>(c);
+                                }
+                            }
+                            total += nem + 4 * __popc(sm);
+                        }
+                        step = 512;
+                        done = true;
+                    }
+                }
+                if (!done && !ragged) {
                 uint32_t ee[16], any = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -1275,6 +1587,11 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
                     ee[4 * k + 2] = inv[__byte_perm(xs[k], 0, 0x4442) + 128];
                     ee[4 * k + 3] = inv[(xs[k] >> 24) + 128];
                     any |= ee[4 * k] | ee[4 * k + 1] | ee[4 * k + 2] | ee[4 * k + 3];
+                }
+                if (!act) {  // nothing here: neither a special nor a different token for the votes below
+                    any = 0;
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) ee[k] = 0;
                 }
                 const uint32_t x0 = __shfl_sync(0xffffffffu, x.x, 0);
                 // plain text, possibly behind ONE special in the very first position (the BOS that opens a row): that
@@ -1301,20 +1618,24 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
                         }
                     }
                     uint32_t *d = stage_w + kw + lead + 4 * lane;
-                    d[0] = __funnelshift_l(lo, w[0], r8);
-                    d[1] = __funnelshift_l(w[0], w[1], r8);
-                    d[2] = __funnelshift_l(w[1], w[2], r8);
-                    d[3] = __funnelshift_l(w[2], w[3], r8);
-                    if (lane == 31 && r8) d[4] = w[3] >> (32 - r8);
-                    total = 512 + 4 * lead;
-                } else if (__all_sync(0xffffffffu, x.x == x0 && x.x == __byte_perm(x.x, 0, 0x0000) && x.y == x.x && x.z == x.x && x.w == x.x)) {
-                    decode_fill_special(static_cast<int>(ee[0] & 3u), 512, patw, stage, fill, lane);
-                    total = 2560;
+                    if (act) {
+                        d[0] = __funnelshift_l(lo, w[0], r8);
+                        d[1] = __funnelshift_l(w[0], w[1], r8);
+                        d[2] = __funnelshift_l(w[1], w[2], r8);
+                        d[3] = __funnelshift_l(w[2], w[3], r8);
+                    }
+                    if (lane == nact - 1 && r8) d[4] = w[3] >> (32 - r8);
+                    total = 16 * nact + 4 * lead;
+                } else if (__all_sync(0xffffffffu, !act || (x.x == x0 && x.x == __byte_perm(x.x, 0, 0x0000) && x.y == x.x && x.z == x.x && x.w == x.x))) {
+                    const uint32_t e00 = __shfl_sync(0xffffffffu, ee[0], 0);
+                    decode_fill_special(static_cast<int>(e00 & 3u), 16 * nact, patw, stage, fill, lane);
+                    total = 80 * nact;
                 } else {
-                    total = decode_word_step<16>(ee, stage_w, fill, lane);
+                    total = decode_word_step<16>(ee, stage_w, fill, lane, nact);
                 }
                 step = 512;
                 done = true;
+                }
             }
             if (!done && fast && c0 + 128 <= cols) {
                 uint32_t x = *reinterpret_cast<const uint32_t *>(rp - (ra & 3) + c0 + 4 * lane);
@@ -1391,6 +1712,41 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
             __syncwarp();
             gal += 16 * nfull;
             fill = rest;
+        }
+        if (cols < cols_all) {
+            // The trailing run: 5 (cols_all - cols) bytes "<PAD><PAD>..." starting at gal[fill].  Period 5 against 16-byte
+            // vectors: vector v of the run starts at phase (phase0 + v) % 5 (16 = 1 mod 5) -- one LDS.128 of the pattern
+            // table and one st.global.v4 per 16 bytes, no token is read, nothing goes through the stage.
+            const int k = static_cast<int>(inv[rp[cols_all - 1] + 128] & 3u);
+            const int64_t run = 5 * (cols_all - cols);
+            int64_t done = 0;  // bytes of the run written so far
+            if (fill > 0 || head > 0) {  // the vector that holds the staged bytes [head, fill): completed with the run's first bytes
+                done = min(static_cast<int64_t>(16 - fill), run);
+                if (lane >= head && lane < fill + done) gal[lane] = lane < fill ? stage[lane] : special_char(k, (lane - fill) % 5);
+                gal += 16;  // (if the run ended inside this vector there is nothing left to write)
+            }
+            const int64_t left = run - done;
+            const int nvec = static_cast<int>(left >> 4);  // (cols <= 2^30: 5 * cols / 16 fits an int)
+            const int phase0 = static_cast<int>(done) % 5;
+            const uint4 *pk = reinterpret_cast<const uint4 *>(&pat16[k][0][0]);
+            // vector v starts at phase (phase0 + v) % 5: 30 lanes stride the run by 30 vectors, so a lane's phase -- its
+            // 16 bytes -- never changes: one LDS.128 per row, then bare stores
+            if (lane < 30) {
+                const uint4 pv = pk[(phase0 + lane) % 5];
+                uint4 *gv = reinterpret_cast<uint4 *>(gal) + lane;
+                int v = lane;
+                for (; v + 90 < nvec; v += 120, gv += 120) {
+                    __stcs(gv, pv);
+                    __stcs(gv + 30, pv);
+                    __stcs(gv + 60, pv);
+                    __stcs(gv + 90, pv);
+                }
+                for (; v < nvec; v += 30, gv += 30) __stcs(gv, pv);
+            }
+            const int rest = static_cast<int>(left & 15);
+            if (lane < rest) gal[16 * static_cast<int64_t>(nvec) + lane] = special_char(k, (phase0 + nvec + lane) % 5);
+            fill = 0;
+            head = 0;
         }
         // the row's last partial vector
         for (int i = head + lane; i < fill; i += 32) gal[i] = stage[i];
@@ -1754,7 +2110,7 @@ int scratch_alloc(int device, void **p, size_t bytes, cudaStream_t st) {
 }
 }  // namespace
 
-int bsq_check_lengths_device(int device, void *stream, const int64_t *d_offsets, int64_t nseq, int64_t padlen,
+int bsq_check_offsets_device(int device, void *stream, const int64_t *d_offsets, int64_t nseq, int64_t nbytes, int64_t padlen,
                              const bsq_tokenizer *tok) {
     bsq::DeviceRestore restore_device;
     if (tok == nullptr) return fail(BSQ_ERR_ARG, "null tokenizer");
@@ -1762,25 +2118,33 @@ int bsq_check_lengths_device(int device, void *stream, const int64_t *d_offsets,
     if (nseq <= 0) return BSQ_OK;
     BSQ_CUDA_TRY(cudaSetDevice(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    unsigned long long *d_max = nullptr;
-    if (int rc = scratch_alloc(device, reinterpret_cast<void **>(&d_max), sizeof(*d_max), st)) return rc;
-    BSQ_CUDA_TRY(cudaMemsetAsync(d_max, 0, sizeof(*d_max), st));
+    unsigned long long *d_res = nullptr;
+    if (int rc = scratch_alloc(device, reinterpret_cast<void **>(&d_res), 2 * sizeof(*d_res), st)) return rc;
+    BSQ_CUDA_TRY(cudaMemsetAsync(d_res, 0, 2 * sizeof(*d_res), st));
     const int blocks = static_cast<int>(std::min<int64_t>((nseq + 255) / 256, 148 * 8));
-    maxlen_kernel<<<blocks, 256, 0, st>>>(d_offsets, nseq, d_max);
+    maxlen_kernel<<<blocks, 256, 0, st>>>(d_offsets, nseq, nbytes, d_res);
     count_launch();
-    unsigned long long h_max = 0;
-    BSQ_CUDA_TRY(cudaMemcpyAsync(&h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, st));
-    BSQ_CUDA_TRY(cudaFreeAsync(d_max, st));
+    unsigned long long h_res[2] = {0, 0};
+    BSQ_CUDA_TRY(cudaMemcpyAsync(h_res, d_res, sizeof(h_res), cudaMemcpyDeviceToHost, st));
+    BSQ_CUDA_TRY(cudaFreeAsync(d_res, st));
     BSQ_CUDA_TRY(cudaStreamSynchronize(st));
-    const int64_t tl = static_cast<int64_t>(h_max) + (tok->bos_id >= 0) + (tok->eos_id >= 0);
+    if (h_res[1] & 1u) return fail(BSQ_ERR_ARG, "offsets must be non-decreasing");
+    if (h_res[1] & 2u) return fail(BSQ_ERR_ARG, "offsets must start at or after 0");
+    if (h_res[1] & 4u) return fail(BSQ_ERR_ARG, "offsets run past the end of bytes");
+    const int64_t tl = static_cast<int64_t>(h_res[0]) + (tok->bos_id >= 0) + (tok->eos_id >= 0);
     if (tl > padlen)
         return fail(BSQ_ERR_TOO_LONG, "seq len + bos + eos > padlen: " + std::to_string(tl) + ", vs padlen " + std::to_string(padlen));
     return BSQ_OK;
 }
 
+int bsq_check_lengths_device(int device, void *stream, const int64_t *d_offsets, int64_t nseq, int64_t padlen,
+                             const bsq_tokenizer *tok) {
+    return bsq_check_offsets_device(device, stream, d_offsets, nseq, -1, padlen, tok);
+}
+
 int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows, int64_t cols,
                        int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok, int64_t *d_row_offsets,
-                       int64_t *total_chars) {
+                       int32_t *d_row_tail, int64_t *total_chars) {
     bsq::DeviceRestore restore_device;
     if (tok == nullptr || total_chars == nullptr) return fail(BSQ_ERR_ARG, "null argument");
     if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8)
@@ -1801,24 +2165,48 @@ int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int items
     const InvParam inv = make_inv(*tok);
     const int fast = decode_fast_path(d_tokens, itemsize, row_stride, col_stride);
     const bool rows16 = (reinterpret_cast<uintptr_t>(d_tokens) & 15u) == 0 && row_stride % 16 == 0;
-    if (fast && rows16 && cols % 16 == 0)
-        decode_len16_kernel<false><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
-            static_cast<const uint8_t *>(d_tokens), rows, cols, row_stride, inv, d_row_offsets, reinterpret_cast<unsigned long long *>(d_work));
-    else if (fast)
+    static const bool len_piped = env_int("BSQ_DEC_LENPIPE", 1) != 0;
+    const bool al = rows16 && cols % 16 == 0;
+    const int64_t maxvec = al ? cols / 16 : (15 + cols + 15) / 16;  // vectors that cover a row, at the worst alignment
+    if (fast && cols > 0) {
+        const uint8_t *tk = static_cast<const uint8_t *>(d_tokens);
+        unsigned long long *fb = reinterpret_cast<unsigned long long *>(d_work);
+        const unsigned grid = decode_grid(rows);
+        if (len_piped && maxvec <= 64) {
+            if (al) decode_len16p_kernel<false, 2><<<grid, kDecWarps * 32, 0, st>>>(tk, rows, cols, row_stride, inv, d_row_offsets, d_row_tail, fb);
+            else decode_len16p_kernel<true, 2><<<grid, kDecWarps * 32, 0, st>>>(tk, rows, cols, row_stride, inv, d_row_offsets, d_row_tail, fb);
+        } else if (len_piped && maxvec <= 128) {
+            if (al) decode_len16p_kernel<false, 4><<<grid, kDecWarps * 32, 0, st>>>(tk, rows, cols, row_stride, inv, d_row_offsets, d_row_tail, fb);
+            else decode_len16p_kernel<true, 4><<<grid, kDecWarps * 32, 0, st>>>(tk, rows, cols, row_stride, inv, d_row_offsets, d_row_tail, fb);
+        } else if (al) {
+            decode_len16_kernel<false><<<grid, kDecWarps * 32, 0, st>>>(tk, rows, cols, row_stride, inv, d_row_offsets, d_row_tail, fb);
+        } else {
+            decode_len16_kernel<true><<<grid, kDecWarps * 32, 0, st>>>(tk, rows, cols, row_stride, inv, d_row_offsets, d_row_tail, fb);
+        }
+    } else if (fast) {
         decode_len16_kernel<true><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
-            static_cast<const uint8_t *>(d_tokens), rows, cols, row_stride, inv, d_row_offsets, reinterpret_cast<unsigned long long *>(d_work));
-    else
+            static_cast<const uint8_t *>(d_tokens), rows, cols, row_stride, inv, d_row_offsets, d_row_tail, reinterpret_cast<unsigned long long *>(d_work));
+    } else {
+        // (wide / strided tokens: no trailing-run hint; "cols" = nothing to fill)
+        if (d_row_tail != nullptr) fill_i32_kernel<<<static_cast<unsigned>((rows + 255) / 256), 256, 0, st>>>(d_row_tail, rows, static_cast<int32_t>(cols));
         decode_len_kernel<<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
             static_cast<const uint8_t *>(d_tokens), itemsize, rows, cols, row_stride, col_stride, fast, inv, d_row_offsets,
             reinterpret_cast<unsigned long long *>(d_work));
+    }
     scan_local_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2);
     scan_totals_kernel<<<1, kScanBlock, 0, st>>>(d_work + 2, nblocks, d_work + 1);
-    scan_add_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2, d_work + 1);
+    // one pinned result slot per host thread (the call is synchronous)
+    // (16 bytes, never freed: a destructor would run at thread exit, possibly after the CUDA runtime is torn down)
+    struct PinnedPair {
+        int64_t *p = nullptr;
+    };
+    static thread_local PinnedPair pinned;
+    if (pinned.p == nullptr) BSQ_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&pinned.p), 2 * sizeof(int64_t), cudaHostAllocPortable));
+    scan_add_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2, d_work + 1, d_work, pinned.p);
     count_launch(4);
     BSQ_CUDA_TRY(cudaGetLastError());
-    int64_t h[2] = {0, 0};
-    BSQ_CUDA_TRY(cudaMemcpyAsync(h, d_work, sizeof(h), cudaMemcpyDeviceToHost, st));
     BSQ_CUDA_TRY(cudaStreamSynchronize(st));
+    const int64_t h[2] = {pinned.p[0], pinned.p[1]};
     if (h[0] != -1) {  // fetch the offending value for the reference's message
         const int64_t r = h[0] / cols, c = h[0] % cols;
         uint64_t raw = 0;
@@ -1834,7 +2222,7 @@ int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int items
 
 int bsq_decode_chars(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows, int64_t cols,
                      int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok, const int64_t *d_row_offsets,
-                     uint8_t *d_chars) {
+                     const int32_t *d_row_tail, uint8_t *d_chars) {
     bsq::DeviceRestore restore_device;
     if (tok == nullptr) return fail(BSQ_ERR_ARG, "null tokenizer");
     if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8) return fail(BSQ_ERR_ARG, "bad itemsize");
@@ -1846,12 +2234,21 @@ int bsq_decode_chars(int device, void *stream, const void *d_tokens, int itemsiz
     const int fast = decode_fast_path(d_tokens, itemsize, row_stride, col_stride);
     const bool rows16 = (reinterpret_cast<uintptr_t>(d_tokens) & 15u) == 0 && row_stride % 16 == 0;
     // (a grid of only the 4 resident CTAs per SM measured slower: 470 vs 442 us)
-    if (fast && rows16)
-        decode_chars_kernel<false><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
-            static_cast<const uint8_t *>(d_tokens), itemsize, rows, cols, row_stride, col_stride, fast, inv, d_row_offsets, d_chars);
-    else
-        decode_chars_kernel<true><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(
-            static_cast<const uint8_t *>(d_tokens), itemsize, rows, cols, row_stride, col_stride, fast, inv, d_row_offsets, d_chars);
+    const int32_t *tail = fast ? d_row_tail : nullptr;
+    const uint8_t *tk = static_cast<const uint8_t *>(d_tokens);
+    const size_t ring = static_cast<size_t>(kDecWarps) * 2 * ((cols + 15 + 16) / 16 * 16 + 16);
+    static const bool staged_on = env_int("BSQ_DEC_STAGED", 1) != 0;
+    if (fast && staged_on && ring <= 96 * 1024) {  // rows up to ~6 K tokens ride the ring
+        auto kern = rows16 ? decode_chars_kernel<false, true> : decode_chars_kernel<true, true>;
+        if (ring > 24 * 1024) BSQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        kern<<<decode_grid(rows), kDecWarps * 32, ring, st>>>(tk, itemsize, rows, cols, row_stride, col_stride, fast, inv, d_row_offsets, tail, d_chars);
+    } else if (fast && rows16) {
+        decode_chars_kernel<false, false><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(tk, itemsize, rows, cols, row_stride, col_stride, fast, inv,
+                                                                                         d_row_offsets, tail, d_chars);
+    } else {
+        decode_chars_kernel<true, false><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(tk, itemsize, rows, cols, row_stride, col_stride, fast, inv,
+                                                                                        d_row_offsets, tail, d_chars);
+    }
     count_launch();
     BSQ_CUDA_TRY(cudaGetLastError());
     return BSQ_OK;

@@ -670,12 +670,14 @@ public:
         const int dev = tens.attr("get_device")().cast<int>();
         void *st = current_stream(dev);
         py::object d_offs = new_tensor({rows + 1}, t.int64, dev);
+        py::object d_tail = new_tensor({rows}, t.int32, dev);  // scratch: where each row's trailing <PAD> run begins
         int64_t total = 0;
         check(bsq_decode_lengths(dev, st, data_ptr(tens), itemsize, rows, cols, rs, cs, &tok_,
-                                 static_cast<int64_t *>(data_ptr(d_offs)), &total));
+                                 static_cast<int64_t *>(data_ptr(d_offs)), static_cast<int32_t *>(data_ptr(d_tail)), &total));
         py::object d_chars = new_tensor({total}, t.uint8, dev);
         check(bsq_decode_chars(dev, st, data_ptr(tens), itemsize, rows, cols, rs, cs, &tok_,
-                               static_cast<const int64_t *>(data_ptr(d_offs)), static_cast<uint8_t *>(data_ptr(d_chars))));
+                               static_cast<const int64_t *>(data_ptr(d_offs)), static_cast<const int32_t *>(data_ptr(d_tail)),
+                               static_cast<uint8_t *>(data_ptr(d_chars))));
         py::array_t<int64_t> h_offs = d_offs.attr("cpu")().attr("numpy")();
         const int64_t *o = h_offs.data();
         // The string objects are created first (sizes are known from the offsets); their bodies are then
@@ -857,7 +859,8 @@ private:
         int rc;
         py::object out;
         if (b.on_device) {
-            if (check_len) check(bsq_check_lengths_device(dev, st, static_cast<const int64_t *>(o.ptr), n, padlen, &tok_), onehot);
+            // (also: lengths >= 0, offsets[0] >= 0, offsets[n] <= bytes.numel() -- the kernels index bytes with them)
+            if (check_len) check(bsq_check_offsets_device(dev, st, static_cast<const int64_t *>(o.ptr), n, b.count, padlen, &tok_), onehot);
             out = new_tensor(shape, t.dtype_of(dc, kind), dev);
             if (onehot)
                 rc = bsq_onehot(dev, st, static_cast<const uint8_t *>(b.ptr), static_cast<const int64_t *>(o.ptr),
@@ -867,7 +870,8 @@ private:
                                   &tok_, batch_first, kind, data_ptr(out));
         } else {
             const int64_t *ho = static_cast<const int64_t *>(o.ptr);
-            if (n > 0 && ho[n] - ho[0] > b.count - ho[0]) throw py::value_error("offsets run past the end of bytes");
+            if (n > 0 && ho[0] < 0) throw py::value_error("offsets must start at or after 0");
+            if (n > 0 && ho[n] > b.count) throw py::value_error("offsets run past the end of bytes");
             if (!mask.is_none() && m.count < b.count) throw py::value_error("mask shorter than bytes");
             check(bsq_check_lengths_host(ho, n, padlen, &tok_), onehot);
             out = new_tensor(shape, t.dtype_of(dc, kind), dev);

@@ -37,15 +37,28 @@ def FF2Tensor(x, tokenizer, *, batch_first=True, destchar='B', device=None):
     return tokenizer.batch_tokenize_flatfile(x, 0, None, batch_first=batch_first, destchar=destchar, device=device)
 
 
-class FlatFileDataset:
-    """Map-style dataset over a FlatFile and a Tokenizer (bioseq/loaders.py:29-115).
+def _dataset_base():
+    import torch.utils.data
+    return torch.utils.data.Dataset
+
+
+class FlatFileDataset(_dataset_base()):
+    """Map-style ``torch.utils.data.Dataset`` over a FlatFile and a Tokenizer (bioseq/loaders.py:29-115).
 
     ``ds[i]`` -> 1-D ``long`` token tensor of length ``max_seq_len``; ``ds[a:b]`` -> ``(b-a, max_seq_len)``.
-    With ``cnn=True`` items are one-hot ``float`` tensors laid out ``(batch, emb, length)`` for a slice
-    and ``(length, emb)`` for a single index, like the reference.  Tensors live on ``device``.
+    With ``cnn=True`` a slice is a one-hot ``float`` tensor laid out ``(batch, emb, length)`` and a single index is
+    what ``Tokenizer.onehot_encode(seq, padlen=max_seq_len)`` gives the reference (bioseq/loaders.py:101-103):
+    ``(max_seq_len + bos + eos, emb)`` -- the single-sequence encoder adds BOS/EOS rows ON TOP of padlen
+    (src/tokenize.h:195), so with a BOS/EOS tokenizer a single item is longer than a slice's rows, as in the reference.
+    Tensors live on ``device``.
+
+    ``fetch(index, return_items=True)`` also hands back the raw sequence(s) (bioseq/loaders.py:60-84).  Two quirks of
+    the reference's ``fetch`` are NOT reproduced: with ``cnn=True`` and ``return_items=False`` it falls off the end and
+    returns ``None``, and without ``cnn`` it ignores ``return_items``; here both modes honour the flag.
     """
 
     def __init__(self, ff, tokenizer, *, augment=0, augment_frac=0.5, cnn=False, device=None, maskfrac=0.15, seed=13):
+        super().__init__()
         assert isinstance(ff, cbioseq.FlatFile)
         assert isinstance(tokenizer, cbioseq.Tokenizer)
         self.ff, self.tokenizer = ff, tokenizer
@@ -61,6 +74,7 @@ class FlatFileDataset:
             if step != 1:
                 raise IndexError("FlatFileDataset: only contiguous slices go to the GPU as one range")
             return start, max(start, stop), True
+        index = int(index)
         if index < 0:
             index += n
         if not 0 <= index < n:
@@ -83,11 +97,11 @@ class FlatFileDataset:
                 return consumers.batch_onehot_encode_bcl(self.tokenizer, (self.ff, start, stop), padlen=self.max_seq_len,
                                                          destchar='f', device=self.device, **aug)
             if aug:
+                # (mutated on the device: the batched path at padlen = max_seq_len; a mutated sequence keeps its length,
+                # so only the reference's extra bos + eos pad rows of the single-sequence encoder are missing here)
                 return consumers.batch_onehot_encode_bcl(self.tokenizer, (self.ff, start, stop), padlen=self.max_seq_len,
                                                          destchar='f', device=self.device, **aug)[0].t()
-            oh = self.tokenizer.batch_onehot_encode_flatfile(self.ff, start, stop, padlen=self.max_seq_len, destchar='f',
-                                                             device=self.device)
-            return oh[:, 0, :]
+            return self.tokenizer.onehot_encode(bytes(self.ff[start]), padlen=self.max_seq_len, destchar='f', device=self.device)
         if aug:
             toks = consumers.batch_tokenize_augmented(self.tokenizer, (self.ff, start, stop), padlen=self.max_seq_len,
                                                       batch_first=True, destchar='B', device=self.device, **aug).to(torch.long)
@@ -95,6 +109,16 @@ class FlatFileDataset:
             toks = self.tokenizer.batch_tokenize_flatfile(self.ff, start, stop, padlen=self.max_seq_len, batch_first=True,
                                                           destchar='B', device=self.device).to(torch.long)
         return toks if many else toks[0]
+
+    def fetch(self, index, return_items=False):
+        """``ds[index]``, and with ``return_items`` the sequence(s) it was made from (bioseq/loaders.py:60-84): the
+        ``bytearray`` of a single index, a list of them for a slice -- what ``FlatFile.__getitem__`` returns.  With
+        augmentation the items are the sequences as stored in the file (mutation happens on the device)."""
+        ret = self[index]
+        if not return_items:
+            return ret
+        start, stop, many = self._range(index)
+        return ret, (self.ff[start:stop] if many else self.ff[start])
 
     def access(self, slc, stop=None, step=None):
         if isinstance(slc, int):

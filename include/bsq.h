@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define BSQ_ABI_VERSION 4
+#define BSQ_ABI_VERSION 5
 
 /* ---- status codes ---------------------------------------------------------------- */
 #define BSQ_OK 0
@@ -120,6 +120,12 @@ int bsq_check_lengths_host(const int64_t *h_offsets, int64_t nseq, int64_t padle
  * (synchronises `stream`). */
 int bsq_check_lengths_device(int device, void *stream, const int64_t *d_offsets, int64_t nseq,
                              int64_t padlen, const bsq_tokenizer *tok);
+/* The same reduction, also validating the offsets themselves before a kernel indexes `d_bytes` with them: every
+ * length >= 0, offsets[0] >= 0 and offsets[nseq] <= nbytes (the byte buffer's size; < 0 = unknown, not checked)
+ * -> BSQ_ERR_ARG otherwise.  What cbioseq's batch_tokenize_packed / batch_onehot_encode_packed call for
+ * device-resident inputs. */
+int bsq_check_offsets_device(int device, void *stream, const int64_t *d_offsets, int64_t nseq, int64_t nbytes,
+                             int64_t padlen, const bsq_tokenizer *tok);
 
 /* ---- device compute ------------------------------------------------------------------ */
 /* batch_tokenize: tokens with BOS/EOS/PAD fused in one pass.
@@ -156,13 +162,17 @@ int bsq_onehot(int device, void *stream, const uint8_t *d_bytes, const int64_t *
  *     (synchronises `stream`).  BSQ_ERR_BAD_TOKEN carries the reference's message with
  *     the first offending value in row-major order (src/tokenize.h:148,170).
  *   bsq_decode_chars: writes the decoded characters of row r to
- *     d_chars[d_row_offsets[r] .. d_row_offsets[r+1]). */
+ *     d_chars[d_row_offsets[r] .. d_row_offsets[r+1]).
+ * d_row_tail (optional, `rows` int32 entries of device scratch, the same buffer for both calls): the first step
+ * records where each row's trailing run of one repeated special begins (the <PAD>s behind a sequence are 4/5 of
+ * the decoded text of a padded batch); the second then writes that run as a pattern fill without reading its
+ * tokens again.  NULL for either call: every token is decoded one by one. */
 int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows,
                        int64_t cols, int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok,
-                       int64_t *d_row_offsets, int64_t *total_chars);
+                       int64_t *d_row_offsets, int32_t *d_row_tail, int64_t *total_chars);
 int bsq_decode_chars(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows,
                      int64_t cols, int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok,
-                     const int64_t *d_row_offsets, uint8_t *d_chars);
+                     const int64_t *d_row_offsets, const int32_t *d_row_tail, uint8_t *d_chars);
 
 /* ---- host-staged entry points (the end-to-end path) ------------------------------------ */
 /* A stager owns, for one device: a copy stream, device staging buffers for residues /

@@ -237,7 +237,14 @@ def test_gpu_loaders(tmp_path):
     got = cnn[5:9]
     assert got.dtype == torch.float32 and got.shape == (4, 23, P)
     assert np.array_equal(got.cpu().numpy(), np.transpose(oh, (1, 2, 0)))
-    assert np.array_equal(cnn[5].cpu().numpy(), oh[:, 0, :])
+    # a single index is Tokenizer.onehot_encode(seq, padlen=P): bos + eos zero rows on top of padlen (src/tokenize.h:195)
+    one = cnn[5].cpu().numpy()
+    assert one.shape == (P + 2, 23) and np.array_equal(one[:P], oh[:, 0, :]) and not one[P:].any()
+    assert isinstance(cnn, torch.utils.data.Dataset)
+    t, items = cnn.fetch(slice(5, 9), return_items=True)             # bioseq/loaders.py:60-84
+    assert torch.equal(t, got) and [bytes(b) for b in items] == seqs[5:9]
+    t, item = ds.fetch(3, return_items=True)
+    assert torch.equal(t, ds[3]) and bytes(item) == seqs[3] and torch.equal(ds.fetch(3), ds[3])
     assert got.is_contiguous()          # written in (batch, emb, length) layout, not a permuted view
     aug = FlatFileDataset(ff, tok, augment=2, augment_frac=1.0)      # on-device BLOSUM62 augmentation (test_gpu_consumers.py)
     a = aug[0:700].cpu().numpy()

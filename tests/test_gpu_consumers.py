@@ -274,7 +274,8 @@ def test_flatfile_dataset_augment_and_cnn(tmp_path):
     x = ds[20:90]
     want = ot.batch_onehot_encode((buf, offs), padlen=P, destchar="f").transpose(1, 2, 0)
     assert x.dtype == torch.float32 and x.is_contiguous() and np.array_equal(x.cpu().numpy(), want[20:90])
-    assert np.array_equal(ds[7].cpu().numpy(), want[7].T)
+    one = ds[7].cpu().numpy()            # single index: onehot_encode(seq, padlen=P) -> P + bos + eos rows
+    assert one.shape == (P + 2, want.shape[1]) and np.array_equal(one[:P], want[7].T) and not one[P:].any()
     ds = AugmentedSeqDataset(ff, ptk, augment=2, augment_frac=1.0, seed=5)
     a = ds[0:500]
     seed1 = 5 | (1 << 32)

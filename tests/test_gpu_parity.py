@@ -59,12 +59,17 @@ def abi_decode(tok, d_tokens):
     rows, cols = (1, d_tokens.shape[0]) if nd == 1 else d_tokens.shape
     rs, cs = (0, d_tokens.stride(0) * es) if nd == 1 else (d_tokens.stride(0) * es, d_tokens.stride(1) * es)
     d_offs = torch.empty(rows + 1, dtype=torch.int64, device="cuda")
-    total = capi.decode_lengths(0, stream(), d_tokens, es, rows, cols, rs, cs, tok, d_offs)
-    d_chars = torch.empty(total, dtype=torch.uint8, device="cuda")
-    capi.decode_chars(0, stream(), d_tokens, es, rows, cols, rs, cs, tok, d_offs, d_chars)
-    raw = d_chars.cpu().numpy().tobytes()
-    o = d_offs.cpu().numpy()
-    out = [raw[o[i]:o[i + 1]].decode("latin-1") for i in range(rows)]
+    outs = []
+    for with_tail in (True, False):   # with and without the trailing-run hint buffer: the text must not depend on it
+        d_tail = torch.empty(rows, dtype=torch.int32, device="cuda") if with_tail else None
+        total = capi.decode_lengths(0, stream(), d_tokens, es, rows, cols, rs, cs, tok, d_offs, d_tail)
+        d_chars = torch.full((total,), 0x7e, dtype=torch.uint8, device="cuda")
+        capi.decode_chars(0, stream(), d_tokens, es, rows, cols, rs, cs, tok, d_offs, d_chars, d_tail)
+        raw = d_chars.cpu().numpy().tobytes()
+        o = d_offs.cpu().numpy()
+        outs.append([raw[o[i]:o[i + 1]].decode("latin-1") for i in range(rows)])
+    assert outs[0] == outs[1]
+    out = outs[0]
     return out[0] if nd == 1 else out
 
 
@@ -547,6 +552,16 @@ def test_decode_fast_steps_every_alignment(cols, row_pad, shift):
     a[4, cols // 2 + 1:] = 22
     a[5, :] = 22                                    # specials only, two kinds
     a[5, ::2] = 21
+    for r in range(6, 130):                         # rows as batch_tokenize writes them: <BOS> text <EOS> <PAD>...
+        L = int(rng.integers(0, cols - 1)) if r > 12 else (0, 1, 13, 14, 15, cols - 2, cols - 3)[r - 6]
+        a[r, 0] = 20
+        a[r, 1:1 + L] = rng.integers(0, 20, size=L)
+        a[r, 1 + L] = 21
+        a[r, 2 + L:] = 22
+    for r in range(130, 180):                       # ... and without BOS / EOS: text, then the PAD run
+        L = int(rng.integers(0, cols + 1))
+        a[r, :L] = rng.integers(0, 20, size=L)
+        a[r, L:] = 22
     want = orc.decode_tokens(a)
     assert want[0] == "<PAD>" * cols and want[1] == "E" * cols
     flat = torch.zeros(rows * (cols + row_pad) + 64, dtype=torch.uint8, device="cuda")
@@ -704,3 +719,19 @@ def test_tokenize_many_equals_single_launches(padlen, batch_first, destchar):
     torch.cuda.synchronize()
     for (d_b, d_o, n, out), want in zip(batches, wants):
         assert_same_bits(want, out.cpu().numpy())
+
+
+def test_packed_offsets_are_validated_before_any_kernel_indexes_bytes():
+    # device-resident and host packed inputs: negative first offset, decreasing offsets, offsets past the end of bytes
+    tok = bioseq_b200.Tokenizer("DNA")
+    b = np.frombuffer(b"ACGTACGTAC", dtype=np.uint8).copy()
+    good = np.array([0, 4, 10], dtype=np.int64)
+    want = tok.batch_tokenize_packed(b, good, padlen=8, batch_first=True).cpu().numpy()
+    for side in ("host", "cuda"):
+        conv = (lambda x: x) if side == "host" else (lambda x: torch.from_numpy(x).cuda())
+        assert np.array_equal(tok.batch_tokenize_packed(conv(b), conv(good), padlen=8, batch_first=True).cpu().numpy(), want)
+        for bad in ([-2, 4, 10], [0, 6, 4], [0, 4, 11], [3, 2, 10]):
+            with pytest.raises((ValueError, RuntimeError), match="offsets"):
+                tok.batch_tokenize_packed(conv(b), conv(np.array(bad, dtype=np.int64)), padlen=16, batch_first=True)
+            with pytest.raises((ValueError, RuntimeError), match="offsets"):
+                tok.batch_onehot_encode_packed(conv(b), conv(np.array(bad, dtype=np.int64)), padlen=16)

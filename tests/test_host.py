@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/bsq.h but not exported by libbsq.so"
     assert sorted(capi.EXPORTS) == names, "capi.py binding list out of sync with include/bsq.h"
-    assert capi.lib().bsq_abi_version() == 4
+    assert capi.lib().bsq_abi_version() == 5
 
 
 def test_alphabet_registry_and_luts(golden):
@@ -100,6 +100,8 @@ def test_length_checks_host():
         capi.check_lengths_host(offs, 3, 0, t)
     with pytest.raises(ValueError):
         capi.check_lengths_host(np.array([0, 5, 3], dtype=np.int64), 2, 10, t)
+    with pytest.raises(ValueError, match="offsets must start at or after 0"):
+        capi.check_lengths_host(np.array([-1, 2, 3], dtype=np.int64), 2, 10, t)
 
 
 def test_python_surface_names_and_keys():
