@@ -60,6 +60,7 @@ def lib():
         "bsq_onehot": (i32, [i32, vp, vp, vp, vp, i64, i64, tokp, i32, vp]),
         "bsq_decode_lengths": (i32, [i32, vp, vp, i32, i64, i64, i64, i64, tokp, vp, vp, C.POINTER(i64)]),
         "bsq_decode_chars": (i32, [i32, vp, vp, i32, i64, i64, i64, i64, tokp, vp, vp, vp]),
+        "bsq_decode_text": (i32, [i32, vp, vp, i32, i64, i64, i64, i64, tokp, vp, vp, vp, i64, C.POINTER(i64)]),
         "bsq_stager_create": (i32, [C.POINTER(vp), i32]),
         "bsq_stager_destroy": (None, [vp]),
         "bsq_stager_sync_copies": (i32, [vp]),
@@ -104,7 +105,7 @@ def lib():
 EXPORTS = ("bsq_abi_version bsq_last_error bsq_launch_count bsq_launch_count_reset bsq_kind_of_destchar bsq_kind_size "
            "bsq_alphabet_count bsq_alphabet_key bsq_tokenizer_init bsq_tokenizer_lookup bsq_pack_create bsq_pack_destroy "
            "bsq_pack_gather bsq_pack_bytes bsq_pack_offsets bsq_pack_nseq bsq_pack_nbytes bsq_pack_maxlen "
-           "bsq_check_lengths_host bsq_check_lengths_device bsq_check_offsets_device bsq_tokenize bsq_onehot bsq_decode_lengths bsq_decode_chars "
+           "bsq_check_lengths_host bsq_check_lengths_device bsq_check_offsets_device bsq_tokenize bsq_onehot bsq_decode_lengths bsq_decode_chars bsq_decode_text "
            "bsq_stager_create bsq_stager_destroy bsq_stager_sync_copies bsq_tokenize_host bsq_onehot_host "
            "bsq_flatfile_make bsq_flatfile_open bsq_flatfile_close bsq_flatfile_nseqs bsq_flatfile_seq_offset "
            "bsq_flatfile_max_seq_len bsq_flatfile_offsets bsq_flatfile_bytes bsq_flatfile_is_pinned bsq_fastx_lengths "
@@ -211,6 +212,14 @@ def decode_lengths(device, stream, d_tokens, itemsize, rows, cols, row_stride, c
 def decode_chars(device, stream, d_tokens, itemsize, rows, cols, row_stride, col_stride, tok, d_row_offsets, d_chars, d_row_tail=None):
     check(lib().bsq_decode_chars(device, stream, _ptr(d_tokens), itemsize, rows, cols, row_stride, col_stride,
                                  C.byref(tok), _ptr(d_row_offsets), _ptr(d_row_tail), _ptr(d_chars)))
+
+
+def decode_text(device, stream, d_tokens, itemsize, rows, cols, row_stride, col_stride, tok, d_row_offsets, d_row_tail, d_chars, capacity):
+    """Both decode passes in one call; returns the total (> capacity: nothing was written, call decode_chars)."""
+    total = C.c_int64()
+    check(lib().bsq_decode_text(device, stream, _ptr(d_tokens), itemsize, rows, cols, row_stride, col_stride,
+                                C.byref(tok), _ptr(d_row_offsets), _ptr(d_row_tail), _ptr(d_chars), capacity, C.byref(total)))
+    return total.value
 
 
 class Stager:

@@ -1094,10 +1094,16 @@ decode_len16_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t co
 // the current one is counted.  The loop above takes one row at a time through the chain last token -> vectors ->
 // reduction per warp and ran at 2.8 TB/s (ncu r02r: 95 us for 268 MB); vectors wholly inside the trailing run skip
 // the class look-ups; the three warp reductions are single REDUX instructions.
-template <bool ANYALIGN, int VPL>
+// THR: the token ids are laid out [0, a) characters, [a, b) five-character specials, [b, 256) nothing, b <= 128 (every
+// tokenizer of the reference: the specials follow the alphabet) -- the class of four tokens is then two SIMD-in-a-word
+// comparisons ((w | 0x80808080) - a x 0x01010101 has bit 7 of a byte set iff that byte >= a) instead of four table
+// look-ups: 8 instructions per word instead of 16 (ncu r02s: the look-ups were 99 of the kernel's 227 instructions
+// per row, issue-active 79 %).
+template <bool ANYALIGN, int VPL, bool THR>
 __global__ void __launch_bounds__(kDecWarps * 32)
 decode_len16p_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t cols, int64_t row_stride, InvParam invp,
-                     int64_t *__restrict__ row_len, int32_t *__restrict__ row_tail, unsigned long long *first_bad) {
+                     int64_t *__restrict__ row_len, int32_t *__restrict__ row_tail, unsigned long long *first_bad,
+                     uint32_t thr_lo4, uint32_t thr_hi4) {
     __shared__ uint16_t cls[256];
     for (int i = threadIdx.x; i < 256; i += kDecWarps * 32) {
         const uint16_t e = invp.e[i + 128];
@@ -1163,6 +1169,18 @@ decode_len16p_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t c
                 if (want_tail && (d[0] | d[1] | d[2] | d[3]) == 0) {  // every token of the row in this vector is T
                     specials += static_cast<uint32_t>(inrow) * (clsT & 1u);
                     bad |= clsT >> 8;
+                } else if (THR) {
+                    constexpr uint32_t H = 0x80808080u;
+                    uint32_t ge = 0, over = 0;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t wh = w[k] | H;
+                        ge += __popc((wh - thr_lo4) & H);
+                        over |= ((wh - thr_hi4) | w[k]) & H;  // a byte >= b, or >= 128
+                    }
+                    specials += ge;
+                    bad |= over;
+                    tail_vec = v + 1;
                 } else {
                     uint32_t sum = 0;
 #pragma unroll
@@ -1401,11 +1419,18 @@ __device__ __forceinline__ void decode_fill_special(int k, int n, const uint32_t
 // (TMA unit) while the current row is decoded, together with the row's output offset: the kernel used to be bound by
 // the chain row offset -> tokens -> text of one row at a time per warp (ncu r02q: long-scoreboard 4.9 per issue,
 // half of the warps' time).  Needs one-byte contiguous tokens and rows that fit the ring.
+#ifndef BSQ_DEC_MINB
+#define BSQ_DEC_MINB 4
+#endif
 template <bool ANYALIGN, bool STAGED>  // ANYALIGN = false: every row is 16-byte aligned (the realignment folds away)
-__global__ void __launch_bounds__(kDecWarps * 32)
+__global__ void __launch_bounds__(kDecWarps * 32, BSQ_DEC_MINB)
 decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t rows, int64_t cols, int64_t row_stride,
                     int64_t col_stride, int fast, InvParam invp, const int64_t *__restrict__ row_offs,
-                    const int32_t *__restrict__ row_tail, uint8_t *__restrict__ chars) {
+                    const int32_t *__restrict__ row_tail, uint8_t *__restrict__ chars, int64_t capacity,
+                    const unsigned long long *__restrict__ first_bad) {
+    // (bsq_decode_text launches this pass before the host knows pass 1's verdict: a text that does not fit is not
+    // written, and neither is one with a token that has no entry -- its row lengths are not what this pass would write)
+    if (capacity >= 0 && (row_offs[rows] > capacity || *first_bad != ~0ull)) return;
     extern __shared__ __align__(128) uint8_t rowring[];  // STAGED: kDecWarps x 2 slots of slot_bytes
     __shared__ __align__(8) uint64_t rowbar[kDecWarps][2];
     __shared__ uint16_t inv[512];
@@ -1445,6 +1470,7 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
     uint32_t *stage_w = reinterpret_cast<uint32_t *>(stage);
     const uint32_t lutbase = smem_u32(lutb);
     const bool bytelut = fast && lutb_bad == 0;
+    const int lane5 = lane % 5;
     const int64_t gw = static_cast<int64_t>(blockIdx.x) * kDecWarps + warp;
     const int64_t GW = static_cast<int64_t>(gridDim.x) * kDecWarps;
     const int slot_bytes = STAGED ? static_cast<int>((cols + 15 + 16) / 16 * 16 + 16) : 0;
@@ -1718,21 +1744,23 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
             // vectors: vector v of the run starts at phase (phase0 + v) % 5 (16 = 1 mod 5) -- one LDS.128 of the pattern
             // table and one st.global.v4 per 16 bytes, no token is read, nothing goes through the stage.
             const int k = static_cast<int>(inv[rp[cols_all - 1] + 128] & 3u);
-            const int64_t run = 5 * (cols_all - cols);
-            int64_t done = 0;  // bytes of the run written so far
+            const int run = 5 * static_cast<int>(cols_all - cols);  // (cols <= 2^28 on this path)
+            int done = 0;  // bytes of the run written so far
             if (fill > 0 || head > 0) {  // the vector that holds the staged bytes [head, fill): completed with the run's first bytes
-                done = min(static_cast<int64_t>(16 - fill), run);
-                if (lane >= head && lane < fill + done) gal[lane] = lane < fill ? stage[lane] : special_char(k, (lane - fill) % 5);
+                done = min(16 - fill, run);
+                // (pat16[k][0][i] = character i % 5 of the special's text)
+                if (lane >= head && lane < fill + done) gal[lane] = lane < fill ? stage[lane] : pat16[k][0][lane - fill];
                 gal += 16;  // (if the run ended inside this vector there is nothing left to write)
             }
-            const int64_t left = run - done;
-            const int nvec = static_cast<int>(left >> 4);  // (cols <= 2^30: 5 * cols / 16 fits an int)
-            const int phase0 = static_cast<int>(done) % 5;
+            const int left = run - done;
+            const int nvec = left >> 4;
+            const int phase0 = done >= 10 ? done - 10 : (done >= 5 ? done - 5 : done);  // done % 5, done <= 16
             const uint4 *pk = reinterpret_cast<const uint4 *>(&pat16[k][0][0]);
             // vector v starts at phase (phase0 + v) % 5: 30 lanes stride the run by 30 vectors, so a lane's phase -- its
             // 16 bytes -- never changes: one LDS.128 per row, then bare stores
             if (lane < 30) {
-                const uint4 pv = pk[(phase0 + lane) % 5];
+                const int phl = phase0 + lane5;  // lane5 = lane % 5
+                const uint4 pv = pk[phl >= 5 ? phl - 5 : phl];
                 uint4 *gv = reinterpret_cast<uint4 *>(gal) + lane;
                 int v = lane;
                 for (; v + 90 < nvec; v += 120, gv += 120) {
@@ -1743,8 +1771,8 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
                 }
                 for (; v < nvec; v += 30, gv += 30) __stcs(gv, pv);
             }
-            const int rest = static_cast<int>(left & 15);
-            if (lane < rest) gal[16 * static_cast<int64_t>(nvec) + lane] = special_char(k, (phase0 + nvec + lane) % 5);
+            const int rest = left & 15;
+            if (lane < rest) gal[16 * static_cast<int64_t>(nvec) + lane] = pat16[k][(phase0 + nvec) % 5][lane];
             fill = 0;
             head = 0;
         }
@@ -2142,25 +2170,19 @@ int bsq_check_lengths_device(int device, void *stream, const int64_t *d_offsets,
     return bsq_check_offsets_device(device, stream, d_offsets, nseq, -1, padlen, tok);
 }
 
-int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows, int64_t cols,
-                       int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok, int64_t *d_row_offsets,
-                       int32_t *d_row_tail, int64_t *total_chars) {
-    bsq::DeviceRestore restore_device;
-    if (tok == nullptr || total_chars == nullptr) return fail(BSQ_ERR_ARG, "null argument");
-    if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8)
-        return fail(BSQ_ERR_ARG, "Unexpected itemsize: expected 1, 2, 4, or 8. Found " + std::to_string(itemsize));  // src/tokenize.h:123
-    if (rows < 0 || cols < 0 || rows > 0x7fffffffll) return fail(BSQ_ERR_ARG, "bad decode shape");
-    *total_chars = 0;
-    BSQ_CUDA_TRY(cudaSetDevice(device));
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (rows == 0) {
-        BSQ_CUDA_TRY(cudaMemsetAsync(d_row_offsets, 0, sizeof(int64_t), st));
-        return BSQ_OK;
-    }
-    if (d_tokens == nullptr && cols > 0) return fail(BSQ_ERR_ARG, "Empty array cannot yield a decoded string");  // src/tokenize.h:133
+}  // extern "C"
+
+namespace {
+
+// pass 1 + scan, enqueued on `st`: d_row_offsets[0 .. rows] and d_row_tail are final when the stream gets there;
+// {first bad token, total} land in *host_pair (pinned) with the last kernel.  *d_work_out is to be freed by the caller.
+int decode_lengths_enqueue(int device, cudaStream_t st, const void *d_tokens, int itemsize, int64_t rows, int64_t cols,
+                           int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok, int64_t *d_row_offsets,
+                           int32_t *d_row_tail, int64_t **host_pair, int64_t **d_work_out) {
     const int64_t nblocks = (rows + kScanBlock - 1) / kScanBlock;
     int64_t *d_work = nullptr;  // [0] first_bad, [1] grand total, [2..] block totals
     if (int rc = scratch_alloc(device, reinterpret_cast<void **>(&d_work), sizeof(int64_t) * (2 + nblocks), st)) return rc;
+    *d_work_out = d_work;
     BSQ_CUDA_TRY(cudaMemsetAsync(d_work, 0xff, sizeof(int64_t), st));
     const InvParam inv = make_inv(*tok);
     const int fast = decode_fast_path(d_tokens, itemsize, row_stride, col_stride);
@@ -2172,12 +2194,26 @@ int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int items
         const uint8_t *tk = static_cast<const uint8_t *>(d_tokens);
         unsigned long long *fb = reinterpret_cast<unsigned long long *>(d_work);
         const unsigned grid = decode_grid(rows);
+        // ids laid out [0, a) characters, [a, b) specials, [b, 256) nothing with b <= 128: classes by comparison
+        int a = 0, b = 0;
+        while (a < 256 && inv.e[a + 128] != kInvNone && !(inv.e[a + 128] & 0x100u)) ++a;
+        b = a;
+        while (b < 256 && inv.e[b + 128] != kInvNone && (inv.e[b + 128] & 0x100u)) ++b;
+        bool thr = b >= 1 && b <= 128 && env_int("BSQ_DEC_LENTHR", 1) != 0;
+        for (int t = b; t < 256 && thr; ++t) thr = inv.e[t + 128] == kInvNone;
+        const uint32_t lo4 = static_cast<uint32_t>(a) * 0x01010101u, hi4 = static_cast<uint32_t>(b) * 0x01010101u;
+#define BSQ_LEN16P(AL, V)                                                                                                                      \
+    do {                                                                                                                                       \
+        if (thr) decode_len16p_kernel<AL, V, true><<<grid, kDecWarps * 32, 0, st>>>(tk, rows, cols, row_stride, inv, d_row_offsets, d_row_tail, fb, lo4, hi4);  \
+        else decode_len16p_kernel<AL, V, false><<<grid, kDecWarps * 32, 0, st>>>(tk, rows, cols, row_stride, inv, d_row_offsets, d_row_tail, fb, lo4, hi4); \
+    } while (0)
         if (len_piped && maxvec <= 64) {
-            if (al) decode_len16p_kernel<false, 2><<<grid, kDecWarps * 32, 0, st>>>(tk, rows, cols, row_stride, inv, d_row_offsets, d_row_tail, fb);
-            else decode_len16p_kernel<true, 2><<<grid, kDecWarps * 32, 0, st>>>(tk, rows, cols, row_stride, inv, d_row_offsets, d_row_tail, fb);
+            if (al) BSQ_LEN16P(false, 2);
+            else BSQ_LEN16P(true, 2);
         } else if (len_piped && maxvec <= 128) {
-            if (al) decode_len16p_kernel<false, 4><<<grid, kDecWarps * 32, 0, st>>>(tk, rows, cols, row_stride, inv, d_row_offsets, d_row_tail, fb);
-            else decode_len16p_kernel<true, 4><<<grid, kDecWarps * 32, 0, st>>>(tk, rows, cols, row_stride, inv, d_row_offsets, d_row_tail, fb);
+            if (al) BSQ_LEN16P(false, 4);
+            else BSQ_LEN16P(true, 4);
+#undef BSQ_LEN16P
         } else if (al) {
             decode_len16_kernel<false><<<grid, kDecWarps * 32, 0, st>>>(tk, rows, cols, row_stride, inv, d_row_offsets, d_row_tail, fb);
         } else {
@@ -2195,18 +2231,24 @@ int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int items
     }
     scan_local_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2);
     scan_totals_kernel<<<1, kScanBlock, 0, st>>>(d_work + 2, nblocks, d_work + 1);
-    // one pinned result slot per host thread (the call is synchronous)
+    // one pinned result slot per host thread (the calls are synchronous)
     // (16 bytes, never freed: a destructor would run at thread exit, possibly after the CUDA runtime is torn down)
     struct PinnedPair {
         int64_t *p = nullptr;
     };
     static thread_local PinnedPair pinned;
     if (pinned.p == nullptr) BSQ_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&pinned.p), 2 * sizeof(int64_t), cudaHostAllocPortable));
+    *host_pair = pinned.p;
     scan_add_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2, d_work + 1, d_work, pinned.p);
     count_launch(4);
     BSQ_CUDA_TRY(cudaGetLastError());
-    BSQ_CUDA_TRY(cudaStreamSynchronize(st));
-    const int64_t h[2] = {pinned.p[0], pinned.p[1]};
+    return BSQ_OK;
+}
+
+// after the stream synchronize: the reference's error for a token without an entry, or the total
+int decode_lengths_finish(cudaStream_t st, const void *d_tokens, int itemsize, int64_t cols, int64_t row_stride, int64_t col_stride,
+                          const int64_t *host_pair, int64_t *d_work, int64_t *total_chars) {
+    const int64_t h[2] = {host_pair[0], host_pair[1]};
     if (h[0] != -1) {  // fetch the offending value for the reference's message
         const int64_t r = h[0] / cols, c = h[0] % cols;
         uint64_t raw = 0;
@@ -2220,6 +2262,67 @@ int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int items
     return BSQ_OK;
 }
 
+int decode_chars_enqueue(cudaStream_t st, const void *d_tokens, int itemsize, int64_t rows, int64_t cols, int64_t row_stride,
+                         int64_t col_stride, const bsq_tokenizer *tok, const int64_t *d_row_offsets, const int32_t *d_row_tail,
+                         uint8_t *d_chars, int64_t capacity, const unsigned long long *d_first_bad) {
+    const InvParam inv = make_inv(*tok);
+    const int fast = decode_fast_path(d_tokens, itemsize, row_stride, col_stride);
+    const bool rows16 = (reinterpret_cast<uintptr_t>(d_tokens) & 15u) == 0 && row_stride % 16 == 0;
+    // (a grid of only the 4 resident CTAs per SM measured slower: 470 vs 442 us)
+    const int32_t *tail = (fast && cols <= (1 << 28)) ? d_row_tail : nullptr;  // (the run's byte count is an int in the kernel)
+    const uint8_t *tk = static_cast<const uint8_t *>(d_tokens);
+    const size_t ring = static_cast<size_t>(kDecWarps) * 2 * ((cols + 15 + 16) / 16 * 16 + 16);
+    static const bool staged_on = env_int("BSQ_DEC_STAGED", 1) != 0;
+    if (fast && staged_on && ring <= 96 * 1024) {  // rows up to ~6 K tokens ride the ring
+        auto kern = rows16 ? decode_chars_kernel<false, true> : decode_chars_kernel<true, true>;
+        if (ring > 24 * 1024) BSQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        kern<<<decode_grid(rows), kDecWarps * 32, ring, st>>>(tk, itemsize, rows, cols, row_stride, col_stride, fast, inv, d_row_offsets, tail, d_chars, capacity, d_first_bad);
+    } else if (fast && rows16) {
+        decode_chars_kernel<false, false><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(tk, itemsize, rows, cols, row_stride, col_stride, fast, inv,
+                                                                                         d_row_offsets, tail, d_chars, capacity, d_first_bad);
+    } else {
+        decode_chars_kernel<true, false><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(tk, itemsize, rows, cols, row_stride, col_stride, fast, inv,
+                                                                                        d_row_offsets, tail, d_chars, capacity, d_first_bad);
+    }
+    count_launch();
+    BSQ_CUDA_TRY(cudaGetLastError());
+    return BSQ_OK;
+}
+
+int decode_args_check(const bsq_tokenizer *tok, int itemsize, int64_t rows, int64_t cols) {
+    if (tok == nullptr) return fail(BSQ_ERR_ARG, "null argument");
+    if (itemsize != 1 && itemsize != 2 && itemsize != 4 && itemsize != 8)
+        return fail(BSQ_ERR_ARG, "Unexpected itemsize: expected 1, 2, 4, or 8. Found " + std::to_string(itemsize));  // src/tokenize.h:123
+    if (rows < 0 || cols < 0 || rows > 0x7fffffffll) return fail(BSQ_ERR_ARG, "bad decode shape");
+    return BSQ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bsq_decode_lengths(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows, int64_t cols,
+                       int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok, int64_t *d_row_offsets,
+                       int32_t *d_row_tail, int64_t *total_chars) {
+    bsq::DeviceRestore restore_device;
+    if (total_chars == nullptr) return fail(BSQ_ERR_ARG, "null argument");
+    if (int rc = decode_args_check(tok, itemsize, rows, cols)) return rc;
+    *total_chars = 0;
+    BSQ_CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (rows == 0) {
+        BSQ_CUDA_TRY(cudaMemsetAsync(d_row_offsets, 0, sizeof(int64_t), st));
+        return BSQ_OK;
+    }
+    if (d_tokens == nullptr && cols > 0) return fail(BSQ_ERR_ARG, "Empty array cannot yield a decoded string");  // src/tokenize.h:133
+    int64_t *host_pair = nullptr, *d_work = nullptr;
+    if (int rc = decode_lengths_enqueue(device, st, d_tokens, itemsize, rows, cols, row_stride, col_stride, tok, d_row_offsets, d_row_tail,
+                                        &host_pair, &d_work))
+        return rc;
+    BSQ_CUDA_TRY(cudaStreamSynchronize(st));
+    return decode_lengths_finish(st, d_tokens, itemsize, cols, row_stride, col_stride, host_pair, d_work, total_chars);
+}
+
 int bsq_decode_chars(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows, int64_t cols,
                      int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok, const int64_t *d_row_offsets,
                      const int32_t *d_row_tail, uint8_t *d_chars) {
@@ -2229,29 +2332,41 @@ int bsq_decode_chars(int device, void *stream, const void *d_tokens, int itemsiz
     if (rows <= 0 || cols <= 0) return BSQ_OK;
     if (rows > 0x7fffffffll) return fail(BSQ_ERR_ARG, "bad decode shape");
     BSQ_CUDA_TRY(cudaSetDevice(device));
+    return decode_chars_enqueue(static_cast<cudaStream_t>(stream), d_tokens, itemsize, rows, cols, row_stride, col_stride, tok, d_row_offsets,
+                                d_row_tail, d_chars, -1, nullptr);
+}
+
+int bsq_decode_text(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows, int64_t cols, int64_t row_stride,
+                    int64_t col_stride, const bsq_tokenizer *tok, int64_t *d_row_offsets, int32_t *d_row_tail, uint8_t *d_chars,
+                    int64_t capacity, int64_t *total_chars) {
+    bsq::DeviceRestore restore_device;
+    if (total_chars == nullptr || capacity < 0) return fail(BSQ_ERR_ARG, "null argument");
+    if (int rc = decode_args_check(tok, itemsize, rows, cols)) return rc;
+    *total_chars = 0;
+    BSQ_CUDA_TRY(cudaSetDevice(device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const InvParam inv = make_inv(*tok);
-    const int fast = decode_fast_path(d_tokens, itemsize, row_stride, col_stride);
-    const bool rows16 = (reinterpret_cast<uintptr_t>(d_tokens) & 15u) == 0 && row_stride % 16 == 0;
-    // (a grid of only the 4 resident CTAs per SM measured slower: 470 vs 442 us)
-    const int32_t *tail = fast ? d_row_tail : nullptr;
-    const uint8_t *tk = static_cast<const uint8_t *>(d_tokens);
-    const size_t ring = static_cast<size_t>(kDecWarps) * 2 * ((cols + 15 + 16) / 16 * 16 + 16);
-    static const bool staged_on = env_int("BSQ_DEC_STAGED", 1) != 0;
-    if (fast && staged_on && ring <= 96 * 1024) {  // rows up to ~6 K tokens ride the ring
-        auto kern = rows16 ? decode_chars_kernel<false, true> : decode_chars_kernel<true, true>;
-        if (ring > 24 * 1024) BSQ_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        kern<<<decode_grid(rows), kDecWarps * 32, ring, st>>>(tk, itemsize, rows, cols, row_stride, col_stride, fast, inv, d_row_offsets, tail, d_chars);
-    } else if (fast && rows16) {
-        decode_chars_kernel<false, false><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(tk, itemsize, rows, cols, row_stride, col_stride, fast, inv,
-                                                                                         d_row_offsets, tail, d_chars);
-    } else {
-        decode_chars_kernel<true, false><<<decode_grid(rows), kDecWarps * 32, 0, st>>>(tk, itemsize, rows, cols, row_stride, col_stride, fast, inv,
-                                                                                        d_row_offsets, tail, d_chars);
+    if (rows == 0) {
+        BSQ_CUDA_TRY(cudaMemsetAsync(d_row_offsets, 0, sizeof(int64_t), st));
+        return BSQ_OK;
     }
-    count_launch();
-    BSQ_CUDA_TRY(cudaGetLastError());
-    return BSQ_OK;
+    if (d_tokens == nullptr && cols > 0) return fail(BSQ_ERR_ARG, "Empty array cannot yield a decoded string");  // src/tokenize.h:133
+    int64_t *host_pair = nullptr, *d_work = nullptr;
+    if (int rc = decode_lengths_enqueue(device, st, d_tokens, itemsize, rows, cols, row_stride, col_stride, tok, d_row_offsets, d_row_tail,
+                                        &host_pair, &d_work))
+        return rc;
+    // pass 2 follows pass 1 on the stream without a host round trip; it reads the total on the device and writes
+    // nothing when the text does not fit `capacity` (or when a token had no entry: the offsets are then meaningless
+    // but bounded by 5 x tokens, and the call fails below)
+    if (cols > 0 && d_chars != nullptr && capacity > 0) {
+        if (int rc = decode_chars_enqueue(st, d_tokens, itemsize, rows, cols, row_stride, col_stride, tok, d_row_offsets, d_row_tail,
+                                          d_chars, capacity, reinterpret_cast<const unsigned long long *>(d_work))) {
+            cudaStreamSynchronize(st);
+            cudaFreeAsync(d_work, st);
+            return rc;
+        }
+    }
+    BSQ_CUDA_TRY(cudaStreamSynchronize(st));
+    return decode_lengths_finish(st, d_tokens, itemsize, cols, row_stride, col_stride, host_pair, d_work, total_chars);
 }
 
 }  // extern "C"

@@ -672,12 +672,19 @@ public:
         py::object d_offs = new_tensor({rows + 1}, t.int64, dev);
         py::object d_tail = new_tensor({rows}, t.int32, dev);  // scratch: where each row's trailing <PAD> run begins
         int64_t total = 0;
-        check(bsq_decode_lengths(dev, st, data_ptr(tens), itemsize, rows, cols, rs, cs, &tok_,
-                                 static_cast<int64_t *>(data_ptr(d_offs)), static_cast<int32_t *>(data_ptr(d_tail)), &total));
-        py::object d_chars = new_tensor({total}, t.uint8, dev);
-        check(bsq_decode_chars(dev, st, data_ptr(tens), itemsize, rows, cols, rs, cs, &tok_,
-                               static_cast<const int64_t *>(data_ptr(d_offs)), static_cast<const int32_t *>(data_ptr(d_tail)),
-                               static_cast<uint8_t *>(data_ptr(d_chars))));
+        // Both passes behind one another with one synchronisation (bsq_decode_text): the text buffer is sized by a guess
+        // -- 3 characters per token covers batches that are up to half <PAD> (5 each) -- and only a text that does
+        // not fit costs a second, exactly sized pass 2.
+        const int64_t guess = std::max<int64_t>(rows * cols * 3, 4096);
+        py::object d_chars = new_tensor({guess}, t.uint8, dev);
+        check(bsq_decode_text(dev, st, data_ptr(tens), itemsize, rows, cols, rs, cs, &tok_, static_cast<int64_t *>(data_ptr(d_offs)),
+                              static_cast<int32_t *>(data_ptr(d_tail)), static_cast<uint8_t *>(data_ptr(d_chars)), guess, &total));
+        if (total > guess) {
+            d_chars = new_tensor({total}, t.uint8, dev);
+            check(bsq_decode_chars(dev, st, data_ptr(tens), itemsize, rows, cols, rs, cs, &tok_,
+                                   static_cast<const int64_t *>(data_ptr(d_offs)), static_cast<const int32_t *>(data_ptr(d_tail)),
+                                   static_cast<uint8_t *>(data_ptr(d_chars))));
+        }
         py::array_t<int64_t> h_offs = d_offs.attr("cpu")().attr("numpy")();
         const int64_t *o = h_offs.data();
         // The string objects are created first (sizes are known from the offsets); their bodies are then

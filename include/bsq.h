@@ -174,6 +174,16 @@ int bsq_decode_chars(int device, void *stream, const void *d_tokens, int itemsiz
                      int64_t cols, int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok,
                      const int64_t *d_row_offsets, const int32_t *d_row_tail, uint8_t *d_chars);
 
+/* Both passes in ONE call and one host synchronisation (ABI v5): pass 2 is enqueued right behind pass 1 and reads the
+ * total on the device, so the GPU does not idle while the host learns the size and allocates.  The caller provides
+ * `capacity` bytes at d_chars (a guess: 3 bytes per token covers batches that are up to half <PAD>; 5 per token
+ * always suffices).  Returns like bsq_decode_lengths (*total_chars, d_row_offsets, BSQ_ERR_BAD_TOKEN).  If
+ * *total_chars > capacity NOTHING was written to d_chars: allocate *total_chars and call bsq_decode_chars with the
+ * offsets and hint this call produced. */
+int bsq_decode_text(int device, void *stream, const void *d_tokens, int itemsize, int64_t rows, int64_t cols,
+                    int64_t row_stride, int64_t col_stride, const bsq_tokenizer *tok, int64_t *d_row_offsets,
+                    int32_t *d_row_tail, uint8_t *d_chars, int64_t capacity, int64_t *total_chars);
+
 /* ---- host-staged entry points (the end-to-end path) ------------------------------------ */
 /* A stager owns, for one device: a copy stream, device staging buffers for residues /
  * offsets / mask, and a pinned bounce ring for pageable sources.  The *_host calls split

@@ -69,6 +69,23 @@ def abi_decode(tok, d_tokens):
         o = d_offs.cpu().numpy()
         outs.append([raw[o[i]:o[i + 1]].decode("latin-1") for i in range(rows)])
     assert outs[0] == outs[1]
+    # the one-call form (bsq_decode_text): a buffer that is large enough is filled; one that is too small is not
+    # touched and the exactly sized second pass gives the same text
+    d_tail = torch.empty(rows, dtype=torch.int32, device="cuda")
+    cap = 5 * rows * cols + 16
+    d_chars = torch.full((cap,), 0x7e, dtype=torch.uint8, device="cuda")
+    total = capi.decode_text(0, stream(), d_tokens, es, rows, cols, rs, cs, tok, d_offs, d_tail, d_chars, cap)
+    raw = d_chars.cpu().numpy().tobytes()
+    o = d_offs.cpu().numpy()
+    assert total == o[rows] and [raw[o[i]:o[i + 1]].decode("latin-1") for i in range(rows)] == outs[0]
+    assert raw[total:] == b"\x7e" * (cap - total)
+    if total > 1:
+        small = torch.full((total - 1,), 0x7e, dtype=torch.uint8, device="cuda")
+        assert capi.decode_text(0, stream(), d_tokens, es, rows, cols, rs, cs, tok, d_offs, d_tail, small, total - 1) == total
+        assert bool((small == 0x7e).all())
+        exact = torch.empty(total, dtype=torch.uint8, device="cuda")
+        capi.decode_chars(0, stream(), d_tokens, es, rows, cols, rs, cs, tok, d_offs, exact, d_tail)
+        assert exact.cpu().numpy().tobytes() == raw[:total]
     out = outs[0]
     return out[0] if nd == 1 else out
 
@@ -735,3 +752,30 @@ def test_packed_offsets_are_validated_before_any_kernel_indexes_bytes():
                 tok.batch_tokenize_packed(conv(b), conv(np.array(bad, dtype=np.int64)), padlen=16, batch_first=True)
             with pytest.raises((ValueError, RuntimeError), match="offsets"):
                 tok.batch_onehot_encode_packed(conv(b), conv(np.array(bad, dtype=np.int64)), padlen=16)
+
+
+def test_cuda_graph_of_small_batches_replays_bit_exact():
+    # INTEGRATION.md "Small batches": a train of bsq_tokenize calls captured once and replayed (the launches are
+    # capturable; under capture the span kernel uses its static tile order), against the same calls made directly
+    tok = capi.tokenizer("DNA", bos=True, eos=True, padchar=True)
+    st_default = torch.cuda.current_stream().cuda_stream
+    batches = []
+    for i in range(6):
+        buf, offs = gen(900 + i, 512, 0, 998, b"ACGTN")
+        d_b, d_o = torch.from_numpy(buf).cuda(), torch.from_numpy(offs).cuda()
+        direct = torch.empty((512, 1000), dtype=torch.uint8, device="cuda")
+        capi.tokenize(0, st_default, d_b, d_o, 512, 1000, tok, True, 0, direct)
+        batches.append((d_b, d_o, direct, torch.zeros_like(direct)))
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        st = torch.cuda.current_stream().cuda_stream
+        for d_b, d_o, _, out in batches:
+            capi.tokenize(0, st, d_b, d_o, 512, 1000, tok, True, 0, out)
+    for rep in range(3):
+        for b in batches:
+            b[3].zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        for _, _, direct, out in batches:
+            assert torch.equal(direct, out)

@@ -31,7 +31,9 @@ STALL = "smsp__average_warps_issue_stalled_"
 
 def main():
     rep = sys.argv[1]
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    # --print-units base: every value in its base unit (bytes, ns, ...): columns of one report otherwise come out
+    # scaled independently (dram read in Mbyte next to dram write in Gbyte)
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units, data = rows[0], rows[1], rows[2:]
     col = {h: i for i, h in enumerate(hdr)}
@@ -45,11 +47,13 @@ def main():
                      for h, i in col.items() if h.startswith(STALL) and h.endswith("_per_issue_active.ratio")), reverse=True)
         print("warp-stall reasons per issue-active cycle: " + ", ".join(f"{n}={v:.2f}" for v, n in st[:8]))
         try:
-            rd = float(r[col["dram__bytes_read.sum"]].replace(',', '')); wr = float(r[col["dram__bytes_write.sum"]].replace(',', ''))
-            u = units[col["dram__bytes_read.sum"]]
-            print(f"traffic (dram read+write) = {rd + wr:.3f} {u}")
-        except Exception:
-            pass
+            def in_bytes(key):
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}[units[col[key]]]
+                return float(r[col[key]].replace(',', '')) * scale
+            rd, wr = in_bytes("dram__bytes_read.sum"), in_bytes("dram__bytes_write.sum")
+            print(f"traffic (dram read+write) = {(rd + wr) / 1e6:.3f} MB ({rd / 1e6:.3f} MB read + {wr / 1e6:.3f} MB written)")
+        except Exception as e:
+            print(f"traffic: not available ({e})")
 
 
 if __name__ == "__main__":
