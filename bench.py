@@ -173,6 +173,19 @@ def cpu_arm(buf, offs, steps, warmup, budget_s=20.0, opt="O3", nthreads=None):
             "ms_per_step": 1e3 * total / len(times), "best_ms": 1e3 * min(times)}, out
 
 
+def native_so_loaded():
+    """Shared objects of this repository mapped into the process right now (the driver records the same from outside)."""
+    out = set()
+    try:
+        for ln in open("/proc/self/maps"):
+            path = ln.rsplit(None, 1)[-1]
+            if path.startswith(ROOT) and ".so" in os.path.basename(path):
+                out.add(os.path.relpath(path, ROOT))
+    except OSError:
+        pass
+    return sorted(out)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -185,7 +198,7 @@ def run_reference(args):
             "config": bench_config(args.gpus), "note": "CPU arm: one host, all threads; not sharded over GPUs",
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "Gbases/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "native_so_loaded": native_so_loaded()}
     print(json.dumps(line), flush=True)
 
 
@@ -511,7 +524,7 @@ def run_ours(args):
                         frac_list_api=(h2d * e2e_steps * world / (e2e_ms_max * 1e-3) / 1e9) / host_link["h2d_gbs_all_ranks_concurrent"],
                         frac_packed=(h2d * e2e_steps * world / (packed_ms_max * 1e-3) / 1e9) / host_link["h2d_gbs_all_ranks_concurrent"],
                         note="frac = e2e H2D bytes/s over the pinned H2D rate of all ranks copying at once (best of 256 MiB copies and double-buffered 46 MB copies)")},
-            "gpu_launches": int(launches_all),
+            "gpu_launches": int(launches_all), "native_so_loaded": native_so_loaded(),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "kernel": "tokenize_span_kernel (K1s)",
