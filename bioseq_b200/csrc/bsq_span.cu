@@ -112,6 +112,7 @@ struct SpanParams {
     int stage_bytes;  // data area of a stage
     int max_rows;     // row-table entries of a stage
     uint32_t div_mul, div_shift;  // n / padlen = umulhi(n, div_mul) >> div_shift for 0 <= n < 2^31 (span_magic)
+    int straddle;     // != 0: a warp's 32 vectors can lie in two rows (padlen % 512 != 0)
 };
 
 // Shared-memory loads by 32-bit shared address (the addresses are formed once per tile, outside the vector loop).
@@ -159,16 +160,34 @@ __device__ __forceinline__ void span_translate16(const uint4 &v0, const uint4 &v
     }
 }
 template <bool PRE>
-__device__ __forceinline__ void span_window16(uint32_t S, uint32_t lutb, uint32_t t[4]) {
+__device__ __forceinline__ void span_window16(uint32_t S, uint32_t lutb, int straddle, uint32_t t[4]) {
     const uint4 v0 = lds128(S & ~15u), v1 = lds128((S & ~15u) + 16u);
     const uint32_t sh = S << 3;
-    // one whole specialised body per word shift: warp-uniform (no divergence) whenever the warp's vectors lie
-    // in one row, which is the case for every padlen >= 512
-    switch (S & 12u) {
-        case 0: span_translate16<0, PRE>(v0, v1, sh, lutb, t); break;
-        case 4: span_translate16<1, PRE>(v0, v1, sh, lutb, t); break;
-        case 8: span_translate16<2, PRE>(v0, v1, sh, lutb, t); break;
-        default: span_translate16<3, PRE>(v0, v1, sh, lutb, t); break;
+    // One whole specialised body per word shift, entered by a branch that is warp-uniform whenever the warp's 32
+    // vectors lie in one row.  A warp that holds two rows with different shifts (padlen % 512 != 0: most warps at
+    // padlen 656) would run two of the 50-instruction bodies one after the other: such a warp takes a fifth body,
+    // which picks its words with 11 selects instead (padlen 656: 0.755 -> 0.807 of the HBM peak, 652: 0.665 -> 0.691).
+    // Rows of whole 512-byte windows never straddle and skip the vote (it costs 0.4 us of C2's 20.4).
+    const uint32_t q = S & 12u;
+    int uni = 1;
+    if (straddle) __match_all_sync(__activemask(), q, &uni);
+    if (uni) {
+        switch (q) {
+            case 0: span_translate16<0, PRE>(v0, v1, sh, lutb, t); break;
+            case 4: span_translate16<1, PRE>(v0, v1, sh, lutb, t); break;
+            case 8: span_translate16<2, PRE>(v0, v1, sh, lutb, t); break;
+            default: span_translate16<3, PRE>(v0, v1, sh, lutb, t); break;
+        }
+    } else {
+        const bool q2 = (S & 8u) != 0, q1 = (S & 4u) != 0;
+        const uint32_t a0 = q2 ? v0.z : v0.x, a1 = q2 ? v0.w : v0.y, a2 = q2 ? v1.x : v0.z, a3 = q2 ? v1.y : v0.w;
+        const uint32_t a4 = q2 ? v1.z : v1.x, a5 = q2 ? v1.w : v1.y;
+        const uint32_t x[5] = {q1 ? a1 : a0, q1 ? a2 : a1, q1 ? a3 : a2, q1 ? a4 : a3, q1 ? a5 : a4};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t y = __funnelshift_r(x[k], x[k + 1], sh);
+            t[k] = PRE ? y : span_translate4(y, lutb);
+        }
     }
 }
 
@@ -183,6 +202,7 @@ struct SpanRegs {
     uint4 padq;               // the constant pad vector
     int bos, eos, padlen, neg_padlen;
     uint32_t mul, shift;  // multiply-shift division by padlen
+    int straddle;         // a warp's 32 vectors can lie in two rows
 };
 constexpr int kCstWords = 16;
 
@@ -193,7 +213,7 @@ constexpr int kCstWords = 16;
 template <bool PRE>
 __device__ __forceinline__ uint4 span_row_codes(uint32_t srow, int n, int c0, const SpanRegs &g) {
     uint32_t t[4];
-    span_window16<PRE>(srow + static_cast<uint32_t>(c0), g.lutb, t);
+    span_window16<PRE>(srow + static_cast<uint32_t>(c0), g.lutb, g.straddle, t);
     if (c0 == 0) t[0] = __byte_perm(t[0], g.bos_w, g.bos_sel);
     if (c0 + 16 > n) {  // the row's residues end inside this vector: keep n - c0 bytes, then EOS / pad
         const uint32_t a = g.tab_m + 16u * static_cast<uint32_t>(n - c0);
@@ -209,7 +229,7 @@ __device__ __forceinline__ uint4 span_row_codes(uint32_t srow, int n, int c0, co
 template <bool PRE>
 __device__ __forceinline__ uint4 span_row_codes_u(uint32_t srow, int n, int c0, const SpanRegs &g) {
     uint32_t t[4];
-    span_window16<PRE>(srow + static_cast<uint32_t>(c0), g.lutb, t);
+    span_window16<PRE>(srow + static_cast<uint32_t>(c0), g.lutb, g.straddle, t);
     if (c0 <= 0) {  // bytes [0, -c0): pad; byte -c0: BOS when the tokenizer has one
         const uint32_t a = g.tab_m - 16u * static_cast<uint32_t>(c0);
         const uint4 ma = lds128(a), mb = lds128(a + 16u * static_cast<uint32_t>(g.bos));
@@ -266,7 +286,7 @@ tokenize_span_kernel(const SpanParams q, const __grid_constant__ SpanBatches mb,
         cst[0] = static_cast<uint32_t>(q.padlen); cst[1] = q.div_mul; cst[2] = q.div_shift;
         cst[3] = static_cast<uint32_t>(sp.eos); cst[4] = sp.bos ? sp.bos_w : 0u; cst[5] = sp.bos ? 0x3214u : 0x3210u;
         cst[6] = static_cast<uint32_t>(-q.padlen); cst[7] = static_cast<uint32_t>(sp.bos);
-        cst[8] = s_u32(lut); cst[9] = s_u32(&tab.m[0]);
+        cst[8] = s_u32(lut); cst[9] = s_u32(&tab.m[0]); cst[10] = static_cast<uint32_t>(q.straddle);
         cst[12] = cst[13] = cst[14] = cst[15] = sp.pad_w;
     }
     if (threadIdx.x == 128) {
@@ -441,6 +461,7 @@ tokenize_span_kernel(const SpanParams q, const __grid_constant__ SpanBatches mb,
     g.bos = static_cast<int>(lds32(cst_a + 28u));
     g.lutb = lds32(cst_a + 32u);
     g.tab_m = lds32(cst_a + 36u);
+    g.straddle = static_cast<int>(lds32(cst_a + 40u));
     g.padq = lds128(cst_a + 48u);
     const uint32_t dyn_a = s_u32(dyn);
     for (uint32_t it = 0;; ++it) {
@@ -657,6 +678,11 @@ int launch_tokenize_span_many(int device, cudaStream_t st, int nbatch, const uin
     q.stage_bytes = (kSpanSlack + static_cast<int>(vt) * 16 + 32 + kSpanTail + 127) / 128 * 128;
     q.max_rows = (static_cast<int>(std::min<int64_t>(vt * 16 / padlen + 3, max_nseq + 1)) + 7) / 8 * 8;
     span_magic(static_cast<uint32_t>(padlen), &q.div_mul, &q.div_shift);
+    {
+        static int sel_body = span_env("BSQ_SPAN_SEL", 1);
+        if (tune) sel_body = span_env("BSQ_SPAN_SEL", 1);
+        q.straddle = (sel_body != 0 && padlen % 512 != 0) ? 1 : 0;
+    }
     const size_t smem = static_cast<size_t>(nstage) * (q.stage_bytes + 16 * q.max_rows);
     const bool aligned = padlen % 16 == 0;
 
