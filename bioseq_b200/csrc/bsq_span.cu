@@ -198,6 +198,7 @@ __device__ __forceinline__ void span_window16(uint32_t S, uint32_t lutb, int str
 struct SpanRegs {
     uint32_t lutb;   // shared address of the LUT (256-byte aligned)
     uint32_t tab_m;  // shared address of TailTab::m[0]; TailTab::f[k] is 17 * 16 bytes further on
+    uint32_t tab_h;  // shared address of the head table: entry j = j pad codes, then BOS (if any), then zeros
     uint32_t bos_w, bos_sel;  // BOS byte and the PRMT selector that puts it into byte 0 (identity without BOS)
     uint4 padq;               // the constant pad vector
     int bos, eos, padlen, neg_padlen;
@@ -230,13 +231,13 @@ template <bool PRE>
 __device__ __forceinline__ uint4 span_row_codes_u(uint32_t srow, int n, int c0, const SpanRegs &g) {
     uint32_t t[4];
     span_window16<PRE>(srow + static_cast<uint32_t>(c0), g.lutb, g.straddle, t);
-    if (c0 <= 0) {  // bytes [0, -c0): pad; byte -c0: BOS when the tokenizer has one
-        const uint32_t a = g.tab_m - 16u * static_cast<uint32_t>(c0);
-        const uint4 ma = lds128(a), mb = lds128(a + 16u * static_cast<uint32_t>(g.bos));
-        t[0] = (t[0] & ~mb.x) | (g.bos_w & mb.x & ~ma.x) | (g.padq.x & ma.x);
-        t[1] = (t[1] & ~mb.y) | (g.bos_w & mb.y & ~ma.y) | (g.padq.x & ma.y);
-        t[2] = (t[2] & ~mb.z) | (g.bos_w & mb.z & ~ma.z) | (g.padq.x & ma.z);
-        t[3] = (t[3] & ~mb.w) | (g.bos_w & mb.w & ~ma.w) | (g.padq.x & ma.w);
+    if (c0 <= 0) {  // bytes [0, -c0): pad; byte -c0: BOS when the tokenizer has one -- a ready-made vector per -c0
+        const uint32_t j16 = 16u * static_cast<uint32_t>(-c0);
+        const uint4 mb = lds128(g.tab_m + j16 + 16u * static_cast<uint32_t>(g.bos)), hh = lds128(g.tab_h + j16);
+        t[0] = (t[0] & ~mb.x) | hh.x;
+        t[1] = (t[1] & ~mb.y) | hh.y;
+        t[2] = (t[2] & ~mb.z) | hh.z;
+        t[3] = (t[3] & ~mb.w) | hh.w;
     }
     if (c0 + 16 > n) {  // the row's residues end inside this vector: keep n - c0 bytes, then EOS / pad
         const uint32_t a = g.tab_m + 16u * static_cast<uint32_t>(n - c0);
@@ -272,6 +273,7 @@ tokenize_span_kernel(const SpanParams q, const __grid_constant__ SpanBatches mb,
     extern __shared__ __align__(128) uint8_t dyn[];  // NSTAGE x { data[stage_bytes], rows[max_rows] x 16 B }
     __shared__ __align__(256) uint8_t lut[256];
     __shared__ TailTab tab;
+    __shared__ uint4 headtab[16];
     __shared__ __align__(8) uint64_t full[NSTAGE], empty[NSTAGE];
     __shared__ __align__(16) int4 hdr[NSTAGE];           // c_first, nrows, nvec, -
     __shared__ __align__(16) uint32_t cst[kCstWords];    // loop invariants of the consumers (see SpanRegs)
@@ -282,11 +284,21 @@ tokenize_span_kernel(const SpanParams q, const __grid_constant__ SpanBatches mb,
     asm volatile("griddepcontrol.launch_dependents;");
     load_lut(lut, lutp);
     init_tailtab(tab, sp);
+    if (threadIdx.x >= 160 && threadIdx.x < 176) {
+        const int j = static_cast<int>(threadIdx.x) - 160;
+        uint32_t hw[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t mj = lt_mask(j, w), mjb = lt_mask(clamp16(j + sp.bos), w);
+            hw[w] = (sp.pad_w & mj) | (sp.bos_w & mjb & ~mj);
+        }
+        headtab[j] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    }
     if (threadIdx.x == 96) {
         cst[0] = static_cast<uint32_t>(q.padlen); cst[1] = q.div_mul; cst[2] = q.div_shift;
         cst[3] = static_cast<uint32_t>(sp.eos); cst[4] = sp.bos ? sp.bos_w : 0u; cst[5] = sp.bos ? 0x3214u : 0x3210u;
         cst[6] = static_cast<uint32_t>(-q.padlen); cst[7] = static_cast<uint32_t>(sp.bos);
-        cst[8] = s_u32(lut); cst[9] = s_u32(&tab.m[0]); cst[10] = static_cast<uint32_t>(q.straddle);
+        cst[8] = s_u32(lut); cst[9] = s_u32(&tab.m[0]); cst[10] = static_cast<uint32_t>(q.straddle); cst[11] = s_u32(&headtab[0]);
         cst[12] = cst[13] = cst[14] = cst[15] = sp.pad_w;
     }
     if (threadIdx.x == 128) {
@@ -462,6 +474,7 @@ tokenize_span_kernel(const SpanParams q, const __grid_constant__ SpanBatches mb,
     g.lutb = lds32(cst_a + 32u);
     g.tab_m = lds32(cst_a + 36u);
     g.straddle = static_cast<int>(lds32(cst_a + 40u));
+    g.tab_h = lds32(cst_a + 44u);
     g.padq = lds128(cst_a + 48u);
     const uint32_t dyn_a = s_u32(dyn);
     for (uint32_t it = 0;; ++it) {
