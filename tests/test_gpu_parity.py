@@ -779,3 +779,20 @@ def test_cuda_graph_of_small_batches_replays_bit_exact():
         torch.cuda.synchronize()
         for _, _, direct, out in batches:
             assert torch.equal(direct, out)
+
+
+def test_python_decode_text_guess_overflow_falls_back_to_exact_pass():
+    # Tokenizer.decode_tokens sizes its text buffer by a guess (3 characters per token) and runs both passes in one
+    # call; a batch that is nearly all <PAD> (5 characters per token) does not fit: nothing is written, and the
+    # exactly sized second pass must give the same strings
+    t = bioseq_b200.pbeos_tokenizers["PROTEIN"]
+    o = OracleTokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    rows, cols = 300, 777
+    a = np.full((rows, cols), 22, dtype=np.uint8)           # <PAD> everywhere ...
+    a[:, 0] = 20                                            # ... behind <BOS> X <EOS>
+    a[:, 1] = np.arange(rows) % 20
+    a[:, 2] = 21
+    want = o.decode_tokens(a)
+    assert sum(map(len, want)) > 3 * rows * cols
+    assert t.decode_tokens(torch.from_numpy(a).cuda()) == want
+    assert t.decode_tokens(a) == want
