@@ -12,10 +12,15 @@ There is no CPU fallback: importing this package needs the compiled extension
 (``python -m bioseq_b200.build``) and calling a batch method needs a CUDA device.
 """
 import os as _os
+import sys as _sys
 
 try:
     from . import cbioseq
 except ImportError as _e:  # pragma: no cover - exercised only on a broken checkout
+    if "bioseq_b200.build" in getattr(_sys, "orig_argv", ()):
+        # `python -m bioseq_b200.build` on a checkout whose extension is missing or stale: let the build script run
+        _sys.exit(__import__("runpy").run_path(_os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "build.py"),
+                                               run_name="__main__") and 0)
     raise ImportError(
         "bioseq_b200: the compiled extension is missing (%s). Build it with "
         "`python -m bioseq_b200.build`; there is no pure-Python or CPU fallback." % (_e,)) from _e

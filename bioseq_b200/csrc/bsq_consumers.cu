@@ -376,7 +376,7 @@ augment_kernel(uint8_t *__restrict__ bytes, const int64_t *__restrict__ offs, in
 
 int grid_for(int64_t work_items, int per_cta, int ctas_per_sm) {
     const int64_t want = (work_items + per_cta - 1) / per_cta;
-    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, 148ll * ctas_per_sm)));
+    return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(want, static_cast<int64_t>(cur_sms()) * ctas_per_sm)));
 }
 
 void one_pattern(int kind, uint32_t *lo, uint32_t *hi) {
@@ -468,7 +468,7 @@ int bsq_embed(int device, void *stream, const uint8_t *d_bytes, const int64_t *d
     const int used_rows = tok->alphabet_size;
     const size_t table_bytes = static_cast<size_t>(used_rows) * row_bytes;
     const bool in_smem = table_bytes <= (96u << 10);
-    const int grid = static_cast<int>(std::min<int64_t>(ntiles, 148 * (in_smem && table_bytes > (40u << 10) ? 2 : 4)));
+    const int grid = static_cast<int>(std::min<int64_t>(ntiles, static_cast<int64_t>(cur_sms()) * (in_smem && table_bytes > (40u << 10) ? 2 : 4)));
     const uint4 *w = static_cast<const uint4 *>(d_weight);
     uint4 *out = static_cast<uint4 *>(d_out);
 #define BSQ_EMB(SF, TS)                                                                                              \

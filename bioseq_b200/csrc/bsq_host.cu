@@ -354,6 +354,7 @@ struct bsq_stager {
     bool ring_used[kRingSlots] = {};
     int ring_next = 0;
     std::vector<cudaEvent_t> events;  // one per chunk in flight
+    cudaEvent_t grow_ev = nullptr;    // orders a staging buffer's release behind the kernels that still read it
     // device -> host ring of bsq_fetch_rows
     uint8_t *fetch_ring[kRingSlots] = {};
     cudaEvent_t fetch_ev[kRingSlots] = {};
@@ -381,13 +382,24 @@ struct bsq_stager {
 
 namespace {
 
-int dev_reserve(void **p, size_t *cap, size_t want) {
+// Grows a device staging buffer, stream-ordered on the stager's copy stream (cudaFreeAsync / cudaMallocAsync): no
+// device-wide synchronisation, other streams of the device keep running.  The copy stream already waits for the kernels
+// that read the slot's previous contents (slot_begin); `reader`, if given, is a stream with kernels of the CURRENT call
+// that still read the old buffer.
+int dev_reserve(bsq_stager *s, void **p, size_t *cap, size_t want, cudaStream_t reader = nullptr, bool have_reader = false) {
     if (want <= *cap) return BSQ_OK;
-    if (*p != nullptr) BSQ_CUDA_TRY(cudaFree(*p));  // implicit device sync: nothing is still reading it
+    if (*p != nullptr) {
+        if (have_reader) {
+            if (s->grow_ev == nullptr) BSQ_CUDA_TRY(cudaEventCreateWithFlags(&s->grow_ev, cudaEventDisableTiming));
+            BSQ_CUDA_TRY(cudaEventRecord(s->grow_ev, reader));
+            BSQ_CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->grow_ev, 0));
+        }
+        BSQ_CUDA_TRY(cudaFreeAsync(*p, s->copy_stream));
+    }
     *p = nullptr;
     *cap = 0;
     const size_t n = want + want / 4 + 256;
-    BSQ_CUDA_TRY(cudaMalloc(p, n));
+    BSQ_CUDA_TRY(cudaMallocAsync(p, n, s->copy_stream));
     *cap = n;
     return BSQ_OK;
 }
@@ -578,10 +590,10 @@ int slot_begin(bsq_stager *s, int64_t nbytes, int64_t nseq, bool with_mask) {
     s->cur = (s->cur + 1) % kDevSlots;
     DevSlot &d = s->slot[s->cur];
     if (d.busy) BSQ_CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, d.done, 0));  // the kernels that read this slot two calls ago
-    if (int rc = dev_reserve(reinterpret_cast<void **>(&d.d_bytes), &d.cap_bytes, static_cast<size_t>(nbytes) + 32)) return rc;
-    if (int rc = dev_reserve(reinterpret_cast<void **>(&d.d_offs), &d.cap_offs, sizeof(int64_t) * (nseq + 1))) return rc;
+    if (int rc = dev_reserve(s, reinterpret_cast<void **>(&d.d_bytes), &d.cap_bytes, static_cast<size_t>(nbytes) + 32)) return rc;
+    if (int rc = dev_reserve(s, reinterpret_cast<void **>(&d.d_offs), &d.cap_offs, sizeof(int64_t) * (nseq + 1))) return rc;
     if (with_mask)
-        if (int rc = dev_reserve(reinterpret_cast<void **>(&d.d_mask), &d.cap_mask, static_cast<size_t>(nbytes) + 32)) return rc;
+        if (int rc = dev_reserve(s, reinterpret_cast<void **>(&d.d_mask), &d.cap_mask, static_cast<size_t>(nbytes) + 32)) return rc;
     return BSQ_OK;
 }
 
@@ -896,7 +908,8 @@ int items_stream_run(bsq_stager *s, cudaStream_t st, int64_t n, bsq_resolve_fn r
             const int64_t est = static_cast<int64_t>(static_cast<double>(running + total_k) * static_cast<double>(n) / static_cast<double>(seen) * 1.15) + 4096;
             if ((rc = pack_reserve(pack, est, n)) != BSQ_OK) break;  // (offsets keep their buffer: capacity n + 1 already)
             DevSlot &d = s->slot[s->cur];
-            if ((rc = dev_reserve(reinterpret_cast<void **>(&d.d_bytes), &d.cap_bytes, pack->cap_bytes)) != BSQ_OK) break;
+            // (kernels of this call's earlier ranges, on `stream`, may still read the old device buffer)
+            if ((rc = dev_reserve(s, reinterpret_cast<void **>(&d.d_bytes), &d.cap_bytes, pack->cap_bytes, st, true)) != BSQ_OK) break;
         }
         pack->offs[sh.lo(k)] = running;
         running += total_k;
@@ -1065,6 +1078,7 @@ void bsq_stager_destroy(bsq_stager *s) {
         if (s->ring_free[k]) cudaEventDestroy(s->ring_free[k]);
     }
     for (cudaEvent_t e : s->events) cudaEventDestroy(e);
+    if (s->grow_ev) cudaEventDestroy(s->grow_ev);
     for (int k = 0; k < kRingSlots; ++k) {
         if (s->fetch_ring[k]) cudaFreeHost(s->fetch_ring[k]);
         if (s->fetch_ev[k]) cudaEventDestroy(s->fetch_ev[k]);

@@ -1975,7 +1975,7 @@ int launch_sf(cudaStream_t st, const SeqView &v, int64_t nseq, int64_t ld, int64
         if (sizeof(T) == 1 && aligned && ld % 16 == 0 && tok.pad_id < 0x80) {
             if (env_int("BSQ_SF_OLD", 0)) BSQ_SF(kTokFast);
             else if (gx * gy > 0x7fffffffll) return fail(BSQ_ERR_ARG, "batch too large for one launch");
-            else if (env_int("BSQ_SF_TPC", 2) == 2 && gy % 2 == 0 && gx * gy / 2 >= 8ll * 148 * 6)  // enough CTAs left to balance 888 resident slots
+            else if (env_int("BSQ_SF_TPC", 2) == 2 && gy % 2 == 0 && gx * gy / 2 >= 8ll * cur_sms() * 6)  // enough CTAs left to balance the resident slots (6 per SM)
                 seqfirst_tok8_kernel<2><<<static_cast<unsigned>(gx * gy / 2), kThreads, 0, st>>>(
                     v, nseq, ld, pl, make_fastdiv(static_cast<uint32_t>(gy / 2)), p.lut, p.sp, reinterpret_cast<uint8_t *>(o));
             else seqfirst_tok8_kernel<1><<<static_cast<unsigned>(gx * gy), kThreads, 0, st>>>(
@@ -2002,7 +2002,7 @@ int decode_fast_path(const void * /*d_tokens*/, int itemsize, int64_t /*row_stri
     return itemsize == 1 && col_stride == 1;
 }
 unsigned decode_grid(int64_t rows, int ctas_per_sm = 8) {  // persistent: one warp per row, rows dealt round-robin
-    return static_cast<unsigned>(std::min<int64_t>((rows + kDecWarps - 1) / kDecWarps, 148 * ctas_per_sm));
+    return static_cast<unsigned>(std::min<int64_t>((rows + kDecWarps - 1) / kDecWarps, static_cast<int64_t>(cur_sms()) * ctas_per_sm));
 }
 
 InvParam make_inv(const bsq_tokenizer &tok) {
@@ -2149,7 +2149,7 @@ int bsq_check_offsets_device(int device, void *stream, const int64_t *d_offsets,
     unsigned long long *d_res = nullptr;
     if (int rc = scratch_alloc(device, reinterpret_cast<void **>(&d_res), 2 * sizeof(*d_res), st)) return rc;
     BSQ_CUDA_TRY(cudaMemsetAsync(d_res, 0, 2 * sizeof(*d_res), st));
-    const int blocks = static_cast<int>(std::min<int64_t>((nseq + 255) / 256, 148 * 8));
+    const int blocks = static_cast<int>(std::min<int64_t>((nseq + 255) / 256, static_cast<int64_t>(cur_sms()) * 8));
     maxlen_kernel<<<blocks, 256, 0, st>>>(d_offsets, nseq, nbytes, d_res);
     count_launch();
     unsigned long long h_res[2] = {0, 0};

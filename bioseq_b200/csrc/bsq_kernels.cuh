@@ -72,6 +72,12 @@ Prepared prepare(const bsq_tokenizer &tok, int mode);
 
 // K1s (bsq_span.cu): batch-first one-byte tokens, tile-staged and warp-specialised.
 bool span_kernel_applicable(int64_t padlen);
+int sm_count(int device);  // SMs of the device (cached per device)
+inline int cur_sms() {     // ... of the current device (the entry points have made the call's device current)
+    int d = 0;
+    cudaGetDevice(&d);
+    return sm_count(d);
+}
 int launch_tokenize_span(int device, cudaStream_t st, const SeqView &v, int64_t nseq, int64_t padlen, const Prepared &p,
                          uint8_t *out, bool pdl_allowed);
 // A slot of the per-stream tile counters of the dynamic schedulers (bsq_span.cu), or nullptr when none can be used

@@ -614,6 +614,13 @@ void span_magic(uint32_t d, uint32_t *mul, uint32_t *shift) {
     *shift = s - 1;
 }
 
+// SMs of a device (cached): grids are sized from this, never from a constant
+int sm_count(int device) {
+    std::lock_guard<std::mutex> g(g_dev_mu);
+    const int n = dev_info(device).sms;
+    return n > 0 ? n : 148;
+}
+
 unsigned int *tile_counter_slot(int device, cudaStream_t st) {
     std::lock_guard<std::mutex> dev_lock(g_dev_mu);
     return span_counter(dev_info(device), st);
