@@ -2210,6 +2210,9 @@ int decode_lengths_enqueue(int device, cudaStream_t st, const void *d_tokens, in
         if (len_piped && maxvec <= 64) {
             if (al) BSQ_LEN16P(false, 2);
             else BSQ_LEN16P(true, 2);
+        } else if (len_piped && maxvec <= 96) {  // (padlen 1026, rows at any alignment: 66 vectors)
+            if (al) BSQ_LEN16P(false, 3);
+            else BSQ_LEN16P(true, 3);
         } else if (len_piped && maxvec <= 128) {
             if (al) BSQ_LEN16P(false, 4);
             else BSQ_LEN16P(true, 4);
