@@ -1506,7 +1506,131 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
         // columns [cols_head, cols) are one repeated special (found by pass 1): written below as a pattern fill
         const int64_t cols_all = cols;
         const int64_t cols = row_tail != nullptr ? static_cast<int64_t>(row_tail[r]) : cols_all;
-        for (int64_t c0 = 0; c0 < cols; c0 += step) {
+        // One 16-tokens-per-lane step in its byte-table form (tokens [c0, c0 + min(left, 512)) of the row, appended to the
+        // stage at `fill`): false = the step does not have the shape this form handles, nothing was written.
+        auto step16 = [&](int c0, int left, int &total) -> bool {
+            const bool ragged = left < 512 && (left & 15) != 0;
+            const int nact = min(32, (left + 15) >> 4);
+            const int nlast = ragged ? (left & 15) : 16;  // tokens of the last active vector
+            const bool act = lane < nact;
+            uint4 x = make_uint4(0u, 0u, 0u, 0u);
+            if (act) x = *reinterpret_cast<const uint4 *>(rp - ra + c0 + 16 * lane);
+            if (ra != 0) {  // (warp-uniform) tokens of this lane: bytes [ra, ra + 16) of its vector and the next one
+                uint4 nx;
+                nx.x = __shfl_down_sync(0xffffffffu, x.x, 1); nx.y = __shfl_down_sync(0xffffffffu, x.y, 1);
+                nx.z = __shfl_down_sync(0xffffffffu, x.z, 1); nx.w = __shfl_down_sync(0xffffffffu, x.w, 1);
+                if (lane == nact - 1) {  // (the vector behind the last one is read only if the row reaches into it)
+                    nx = make_uint4(0u, 0u, 0u, 0u);
+                    if (c0 + 16 * nact < ra + cols_all) nx = *reinterpret_cast<const uint4 *>(rp - ra + c0 + 16 * nact);
+                }
+                x = shift16(x, nx, ra);
+            }
+            // The shape of nearly every step of a tokenised batch: plain text, possibly behind ONE special in the
+            // very first position (the BOS that opens a row: one extra word "<BOS" in front, its '>' takes the
+            // first byte of lane 0's first word), possibly with specials in the LAST active vector only (the EOS and
+            // the first <PAD>s in front of the trailing run).  Lanes in front of that vector store four words each;
+            // the last vector's 16 tokens are then laid down byte-wise by 16 lanes.  No scan.
+            uint32_t w[4];
+            w[0] = dec_lut4(lutbase, x.x); w[1] = dec_lut4(lutbase, x.y); w[2] = dec_lut4(lutbase, x.z); w[3] = dec_lut4(lutbase, x.w);
+            const uint32_t spm = (w[0] | w[1] | w[2] | w[3]) & 0x80808080u;
+            const uint32_t spb = __ballot_sync(0xffffffffu, act && spm != 0);
+            const bool tail_emit = ragged || ((spb >> (nact - 1)) & 1u) != 0;  // warp-uniform
+            // (ragged: the EOS sits in the last 16 BYTES of the head, which straddle the last two token vectors)
+            const int nev = !tail_emit ? 0 : ((ragged && nact > 1) ? 2 : 1);  // vectors laid down byte-wise
+            const int nwl = nact - nev;                                        // lanes that store whole words
+            const uint32_t w00 = __shfl_sync(0xffffffffu, w[0], 0);
+            const int lead = (nwl > 0 && (w00 & 0x80u)) ? 1 : 0;
+            uint32_t rest = spm;
+            if (lane == 0) rest = ((w[0] & 0xffffff00u) | w[1] | w[2] | w[3]) & 0x80808080u;
+            if (__any_sync(0xffffffffu, lane < nwl && rest != 0)) return false;
+            const int r8 = (fill & 3) * 8, kw = fill >> 2;
+            uint32_t lo = __shfl_up_sync(0xffffffffu, w[3], 1);
+            uint32_t w0 = w[0];
+            if (lane == 0) {
+                lo = r8 ? stage_w[kw] << (32 - r8) : 0u;
+                if (lead) {
+                    const uint32_t P = special_word(w00);
+                    stage_w[kw] = __funnelshift_l(lo, P, r8);
+                    lo = P;
+                    w0 = (w0 & 0xffffff00u) | 0x3eu;
+                }
+            }
+            uint32_t *d = stage_w + kw + lead + 4 * lane;
+            if (lane < nwl) {
+                d[0] = __funnelshift_l(lo, w0, r8);
+                d[1] = __funnelshift_l(w0, w[1], r8);
+                d[2] = __funnelshift_l(w[1], w[2], r8);
+                d[3] = __funnelshift_l(w[2], w[3], r8);
+                if (lane == nwl - 1 && r8) d[4] = w[3] >> (32 - r8);
+            }
+            total = 16 * nwl + 4 * lead;
+            if (tail_emit) {
+                __syncwarp();  // (the carry word above covers the first bytes written here)
+                // lane t owns token t of the last vector(s)
+                const int q = (lane >> 2) & 3, src = nwl + (lane >> 4);
+                const uint32_t t0 = __shfl_sync(0xffffffffu, w[0], src), t1 = __shfl_sync(0xffffffffu, w[1], src);
+                const uint32_t t2 = __shfl_sync(0xffffffffu, w[2], src), t3 = __shfl_sync(0xffffffffu, w[3], src);
+                const uint32_t tw = q == 0 ? t0 : (q == 1 ? t1 : (q == 2 ? t2 : t3));
+                const uint32_t c = (tw >> (8 * (lane & 3))) & 0xffu;
+                const int nem = 16 * (nev - 1) + nlast;  // tokens laid down here
+                const bool mine = lane < nem;
+                const uint32_t sm = __ballot_sync(0xffffffffu, mine && (c & 0x80u));
+                uint8_t *o = stage + fill + total + lane + 4 * __popc(sm & ((1u << lane) - 1u));
+                if (mine) {
+                    if (c & 0x80u) {
+                        const int sp = static_cast<int>(c & 3u);
+#pragma unroll
+                        for (int j = 0; j < 5; ++j) o[j] = special_char(sp, j);
+                    } else {
+                        *o = static_cast<uint8_t>(c);
+                    }
+                }
+                total += nem + 4 * __popc(sm);
+            }
+            return true;
+        };
+        // the stage's whole 16-byte vectors leave for global memory; what is left moves to its front
+        auto flush = [&]() {
+            const int nfull = fill >> 4;
+            int vfirst = lane;
+            if (head > 0 && nfull > 0) {  // first vector of the row: bytes [0, head) belong to the previous row
+                if (lane >= head && lane < 16) gal[lane] = stage[lane];
+                if (lane == 0) vfirst = 32;
+            }
+            {
+                const uint4 *sv = reinterpret_cast<const uint4 *>(stage) + vfirst;
+                uint4 *gv = reinterpret_cast<uint4 *>(gal) + vfirst;
+                int left_v = nfull - vfirst;  // (a handful of trips: no unrolling, no remainder code)
+#pragma unroll 1
+                for (; left_v > 0; left_v -= 32, sv += 32, gv += 32) *gv = *sv;
+            }
+            if (nfull > 0) head = 0;
+            const int rest = fill & 15;
+            uint8_t keep = 0;
+            if (lane < rest) keep = stage[16 * nfull + lane];
+            __syncwarp();
+            if (nfull > 0 && lane < rest) stage[lane] = keep;
+            __syncwarp();
+            gal += 16 * nfull;
+            fill = rest;
+        };
+        // A row of a tokenised batch -- its head in front of the trailing run is at most two such steps -- goes into the
+        // stage in one piece and is flushed once (the stage holds 2 x (512 + 4 + 5 x 32) bytes and the carry).
+        int64_t c_begin = 0;
+        bool try16 = bytelut;  // (a row whose step did not have the shape stops asking: rows without the hint hold <PAD> runs)
+        if (bytelut && cols <= 1024) {
+            const int h = static_cast<int>(cols);
+            int c = 0, total = 0;
+            while (c < h && step16(c, h - c, total)) {
+                __syncwarp();
+                fill += total;
+                c += 512;
+            }
+            c_begin = min(c, h);
+            try16 = c_begin >= h;
+            if (c_begin > 0) flush();
+        }
+        for (int64_t c0 = c_begin; c0 < cols; c0 += step) {
             step = 128;
             int total;
             bool done = false;
@@ -1520,8 +1644,14 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
             const int64_t left = cols - c0;
             const bool ragged = left < 512 && (left & 15) != 0;
             if (fast && (!ragged || bytelut)) {
+                if (try16 && left < (1ll << 30) && c0 < (1ll << 30) && step16(static_cast<int>(c0), static_cast<int>(min(left, static_cast<int64_t>(512))), total)) {
+                    step = 512;
+                    done = true;
+                } else {
+                    try16 = false;
+                }
+                if (!done && !ragged) {
                 const int nact = static_cast<int>(min(static_cast<int64_t>(32), (left + 15) >> 4));
-                const int nlast = ragged ? static_cast<int>(left & 15) : 16;  // tokens of the last active vector
                 const bool act = lane < nact;
                 uint4 x = make_uint4(0u, 0u, 0u, 0u);
                 if (act) x = *reinterpret_cast<const uint4 *>(rp - ra + c0 + 16 * lane);
@@ -1529,82 +1659,13 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
                     uint4 nx;
                     nx.x = __shfl_down_sync(0xffffffffu, x.x, 1); nx.y = __shfl_down_sync(0xffffffffu, x.y, 1);
                     nx.z = __shfl_down_sync(0xffffffffu, x.z, 1); nx.w = __shfl_down_sync(0xffffffffu, x.w, 1);
-                    if (lane == nact - 1) {  // (the vector behind the last one is read only if the row reaches into it)
+                    if (lane == nact - 1) {
                         nx = make_uint4(0u, 0u, 0u, 0u);
                         if (c0 + 16 * nact < ra + cols_all) nx = *reinterpret_cast<const uint4 *>(rp - ra + c0 + 16 * nact);
                     }
                     x = shift16(x, nx, ra);
                 }
                 const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
-                // The shape of nearly every step of a tokenised batch: plain text, possibly behind ONE special in the
-                // very first position (the BOS that opens a row: one extra word "<BOS" in front, its '>' takes the
-                // first byte of lane 0's first word), possibly with specials in the LAST active vector only (the EOS and
-                // the first <PAD>s in front of the trailing run).  Lanes in front of that vector store four words each;
-                // the last vector's 16 tokens are then laid down byte-wise by 16 lanes.  No scan.
-                if (bytelut) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) w[k] = dec_lut4(lutbase, xs[k]);
-                    const uint32_t spm = (w[0] | w[1] | w[2] | w[3]) & 0x80808080u;
-                    const uint32_t spb = __ballot_sync(0xffffffffu, act && spm != 0);
-                    const bool tail_emit = ragged || ((spb >> (nact - 1)) & 1u) != 0;  // warp-uniform
-                    // (ragged: the EOS sits in the last 16 BYTES of the head, which straddle the last two token vectors)
-                    const int nev = !tail_emit ? 0 : ((ragged && nact > 1) ? 2 : 1);  // vectors laid down byte-wise
-                    const int nwl = nact - nev;                                        // lanes that store whole words
-                    const uint32_t w00 = __shfl_sync(0xffffffffu, w[0], 0);
-                    const int lead = (nwl > 0 && (w00 & 0x80u)) ? 1 : 0;
-                    uint32_t rest = spm;
-                    if (lane == 0) rest = ((w[0] & 0xffffff00u) | w[1] | w[2] | w[3]) & 0x80808080u;
-                    if (!__any_sync(0xffffffffu, lane < nwl && rest != 0)) {
-                        const int r8 = (fill & 3) * 8, kw = fill >> 2;
-                        uint32_t lo = __shfl_up_sync(0xffffffffu, w[3], 1);
-                        uint32_t w0 = w[0];
-                        if (lane == 0) {
-                            lo = r8 ? stage_w[kw] << (32 - r8) : 0u;
-                            if (lead) {
-                                const uint32_t P = special_word(w00);
-                                stage_w[kw] = __funnelshift_l(lo, P, r8);
-                                lo = P;
-                                w0 = (w0 & 0xffffff00u) | 0x3eu;
-                            }
-                        }
-                        uint32_t *d = stage_w + kw + lead + 4 * lane;
-                        if (lane < nwl) {
-                            d[0] = __funnelshift_l(lo, w0, r8);
-                            d[1] = __funnelshift_l(w0, w[1], r8);
-                            d[2] = __funnelshift_l(w[1], w[2], r8);
-                            d[3] = __funnelshift_l(w[2], w[3], r8);
-                            if (lane == nwl - 1 && r8) d[4] = w[3] >> (32 - r8);
-                        }
-                        total = 16 * nwl + 4 * lead;
-                        if (tail_emit) {
-                            __syncwarp();  // (the carry word above covers the first bytes written here)
-                            // lane t owns token t of the last vector(s)
-                            const int q = (lane >> 2) & 3, src = nwl + (lane >> 4);
-                            const uint32_t t0 = __shfl_sync(0xffffffffu, w[0], src), t1 = __shfl_sync(0xffffffffu, w[1], src);
-                            const uint32_t t2 = __shfl_sync(0xffffffffu, w[2], src), t3 = __shfl_sync(0xffffffffu, w[3], src);
-                            const uint32_t tw = q == 0 ? t0 : (q == 1 ? t1 : (q == 2 ? t2 : t3));
-                            const uint32_t c = (tw >> (8 * (lane & 3))) & 0xffu;
-                            const int nem = 16 * (nev - 1) + nlast;  // tokens laid down here
-                            const bool mine = lane < nem;
-                            const uint32_t sm = __ballot_sync(0xffffffffu, mine && (c & 0x80u));
-                            uint8_t *o = stage + fill + total + lane + 4 * __popc(sm & ((1u << lane) - 1u));
-                            if (mine) {
-                                if (c & 0x80u) {
-                                    const int sp = static_cast<int>(c & 3u);
-#pragma unroll
-                                    for (int j = 0; j < 5; ++j) o[j] = special_char(sp, j);
-                                } else {
-                                    *o = static_cast<uint8_t>(c);
-                                }
-                            }
-                            total += nem + 4 * __popc(sm);
-                        }
-                        step = 512;
-                        done = true;
-                    }
-                }
-                if (!done && !ragged) {
                 uint32_t ee[16], any = 0;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
@@ -1721,23 +1782,7 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
             }
             __syncwarp();
             fill += total;
-            const int nfull = fill >> 4;
-            int vfirst = lane;
-            if (head > 0 && nfull > 0) {  // first vector of the row: bytes [0, head) belong to the previous row
-                if (lane >= head && lane < 16) gal[lane] = stage[lane];
-                if (lane == 0) vfirst = 32;
-            }
-            for (int vv = vfirst; vv < nfull; vv += 32)
-                *reinterpret_cast<uint4 *>(gal + 16 * vv) = *reinterpret_cast<const uint4 *>(stage + 16 * vv);
-            if (nfull > 0) head = 0;
-            const int rest = fill & 15;
-            uint8_t keep = 0;
-            if (lane < rest) keep = stage[16 * nfull + lane];
-            __syncwarp();
-            if (nfull > 0 && lane < rest) stage[lane] = keep;
-            __syncwarp();
-            gal += 16 * nfull;
-            fill = rest;
+            flush();
         }
         if (cols < cols_all) {
             // The trailing run: 5 (cols_all - cols) bytes "<PAD><PAD>..." starting at gal[fill].  Period 5 against 16-byte
@@ -1762,14 +1807,17 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
                 const int phl = phase0 + lane5;  // lane5 = lane % 5
                 const uint4 pv = pk[phl >= 5 ? phl - 5 : phl];
                 uint4 *gv = reinterpret_cast<uint4 *>(gal) + lane;
-                int v = lane;
-                for (; v + 90 < nvec; v += 120, gv += 120) {
+                int left_v = nvec - lane;
+#pragma unroll 1
+                for (; left_v > 90; left_v -= 120, gv += 120) {
                     __stcs(gv, pv);
                     __stcs(gv + 30, pv);
                     __stcs(gv + 60, pv);
                     __stcs(gv + 90, pv);
                 }
-                for (; v < nvec; v += 30, gv += 30) __stcs(gv, pv);
+                if (left_v > 0) __stcs(gv, pv);
+                if (left_v > 30) __stcs(gv + 30, pv);
+                if (left_v > 60) __stcs(gv + 60, pv);
             }
             const int rest = left & 15;
             if (lane < rest) gal[16 * static_cast<int64_t>(nvec) + lane] = pat16[k][(phase0 + nvec) % 5][lane];
