@@ -1020,9 +1020,11 @@ __global__ void __launch_bounds__(kDecWarps * 32)
 decode_len16_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t cols, int64_t row_stride, InvParam invp,
                     int64_t *__restrict__ row_len, int32_t *__restrict__ row_tail, unsigned long long *first_bad) {
     __shared__ uint16_t cls[256];
+    __shared__ uint8_t knd[256];  // which special (0 <BOS>, 1 <EOS>, 2 <PAD>)
     for (int i = threadIdx.x; i < 256; i += kDecWarps * 32) {
         const uint16_t e = invp.e[i + 128];
         cls[i] = e == kInvNone ? 0x100 : ((e >> 8) & 1);
+        knd[i] = static_cast<uint8_t>(e & 3u);
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -1073,7 +1075,8 @@ decode_len16_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t co
             for (int o = 16; o > 0; o >>= 1) tail_vec = max(tail_vec, __shfl_xor_sync(0xffffffffu, tail_vec, o));
             // columns [16 tail_vec - a, cols) all hold T; only a special's run is worth a separate path
             const int64_t ts = min(max(static_cast<int64_t>(16) * tail_vec - a, static_cast<int64_t>(0)), cols);
-            if (lane == 0) row_tail[r] = (cls[T] & 1) ? static_cast<int32_t>(ts) : static_cast<int32_t>(cols);
+            if (lane == 0)
+                row_tail[r] = (cls[T] & 1) ? static_cast<int32_t>(static_cast<uint32_t>(ts) | (static_cast<uint32_t>(knd[T]) << 30)) : static_cast<int32_t>(cols);
         }
         if (__any_sync(0xffffffffu, bad != 0)) {
             unsigned long long b = ~0ull;
@@ -1105,9 +1108,11 @@ decode_len16p_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t c
                      int64_t *__restrict__ row_len, int32_t *__restrict__ row_tail, unsigned long long *first_bad,
                      uint32_t thr_lo4, uint32_t thr_hi4) {
     __shared__ uint16_t cls[256];
+    __shared__ uint8_t knd[256];  // which special (0 <BOS>, 1 <EOS>, 2 <PAD>)
     for (int i = threadIdx.x; i < 256; i += kDecWarps * 32) {
         const uint16_t e = invp.e[i + 128];
         cls[i] = e == kInvNone ? 0x100 : ((e >> 8) & 1);
+        knd[i] = static_cast<uint8_t>(e & 3u);
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -1197,7 +1202,8 @@ decode_len16p_kernel(const uint8_t *__restrict__ tokens, int64_t rows, int64_t c
             tail_vec = __reduce_max_sync(0xffffffffu, tail_vec);
             // columns [16 tail_vec - a, cols) all hold T; only a special's run is worth a separate path
             const int64_t ts = min(max(static_cast<int64_t>(16) * tail_vec - a, static_cast<int64_t>(0)), cols);
-            if (lane == 0) row_tail[r] = (clsT & 1) ? static_cast<int32_t>(ts) : static_cast<int32_t>(cols);
+            if (lane == 0)
+                row_tail[r] = (clsT & 1) ? static_cast<int32_t>(static_cast<uint32_t>(ts) | (static_cast<uint32_t>(knd[T]) << 30)) : static_cast<int32_t>(cols);
         }
         if (__reduce_or_sync(0xffffffffu, bad) != 0) {
             unsigned long long b = ~0ull;
@@ -1268,6 +1274,36 @@ scan_totals_kernel(int64_t *__restrict__ block_tot, int64_t nblocks, int64_t *__
         __syncthreads();
     }
     if (threadIdx.x == 0) *grand_total = carry;
+}
+
+// The second and third step in one for up to a few thousand blocks: every block sums the totals of the blocks in front
+// of it itself (nblocks loads spread over its threads) instead of waiting for a one-block scan of the totals.
+__global__ void __launch_bounds__(kScanBlock)
+scan_add_direct_kernel(int64_t *__restrict__ data, int64_t n, const int64_t *__restrict__ block_tot, const int64_t *__restrict__ first_bad,
+                       int64_t *__restrict__ host_out) {
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_pre;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t part = 0;
+    for (int64_t j = threadIdx.x; j < blockIdx.x; j += kScanBlock) part += block_tot[j];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_warp[warp] = part;
+    __syncthreads();
+    if (warp == 0) {
+        int64_t v = s_warp[lane];  // (kScanBlock / 32 = 32 warps)
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) s_pre = v;
+    }
+    __syncthreads();
+    const int64_t pre = s_pre;
+    const int64_t i = static_cast<int64_t>(blockIdx.x) * kScanBlock + threadIdx.x;
+    if (i < n) data[i] += pre;
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {
+        const int64_t total = pre + block_tot[blockIdx.x];
+        data[n] = total;
+        host_out[0] = *first_bad;
+        host_out[1] = total;
+    }
 }
 
 // (host_out: two words of pinned host memory the caller polls after its stream synchronize -- {first bad token, total}
@@ -1487,11 +1523,15 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
     };
     if (STAGED && gw < rows) fetch_row(gw, 0);
     int64_t off_next = gw < rows ? row_offs[gw] : 0;
+    // (row_tail[r]: where the row's trailing run starts, with the run's kind -- <BOS> <EOS> <PAD> -- in bits 30..31)
+    int32_t tail_next = (row_tail != nullptr && gw < rows) ? row_tail[gw] : 0;
     uint32_t it = 0;
     for (int64_t r = gw; r < rows; r += GW, ++it) {
         const int64_t off_r = off_next;
-        if (r + GW < rows) {  // the next row's output offset and tokens: in flight while this row is decoded
+        const int32_t tail_r = tail_next;
+        if (r + GW < rows) {  // the next row's output offset, hint and tokens: in flight while this row is decoded
             off_next = row_offs[r + GW];
+            if (row_tail != nullptr) tail_next = row_tail[r + GW];
             if (STAGED) fetch_row(r + GW, (it + 1) & 1);
         }
         const uint8_t *gp = tokens + r * row_stride;
@@ -1505,7 +1545,7 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
         int step = 128;
         // columns [cols_head, cols) are one repeated special (found by pass 1): written below as a pattern fill
         const int64_t cols_all = cols;
-        const int64_t cols = row_tail != nullptr ? static_cast<int64_t>(row_tail[r]) : cols_all;
+        const int64_t cols = row_tail != nullptr ? static_cast<int64_t>(tail_r & 0x3fffffff) : cols_all;
         // One 16-tokens-per-lane step in its byte-table form (tokens [c0, c0 + min(left, 512)) of the row, appended to the
         // stage at `fill`): false = the step does not have the shape this form handles, nothing was written.
         auto step16 = [&](int c0, int left, int &total) -> bool {
@@ -1788,7 +1828,7 @@ decode_chars_kernel(const uint8_t *__restrict__ tokens, int itemsize, int64_t ro
             // The trailing run: 5 (cols_all - cols) bytes "<PAD><PAD>..." starting at gal[fill].  Period 5 against 16-byte
             // vectors: vector v of the run starts at phase (phase0 + v) % 5 (16 = 1 mod 5) -- one LDS.128 of the pattern
             // table and one st.global.v4 per 16 bytes, no token is read, nothing goes through the stage.
-            const int k = static_cast<int>(inv[rp[cols_all - 1] + 128] & 3u);
+            const int k = static_cast<int>(static_cast<uint32_t>(tail_r) >> 30);  // (only rows with a hint get here)
             const int run = 5 * static_cast<int>(cols_all - cols);  // (cols <= 2^28 on this path)
             int done = 0;  // bytes of the run written so far
             if (fill > 0 || head > 0) {  // the vector that holds the staged bytes [head, fill): completed with the run's first bytes
@@ -2280,8 +2320,6 @@ int decode_lengths_enqueue(int device, cudaStream_t st, const void *d_tokens, in
             static_cast<const uint8_t *>(d_tokens), itemsize, rows, cols, row_stride, col_stride, fast, inv, d_row_offsets,
             reinterpret_cast<unsigned long long *>(d_work));
     }
-    scan_local_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2);
-    scan_totals_kernel<<<1, kScanBlock, 0, st>>>(d_work + 2, nblocks, d_work + 1);
     // one pinned result slot per host thread (the calls are synchronous)
     // (16 bytes, never freed: a destructor would run at thread exit, possibly after the CUDA runtime is torn down)
     struct PinnedPair {
@@ -2290,6 +2328,14 @@ int decode_lengths_enqueue(int device, cudaStream_t st, const void *d_tokens, in
     static thread_local PinnedPair pinned;
     if (pinned.p == nullptr) BSQ_CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&pinned.p), 2 * sizeof(int64_t), cudaHostAllocPortable));
     *host_pair = pinned.p;
+    scan_local_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2);
+    if (nblocks <= 4096) {  // (up to 4 M rows: two kernels instead of three)
+        scan_add_direct_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2, d_work, pinned.p);
+        count_launch(3);
+        BSQ_CUDA_TRY(cudaGetLastError());
+        return BSQ_OK;
+    }
+    scan_totals_kernel<<<1, kScanBlock, 0, st>>>(d_work + 2, nblocks, d_work + 1);
     scan_add_kernel<<<static_cast<unsigned>(nblocks), kScanBlock, 0, st>>>(d_row_offsets, rows, d_work + 2, d_work + 1, d_work, pinned.p);
     count_launch(4);
     BSQ_CUDA_TRY(cudaGetLastError());
