@@ -301,7 +301,8 @@ class FlatFile:
 
     def __init__(self, path, maxseqlen=-1, pinned=False, prefault=False):
         self.h = C.c_void_p()
-        mode = 1 if pinned else (2 if prefault else 0)   # BSQ_FF_PINNED / BSQ_FF_MMAP_PREFAULT / BSQ_FF_MMAP
+        # BSQ_FF_PINNED / BSQ_FF_MMAP_REGISTERED (prefault=2: populated and page-locked in place) / BSQ_FF_MMAP_PREFAULT / BSQ_FF_MMAP
+        mode = 1 if pinned else (3 if int(prefault) >= 2 else (2 if prefault else 0))
         check(lib().bsq_flatfile_open(C.byref(self.h), os.fsencode(path), maxseqlen, mode))
 
     @staticmethod
@@ -316,6 +317,9 @@ class FlatFile:
     def maxseqlen(self): return lib().bsq_flatfile_max_seq_len(self.h)
     @property
     def bytes_ptr(self): return lib().bsq_flatfile_bytes(self.h)
+
+    @property
+    def pinned(self): return bool(lib().bsq_flatfile_is_pinned(self.h))
     @property
     def offsets_ptr(self): return lib().bsq_flatfile_offsets(self.h)
 

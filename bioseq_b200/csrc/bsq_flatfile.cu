@@ -168,7 +168,8 @@ int bsq_flatfile_make(const char *inpath, const char *outpath, int64_t *nseqs, i
 
 int bsq_flatfile_open(bsq_flatfile **outp, const char *path, int64_t maxseqlen, int mode) {
     if (outp == nullptr || path == nullptr) return fail(BSQ_ERR_ARG, "null argument");
-    if (mode != BSQ_FF_MMAP && mode != BSQ_FF_PINNED && mode != BSQ_FF_MMAP_PREFAULT) return fail(BSQ_ERR_ARG, "bad FlatFile mode");
+    if (mode != BSQ_FF_MMAP && mode != BSQ_FF_PINNED && mode != BSQ_FF_MMAP_PREFAULT && mode != BSQ_FF_MMAP_REGISTERED)
+        return fail(BSQ_ERR_ARG, "bad FlatFile mode");
     const int fd = ::open(path, O_RDONLY);
     if (fd < 0) return fail(BSQ_ERR_IO, std::strerror(errno));  // the reference surfaces mio's system_error text
     struct stat sb;
@@ -183,16 +184,42 @@ int bsq_flatfile_open(bsq_flatfile **outp, const char *path, int64_t maxseqlen, 
         return fail(BSQ_ERR_IO, std::string(path) + ": not a FlatFile (shorter than its header)");
     }
     uint8_t *base = nullptr;
-    if (mode == BSQ_FF_MMAP || mode == BSQ_FF_MMAP_PREFAULT) {
+    bool registered = false;
+    if (mode != BSQ_FF_PINNED) {
         int flags = MAP_SHARED;
 #ifdef MAP_POPULATE
-        if (mode == BSQ_FF_MMAP_PREFAULT) flags |= MAP_POPULATE;  // page tables filled now, not fault by fault under the first pass
+        if (mode != BSQ_FF_MMAP) flags |= MAP_POPULATE;  // page tables filled now, not fault by fault under the first pass
 #endif
         void *m = ::mmap(nullptr, size, PROT_READ, flags, fd, 0);
         const int e = errno;
         ::close(fd);
         if (m == MAP_FAILED) return fail(BSQ_ERR_IO, std::strerror(e));
         base = static_cast<uint8_t *>(m);
+        if (mode == BSQ_FF_MMAP_REGISTERED) {
+            // page-lock the mapping where it lies: the DMA engine then reads the page cache directly
+            registered = cudaHostRegister(base, size, cudaHostRegisterPortable | cudaHostRegisterReadOnly) == cudaSuccess;
+            if (!registered) {
+                // Platforms without read-only registration pin pages for writing, which a PROT_READ mapping refuses:
+                // map the file shared and writable instead (nothing is ever written through it) when it may be.
+                cudaGetLastError();
+                const int wfd = ::open(path, O_RDWR);
+                if (wfd >= 0) {
+                    void *mw = ::mmap(nullptr, size, PROT_READ | PROT_WRITE, flags, wfd, 0);
+                    ::close(wfd);
+                    if (mw != MAP_FAILED) {
+                        if (cudaHostRegister(mw, size, cudaHostRegisterPortable) == cudaSuccess) {
+                            ::munmap(base, size);
+                            base = static_cast<uint8_t *>(mw);
+                            registered = true;
+                        } else {
+                            cudaGetLastError();
+                            ::munmap(mw, size);
+                        }
+                    }
+                }
+            }
+            if (!registered) mode = BSQ_FF_MMAP_PREFAULT;  // (not an error: the file stays a prefaulted pageable mapping)
+        }
     } else {
         // +32: the kernels' host-side staging copies whole ranges; keep a readable tail like the pack layer
         cudaError_t ce = cudaHostAlloc(reinterpret_cast<void **>(&base), size + 32, cudaHostAllocPortable);
@@ -215,6 +242,7 @@ int bsq_flatfile_open(bsq_flatfile **outp, const char *path, int64_t maxseqlen, 
         ::close(fd);
     }
     auto release = [&]() {
+        if (registered) cudaHostUnregister(base);
         if (mode != BSQ_FF_PINNED) ::munmap(base, size);
         else cudaFreeHost(base);
     };
@@ -253,6 +281,7 @@ int bsq_flatfile_open(bsq_flatfile **outp, const char *path, int64_t maxseqlen, 
 void bsq_flatfile_close(bsq_flatfile *f) {
     if (f == nullptr) return;
     if (f->base != nullptr) {
+        if (f->mode == BSQ_FF_MMAP_REGISTERED) cudaHostUnregister(f->base);
         if (f->mode != BSQ_FF_PINNED) ::munmap(f->base, f->size);
         else cudaFreeHost(f->base);
     }
@@ -264,7 +293,7 @@ int64_t bsq_flatfile_seq_offset(const bsq_flatfile *f) { return f ? f->seq_offse
 int64_t bsq_flatfile_max_seq_len(const bsq_flatfile *f) { return f ? f->max_seq_len : 0; }
 const int64_t *bsq_flatfile_offsets(const bsq_flatfile *f) { return f ? reinterpret_cast<const int64_t *>(f->base + 8) : nullptr; }
 const uint8_t *bsq_flatfile_bytes(const bsq_flatfile *f) { return f ? f->base + f->seq_offset : nullptr; }
-int bsq_flatfile_is_pinned(const bsq_flatfile *f) { return f && f->mode == BSQ_FF_PINNED; }
+int bsq_flatfile_is_pinned(const bsq_flatfile *f) { return f && (f->mode == BSQ_FF_PINNED || f->mode == BSQ_FF_MMAP_REGISTERED); }
 
 int bsq_fastx_lengths(const char *path, int64_t **lens, int64_t *n) {
     if (path == nullptr || lens == nullptr || n == nullptr) return fail(BSQ_ERR_ARG, "null argument");

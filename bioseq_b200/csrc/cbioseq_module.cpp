@@ -289,11 +289,14 @@ ArrayArg array_arg(const py::object &obj, const char *what, int itemsize, const 
 // per sequence).
 class FlatFile {
 public:
-    static int mode_of(bool pinned, bool prefault) { return pinned ? BSQ_FF_PINNED : (prefault ? BSQ_FF_MMAP_PREFAULT : BSQ_FF_MMAP); }
-    FlatFile(const std::string &path, py::ssize_t maxseqlen, bool pinned, bool prefault) : path_(path) {
+    // prefault: 0 / False plain mapping, 1 / True populated at open, 2 populated AND page-locked in place (direct DMA)
+    static int mode_of(bool pinned, int prefault) {
+        return pinned ? BSQ_FF_PINNED : (prefault >= 2 ? BSQ_FF_MMAP_REGISTERED : (prefault ? BSQ_FF_MMAP_PREFAULT : BSQ_FF_MMAP));
+    }
+    FlatFile(const std::string &path, py::ssize_t maxseqlen, bool pinned, int prefault) : path_(path) {
         check(bsq_flatfile_open(&f_, path.c_str(), maxseqlen, mode_of(pinned, prefault)));
     }
-    FlatFile(const std::string &inpath, const std::string &outpath, bool pinned, bool prefault)
+    FlatFile(const std::string &inpath, const std::string &outpath, bool pinned, int prefault)
         : path_(outpath.empty() ? inpath + ".ff" : outpath) {
         int64_t n = 0, longest = 0;
         check(bsq_flatfile_make(inpath.c_str(), outpath.c_str(), &n, &longest));
@@ -922,9 +925,9 @@ PYBIND11_MODULE(cbioseq, m) {
 
     py::class_<FlatFile>(m, "FlatFile")
         .def(py::init<std::string, py::ssize_t, bool, bool>(), py::arg("inputfile"), py::arg("maxseqlen") = -1, py::kw_only(),
-             py::arg("pinned") = false, py::arg("prefault") = false)
+             py::arg("pinned") = false, py::arg("prefault") = 0)
         .def(py::init<std::string, std::string, bool, bool>(), py::arg("inputfile"), py::arg("outputfile"), py::kw_only(),
-             py::arg("pinned") = false, py::arg("prefault") = false)
+             py::arg("pinned") = false, py::arg("prefault") = 0)
         .def_property_readonly("path", &FlatFile::path)
         .def("access", &FlatFile::access)
         .def("access", &FlatFile::slice_access)

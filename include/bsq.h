@@ -331,6 +331,11 @@ typedef struct bsq_flatfile bsq_flatfile;
 #define BSQ_FF_PINNED 1 /* read the file into cudaHostAlloc'ed memory once (direct DMA afterwards) */
 #define BSQ_FF_MMAP_PREFAULT 2 /* BSQ_FF_MMAP with the page tables populated at open (MAP_POPULATE): a streamed first
                                   pass over a page-cache-resident file then runs at copy speed instead of fault speed */
+#define BSQ_FF_MMAP_REGISTERED 3 /* BSQ_FF_MMAP_PREFAULT, and the mapping is page-locked IN PLACE (cudaHostRegister):
+                                    ranges go to the device by direct DMA like BSQ_FF_PINNED, without a second copy of
+                                    the file in memory.  Registered read-only where the platform can; else through a
+                                    shared writable mapping of the file (never written) when the file may be opened for
+                                    writing; else the file stays BSQ_FF_MMAP_PREFAULT (bsq_flatfile_is_pinned tells). */
 
 /* FlatFile::make (src/fxstats.cpp:33-64): parse a FASTA/FASTQ file (plain or gzip; kseq.h
  * record rules) and write the flat file.  outpath NULL or "" -> inpath + ".ff".  Returns the

@@ -213,6 +213,30 @@ def test_pyviewff(tmp_path):
 
 
 @pytest.mark.gpu
+def test_gpu_flatfile_open_modes_give_the_same_tokens(tmp_path):
+    # plain mapping, prefaulted mapping, mapping page-locked in place (cudaHostRegister; falls back to prefaulted where
+    # the platform cannot register file pages) and the pinned copy: same tokens, and `pinned` tells which path was taken
+    import torch
+    import bioseq_b200
+    src, seqs = _protein_file(tmp_path, n=900, hi=300, seed=9)
+    cbioseq.FlatFile(src, str(tmp_path / "m.ff"))
+    tok = bioseq_b200.pbeos_tokenizers["PROTEIN"]
+    outs = []
+    for kw in (dict(), dict(prefault=1), dict(prefault=2), dict(pinned=True)):
+        ff = cbioseq.FlatFile(str(tmp_path / "m.ff"), **kw)
+        assert ff.nseqs() == 900
+        if kw.get("pinned"):
+            assert ff.pinned
+        if not kw or kw.get("prefault") == 1:
+            assert not ff.pinned
+        outs.append(tok.batch_tokenize_flatfile(ff, 0, None, batch_first=True, destchar="B"))
+        assert [bytes(b) for b in ff[3:6]] == seqs[3:6]
+        del ff
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+
+
+@pytest.mark.gpu
 def test_gpu_loaders(tmp_path):
     import torch
     import bioseq_b200
