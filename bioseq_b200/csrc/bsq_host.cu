@@ -46,29 +46,21 @@ using bsq::fail;
 
 // ---------------------------------------------------------------------------------------
 // worker pool: persistent host threads for the gather (items -> pinned pack) and scatter
-// (pinned ring -> Python string bodies) loops.  One job at a time; the submitting thread keeps
-// running (it issues the CUDA copies and launches) and joins with wait().
+// (pinned ring -> Python string bodies) loops.  The submitting thread keeps running (it issues the CUDA
+// copies and launches) and joins with wait().  A team of threads runs one job at a time; callers that
+// arrive while a team is busy (other Python threads, other devices) get another team -- up to kTeams --
+// instead of queueing behind it.
 // ---------------------------------------------------------------------------------------
 namespace {
 
 thread_local bool t_in_pool_worker = false;  // set on pool threads: a nested parallel section runs inline instead
 
-class Pool {
+class Team {
 public:
-    static Pool &get() {
-        // leaked: worker threads must not be torn down under a running job at exit.  After fork() the child has
-        // none of the parent's threads, so it starts over with an empty pool (a forked DataLoader worker that only
-        // walks items would otherwise wait for workers that do not exist).
-        static std::once_flag once;
-        std::call_once(once, [] {
-            instance() = new Pool();
-            pthread_atfork(nullptr, nullptr, [] { instance() = new Pool(); });
-        });
-        return *instance();
-    }
-    // run fn(t) for t in [0, nt) on pool threads; returns at once.  Pair with wait().
+    bool try_claim() { return job_mu_.try_lock(); }
+    void claim() { job_mu_.lock(); }
+    // run fn(t) for t in [0, nt) on the team's threads; returns at once.  The team is claimed; wait() releases it.
     void start(int nt, std::function<void(int)> fn) {
-        job_mu_.lock();  // released by wait()
         std::unique_lock<std::mutex> lk(mu_);
         while (static_cast<int>(threads_.size()) < nt) {
             const int id = static_cast<int>(threads_.size());
@@ -91,10 +83,6 @@ public:
     }
 
 private:
-    static Pool *&instance() {
-        static Pool *p = nullptr;
-        return p;
-    }
     void loop(int id) {
         uint64_t seen = 0;
         for (;;) {
@@ -119,6 +107,51 @@ private:
     std::function<void(int)> fn_;
     int nt_ = 0, pending_ = 0;
     uint64_t generation_ = 0;
+};
+
+class Pool {
+public:
+    static constexpr int kTeams = 4;
+    static Pool &get() {
+        // leaked: worker threads must not be torn down under a running job at exit.  After fork() the child has
+        // none of the parent's threads, so it starts over with empty teams (a forked DataLoader worker that only
+        // walks items would otherwise wait for workers that do not exist).
+        static std::once_flag once;
+        std::call_once(once, [] {
+            instance() = new Pool();
+            pthread_atfork(nullptr, nullptr, [] { instance() = new Pool(); });
+        });
+        return *instance();
+    }
+    // run fn(t) for t in [0, nt) on a free team (the first team when all are busy: queue there); returns at once.
+    // Pair with wait() on the same thread.
+    void start(int nt, std::function<void(int)> fn) {
+        Team *team = nullptr;
+        for (int k = 0; k < kTeams && team == nullptr; ++k)
+            if (teams_[k].try_claim()) team = &teams_[k];
+        if (team == nullptr) {
+            team = &teams_[0];
+            team->claim();
+        }
+        mine() = team;
+        team->start(nt, std::move(fn));
+    }
+    void wait() {
+        Team *team = mine();
+        mine() = nullptr;
+        if (team != nullptr) team->wait();
+    }
+
+private:
+    static Pool *&instance() {
+        static Pool *p = nullptr;
+        return p;
+    }
+    static Team *&mine() {  // the team this thread's job in flight runs on
+        static thread_local Team *t = nullptr;
+        return t;
+    }
+    Team teams_[kTeams];
 };
 
 // Pool threads worth using for a memory-bound host loop: the caller's wish, capped at three quarters of the CPUs
