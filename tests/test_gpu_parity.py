@@ -796,3 +796,26 @@ def test_python_decode_text_guess_overflow_falls_back_to_exact_pass():
     assert sum(map(len, want)) > 3 * rows * cols
     assert t.decode_tokens(torch.from_numpy(a).cuda()) == want
     assert t.decode_tokens(a) == want
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_mid_size_batches_span_kernel_and_decode(seed):
+    # the regime of the headline kernel (padlen >= 257: tokenize_span_kernel, several tiles, rows that straddle tiles and
+    # warps) and of the staged decode: random padlens (16-byte aligned or not), row counts, length distributions with
+    # empty and full rows, every flag combination -- tokens against the oracle, text against the oracle's decode
+    rng = np.random.default_rng(9100 + seed)
+    for trial in range(4):
+        key = ("PROTEIN", "DNA", "DAYHOFF", "BYTES")[int(rng.integers(4))]
+        flags = dict(bos=bool(rng.integers(2)), eos=bool(rng.integers(2)), padchar=bool(rng.integers(2)))
+        padlen = int(rng.choice([257, 272, 511, 512, 513, 652, 656, 1000, 1024, 1026, 1500, 2048, 2999]))
+        n = int(rng.choice([1, 7, 64, 500, 1777, 3000]))
+        room = padlen - flags["bos"] - flags["eos"]
+        shape = int(rng.integers(4))
+        lo, hi = ((0, room), (room, room), (0, min(room, 40)), (max(0, room - 20), room))[shape]
+        buf, offs = gen(int(rng.integers(1 << 30)), n, lo, hi, MIX)
+        tok, orc = capi.tokenizer(key, **flags), OracleTokenizer(key, **flags)
+        want = orc.batch_tokenize((buf, offs), padlen=padlen, destchar="B", batch_first=True)
+        got = abi_tokenize(tok, buf, offs, padlen, True, "B")
+        assert_same_bits(want, got.cpu().numpy())
+        if key != "BYTES":
+            assert abi_decode(tok, got) == orc.decode_tokens(want)
