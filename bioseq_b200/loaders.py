@@ -125,10 +125,43 @@ class FlatFileDataset(_dataset_base()):
             slc = slice(slc, stop, step)
         return self[slc]
 
-    def batches(self, batch_size):
-        """Consecutive ``(batch, max_seq_len)`` token batches covering the file."""
+    def batches(self, batch_size, prefetch=0):
+        """Consecutive ``(batch, max_seq_len)`` token batches covering the file.
+
+        ``prefetch=k`` (k > 0) keeps k batches ahead of the consumer on a side stream: the host-to-device copy and the
+        tokeniser of batch i+1 .. i+k run while the caller's stream is still busy with batch i (the reference's
+        training loops, training/cnnpretrain.py:119-128, tokenise on the CPU between optimizer steps).  Every yielded
+        tensor is ready on the caller's current stream."""
+        if prefetch <= 0:
+            for start in range(0, len(self), batch_size):
+                yield self[start:start + batch_size]
+            return
+        import collections
+        import torch
+        dev = torch.device("cuda", torch.cuda.current_device()) if self.device is None else torch.device(self.device)
+        if dev.type != "cuda":
+            raise ValueError("FlatFileDataset.batches(prefetch=...): a CUDA device is needed")
+        side = torch.cuda.Stream(device=dev)
+        ahead = collections.deque()
+
+        def hand_over(item):
+            t, ev = item
+            cur = torch.cuda.current_stream(dev)
+            cur.wait_event(ev)
+            t.record_stream(cur)  # (allocated on the side stream, used on the caller's)
+            return t
+
         for start in range(0, len(self), batch_size):
-            yield self[start:start + batch_size]
+            side.wait_stream(torch.cuda.current_stream(dev))  # nothing the caller enqueued so far is overtaken
+            with torch.cuda.stream(side):
+                t = self[start:start + batch_size]
+                ev = torch.cuda.Event()
+                ev.record(side)
+            ahead.append((t, ev))
+            if len(ahead) > prefetch:
+                yield hand_over(ahead.popleft())
+        while ahead:
+            yield hand_over(ahead.popleft())
 
     def __len__(self):
         return self.ff.nseqs()

@@ -256,6 +256,9 @@ def test_gpu_loaders(tmp_path):
     assert np.array_equal(ds[-1].cpu().numpy(), want[-1])
     assert np.array_equal(ds[10:300].cpu().numpy(), want[10:300])
     assert np.array_equal(torch.cat(list(ds.batches(128))).cpu().numpy(), want)
+    # ... with the next two batches tokenised on a side stream while this one is consumed
+    got = [b.clone() for b in ds.batches(100, prefetch=2)]
+    assert len(got) == 7 and np.array_equal(torch.cat(got).cpu().numpy(), want)
     cnn = FlatFileDataset(ff, tok, cnn=True)
     oh = ora.batch_onehot_encode(pack(seqs[5:9]), padlen=P, destchar="f")        # (P, 4, C)
     got = cnn[5:9]
