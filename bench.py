@@ -405,11 +405,11 @@ def run_ours(args):
     if "e2e" in sections:
         for i in range(2 * ROT):   # every set goes through the link once before timing
             e2e_step(i)
-        e2e_s, e2e_repeats, out = timed_region(e2e_step, e2e_steps, 3)
+        e2e_s, e2e_repeats, out = timed_region(e2e_step, e2e_steps, 5)
         e2e_ok = bool(torch.equal(out, sets[(e2e_steps - 1) % ROT]["out"]))
         for i in range(2 * ROT):
             e2e_packed_step(i)
-        packed_s, packed_repeats, out = timed_region(e2e_packed_step, e2e_steps, 3)
+        packed_s, packed_repeats, out = timed_region(e2e_packed_step, e2e_steps, 5)
         packed_ok = bool(torch.equal(out, sets[(e2e_steps - 1) % ROT]["out"]))
         del out
     barrier()
