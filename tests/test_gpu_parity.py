@@ -819,3 +819,25 @@ def test_random_mid_size_batches_span_kernel_and_decode(seed):
         assert_same_bits(want, got.cpu().numpy())
         if key != "BYTES":
             assert abi_decode(tok, got) == orc.decode_tokens(want)
+
+
+def test_span_kernel_on_concurrent_streams():
+    # the span kernel's dynamic tile scheduler keeps its counters per stream (two slots, alternating): launches that
+    # run concurrently on several streams, back to back on each, must not disturb one another
+    tok = capi.tokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    orc = OracleTokenizer("PROTEIN", bos=True, eos=True, padchar=True)
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    work = []
+    for k, (n, padlen) in enumerate(((3000, 1024), (2500, 1026), (4000, 652), (1500, 2048))):
+        buf, offs = gen(7700 + k, n, 0, padlen - 2, MIX)
+        want = orc.batch_tokenize((buf, offs), padlen=padlen, destchar="B", batch_first=True)
+        work.append((torch.from_numpy(buf).cuda(), torch.from_numpy(offs).cuda(), n, padlen, want,
+                     [torch.zeros((n, padlen), dtype=torch.uint8, device="cuda") for _ in range(6)]))
+    torch.cuda.synchronize()
+    for rep in range(6):
+        for s, (d_b, d_o, n, padlen, _, outs) in zip(streams, work):
+            capi.tokenize(0, s.cuda_stream, d_b, d_o, n, padlen, tok, True, 0, outs[rep])
+    torch.cuda.synchronize()
+    for d_b, d_o, n, padlen, want, outs in work:
+        for o in outs:
+            assert_same_bits(want, o.cpu().numpy())
