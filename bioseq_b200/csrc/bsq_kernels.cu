@@ -10,8 +10,13 @@
 //                           row is written with one 4/8/16-byte store when C*sizeof(T) allows,
 //                           else the run is zero-filled with 16-byte stores and the ones are
 //                           scattered after a barrier (no separate memset pass).
-//   K4 decode_*             tokens -> characters (two passes: lengths+validation, chars).
-//   K0 maxlen_kernel        length validation for device-resident offsets.
+//   K2t seqfirst_tok8_kernel  the instruction-lean form of K2 for one-byte tokens (what batch_first=False runs).
+//   K4 decode_*             tokens -> characters: pass 1 decode_len16p_kernel (lengths, validation, where each row's
+//                           trailing <PAD> run starts) + scan, pass 2 decode_chars_kernel (text); bsq_decode_text
+//                           enqueues both behind one another.
+//   K0 maxlen_kernel        length and offsets validation for device-resident packed input.
+//   (K1s, the batch-first one-byte kernel for padlen >= 257 -- the headline path -- lives in bsq_span.cu;
+//    K1r tokenize_rows_ring_kernel below is its predecessor, kept behind BSQ_SPAN=0 for A/B runs.)
 //
 // Reference semantics: src/tokenize.h:381-485 (K1/K2), :283-371 (K3), :131-179 (K4).
 #include <cuda_runtime.h>
